@@ -1,0 +1,428 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference FAcodec
+encoder -> quantizer -> decoder forward, written as plain functions over the
+reference's ``state_dict`` (no nn.Module, no audiotools / munch / argbind).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` leg may import this file; the product (``facodec_b200``)
+never does.
+
+Pinning: the reference ships no tests or golden vectors.
+This restatement is pinned by (a) ``tests/test_oracle_vs_reference.py`` which,
+inside the build container, runs the *imported unmodified reference*
+(``oracle/ref_import.py``) and requires bit-identical tensors, and (b) the
+fixtures under ``tests/golden/`` produced by ``oracle/make_golden.py`` from the
+imported reference, which the restatement must reproduce bit-for-bit on any box.
+
+It is fp32 torch-functional code because the reference *is* fp32 ATen code; the
+same ATen kernels give the same bits.  Every function cites the reference
+lines it follows (paths relative to the reference root).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+HOP = 300
+
+
+# ----------------------------------------------------------------------------
+# dac/model/encodec.py
+# ----------------------------------------------------------------------------
+def _wn_weight(sd, prefix):
+    """Legacy torch.nn.utils.weight_norm (encodec.py:42-51): w = g * v / ||v||, norm over all
+    dims but 0 (for ConvTranspose1d dim 0 is in-channels)."""
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"]
+    return torch._weight_norm(sd[prefix + ".weight_v"], sd[prefix + ".weight_g"], 0)
+
+
+def _extra_padding(length, kernel_size, stride, padding_total):
+    """encodec.py:71-78 get_extra_padding_for_conv1d."""
+    n_frames = (length - kernel_size + padding_total) / stride + 1
+    ideal_length = (math.ceil(n_frames) - 1) * stride + (kernel_size - padding_total)
+    return ideal_length - length
+
+
+def _pad1d_reflect(x, left, right):
+    """encodec.py:96-113 pad1d(mode='reflect') incl. the short-input zero-extension."""
+    length = x.shape[-1]
+    max_pad = max(left, right)
+    extra = 0
+    if length <= max_pad:
+        extra = max_pad - length + 1
+        x = F.pad(x, (0, extra))
+    padded = F.pad(x, (left, right), "reflect")
+    end = padded.shape[-1] - extra
+    return padded[..., :end]
+
+
+def sconv1d(x, sd, prefix, stride=1, dilation=1, causal=True):
+    """SConv1d.forward, encodec.py:212-228 (pad_mode='reflect'). ``prefix`` is the nn.Conv1d
+    (``...conv.conv``)."""
+    w = _wn_weight(sd, prefix)
+    k = w.shape[-1]
+    k_eff = (k - 1) * dilation + 1
+    padding_total = k_eff - stride
+    extra = _extra_padding(x.shape[-1], k_eff, stride, padding_total)
+    if causal:
+        x = _pad1d_reflect(x, padding_total, extra)
+    else:
+        pr = padding_total // 2
+        pl = padding_total - pr
+        x = _pad1d_reflect(x, pl, pr + extra)
+    return F.conv1d(x, w, sd[prefix + ".bias"], stride=stride, dilation=dilation)
+
+
+def sconvtr1d(x, sd, prefix, stride, causal=True):
+    """SConvTranspose1d.forward, encodec.py:248-270, trim_right_ratio=1."""
+    w = _wn_weight(sd, prefix)
+    k = w.shape[-1]
+    padding_total = k - stride
+    y = F.conv_transpose1d(x, w, sd[prefix + ".bias"], stride=stride)
+    if causal:
+        pr = math.ceil(padding_total * 1.0)
+        pl = padding_total - pr
+    else:
+        pr = padding_total // 2
+        pl = padding_total - pr
+    return y[..., pl: y.shape[-1] - pr]
+
+
+def slstm(x, sd, prefix, num_layers=2):
+    """SLSTM.forward, encodec.py:282-288: [B,C,T] -> [T,B,C] -> nn.LSTM(C,C,num_layers), zero
+    state, + skip."""
+    x = x.permute(2, 0, 1)
+    B, H = x.shape[1], x.shape[2]
+    flat = []
+    for l in range(num_layers):
+        flat += [sd[f"{prefix}.weight_ih_l{l}"], sd[f"{prefix}.weight_hh_l{l}"],
+                 sd[f"{prefix}.bias_ih_l{l}"], sd[f"{prefix}.bias_hh_l{l}"]]
+    h0 = torch.zeros(num_layers, B, H, dtype=x.dtype)
+    y, _, _ = torch._VF.lstm(x, (h0, h0.clone()), flat, True, num_layers, 0.0, False, False, False)
+    y = y + x
+    return y.permute(1, 2, 0)
+
+
+# ----------------------------------------------------------------------------
+# dac/nn/layers.py, dac/model/dac.py
+# ----------------------------------------------------------------------------
+def snake(x, alpha):
+    """dac/nn/layers.py:17-24."""
+    return x + (alpha + 1e-9).reciprocal() * torch.sin(alpha * x).pow(2)
+
+
+def residual_unit(x, sd, prefix, dilation, causal=True):
+    """ResidualUnit, dac.py:25-42 (crop branch dead: same length)."""
+    y = snake(x, sd[prefix + ".block.0.alpha"])
+    y = sconv1d(y, sd, prefix + ".block.1.conv.conv", dilation=dilation, causal=causal)
+    y = snake(y, sd[prefix + ".block.2.alpha"])
+    y = sconv1d(y, sd, prefix + ".block.3.conv.conv", causal=causal)
+    return x + y
+
+
+def encoder_forward(sd, x, rates=(2, 5, 5, 6), taps=None):
+    """Encoder.forward, dac.py:69-104. x [B,1,T] -> z [B,1024,ceil(T/300)]."""
+    h = sconv1d(x, sd, "block.0.conv.conv")
+    if taps is not None:
+        taps["enc_conv0"] = h
+    for i, s in enumerate(rates):
+        p = f"block.{i + 1}"
+        for j, d in enumerate((1, 3, 9)):
+            h = residual_unit(h, sd, f"{p}.block.{j}", d)
+        h = snake(h, sd[f"{p}.block.3.alpha"])
+        h = sconv1d(h, sd, f"{p}.block.4.conv.conv", stride=s)
+        if taps is not None:
+            taps[f"enc_block{i + 1}"] = h
+    n = len(rates)
+    h = slstm(h, sd, f"block.{n + 1}.lstm")
+    if taps is not None:
+        taps["enc_lstm"] = h
+    h = snake(h, sd[f"block.{n + 2}.alpha"])
+    return sconv1d(h, sd, f"block.{n + 3}.conv.conv")
+
+
+def decoder_forward(sd, z, rates=(6, 5, 5, 2), taps=None):
+    """Decoder.forward, dac.py:131-165. z [B,1024,T'] -> y [B,1,300 T']."""
+    h = sconv1d(z, sd, "model.0.conv.conv")
+    if taps is not None:
+        taps["dec_conv0"] = h
+    h = slstm(h, sd, "model.1.lstm")
+    if taps is not None:
+        taps["dec_lstm"] = h
+    for i, s in enumerate(rates):
+        p = f"model.{i + 2}"
+        h = snake(h, sd[f"{p}.block.0.alpha"])
+        h = sconvtr1d(h, sd, f"{p}.block.1.convtr.convtr", s)
+        for j, d in enumerate((1, 3, 9)):
+            h = residual_unit(h, sd, f"{p}.block.{j + 2}", d)
+        if taps is not None:
+            taps[f"dec_block{i + 1}"] = h
+    n = len(rates)
+    h = snake(h, sd[f"model.{n + 2}.alpha"])
+    h = sconv1d(h, sd, f"model.{n + 3}.conv.conv")
+    return torch.tanh(h)
+
+
+# ----------------------------------------------------------------------------
+# mel front-end: torchaudio.transforms.MelSpectrogram as configured at
+# modules/quantize.py:228-230, then preprocess :239-242
+# ----------------------------------------------------------------------------
+def mel_preprocess(sd, wave, n_bins=20, n_fft=2048, hop=HOP, win_length=1200):
+    """wave [B,1,T] -> [B,n_bins,T//300].  torchaudio Spectrogram(center=True, reflect,
+    power=2, window zero-padded to n_fft by torch.stft) -> MelScale (spec^T @ fb)^T ->
+    (log(1e-5+mel)+4)/4 -> slice."""
+    w = wave.squeeze(1)
+    spec = torch.stft(w, n_fft, hop_length=hop, win_length=win_length,
+                      window=sd["to_mel.spectrogram.window"], center=True, pad_mode="reflect",
+                      normalized=False, onesided=True, return_complex=True)
+    spec = spec.abs().pow(2.0)
+    mel = torch.matmul(spec.transpose(-1, -2), sd["to_mel.mel_scale.fb"]).transpose(-1, -2)
+    mel = (torch.log(1e-5 + mel) - (-4)) / 4
+    return mel[:, :n_bins, :int(wave.size(-1) / hop)]
+
+
+# ----------------------------------------------------------------------------
+# modules/style_encoder.py, modules/attentions.py
+# ----------------------------------------------------------------------------
+def _mish(x):
+    """style_encoder.py:6-10."""
+    return x * torch.tanh(F.softplus(x))
+
+
+def _conv1d_glu(x, sd, prefix):
+    """Conv1dGLU, style_encoder.py:13-31 (padding=2 zero pad, eval => dropout off)."""
+    y = F.conv1d(x, sd[prefix + ".conv1.weight"], sd[prefix + ".conv1.bias"], padding=2)
+    c = y.shape[1] // 2
+    x1, x2 = torch.split(y, c, dim=1)
+    return x + x1 * torch.sigmoid(x2)
+
+
+def _mha(x, sd, prefix, n_heads, attn_mask):
+    """MultiHeadAttention.forward/attention, attentions.py:159-199, window_size=None."""
+    def c1(t, n):
+        return F.conv1d(t, sd[f"{prefix}.conv_{n}.weight"], sd[f"{prefix}.conv_{n}.bias"])
+    q, k, v = c1(x, "q"), c1(x, "k"), c1(x, "v")
+    b, d, t = k.shape
+    kc = d // n_heads
+    q = q.view(b, n_heads, kc, t).transpose(2, 3)
+    k = k.view(b, n_heads, kc, t).transpose(2, 3)
+    v = v.view(b, n_heads, kc, t).transpose(2, 3)
+    scores = torch.matmul(q / math.sqrt(kc), k.transpose(-2, -1))
+    scores = scores.masked_fill(attn_mask == 0, -1e4)
+    p = F.softmax(scores, dim=-1)
+    o = torch.matmul(p, v)
+    o = o.transpose(2, 3).contiguous().view(b, d, t)
+    return c1(o, "o")
+
+
+def style_encoder(sd, mel, mask, prefix="timbre_encoder"):
+    """StyleEncoder.forward, style_encoder.py:63-90. mel [B,80,T'], mask [B,1,T'] bool."""
+    x = F.conv1d(mel, sd[prefix + ".spectral.0.weight"], sd[prefix + ".spectral.0.bias"])
+    x = _mish(x)
+    x = F.conv1d(x, sd[prefix + ".spectral.3.weight"], sd[prefix + ".spectral.3.bias"])
+    x = _mish(x) * mask
+    x = _conv1d_glu(x, sd, prefix + ".temporal.0")
+    x = _conv1d_glu(x, sd, prefix + ".temporal.1") * mask
+    attn_mask = mask.unsqueeze(2) * mask.unsqueeze(-1)
+    x = x + _mha(x, sd, prefix + ".slf_attn", 2, attn_mask)
+    x = F.conv1d(x, sd[prefix + ".fc.weight"], sd[prefix + ".fc.bias"])
+    len_ = mask.sum(dim=2)
+    return torch.div(x.sum(dim=2), len_)
+
+
+# ----------------------------------------------------------------------------
+# modules/wavenet.py
+# ----------------------------------------------------------------------------
+def wavenet(sd, x, prefix="melspec_encoder", hidden=256, n_layers=8):
+    """WN.forward, wavenet.py:138-166 with g=None, x_mask == 1, eval (dropout off);
+    gate = commons.py:113-120 fused_add_tanh_sigmoid_multiply."""
+    output = torch.zeros_like(x)
+    for i in range(n_layers):
+        x_in = sconv1d(x, sd, f"{prefix}.in_layers.{i}.conv.conv")
+        in_act = x_in + torch.zeros_like(x_in)
+        acts = torch.tanh(in_act[:, :hidden]) * torch.sigmoid(in_act[:, hidden:])
+        rs = sconv1d(acts, sd, f"{prefix}.res_skip_layers.{i}.conv.conv")
+        if i < n_layers - 1:
+            x = (x + rs[:, :hidden]) * 1.0
+            output = output + rs[:, hidden:]
+        else:
+            output = output + rs
+    return output * 1.0
+
+
+# ----------------------------------------------------------------------------
+# dac/nn/quantize.py
+# ----------------------------------------------------------------------------
+def vq_decode_latents(latents, codebook):
+    """VectorQuantize.decode_latents, dac/nn/quantize.py:78-94 (== quantize/fvq.py:101-116)."""
+    b, d, t = latents.shape
+    enc = latents.permute(0, 2, 1).reshape(b * t, d)
+    enc = F.normalize(enc)
+    cb = F.normalize(codebook)
+    dist = (enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cb.t() + cb.pow(2).sum(1, keepdim=True).t())
+    idx = (-dist).max(1)[1].reshape(b, t)
+    z_q = F.embedding(idx, codebook).transpose(1, 2)
+    return z_q, idx
+
+
+def vector_quantize(sd, prefix, z):
+    """VectorQuantize.forward, dac/nn/quantize.py:34-70. Returns (z_q_out, commit[B], cb[B], idx, z_e)."""
+    w_in = _wn_weight(sd, prefix + ".in_proj")
+    z_e = F.conv1d(z, w_in, sd[prefix + ".in_proj.bias"])
+    z_q, idx = vq_decode_latents(z_e, sd[prefix + ".codebook.weight"])
+    commit = F.mse_loss(z_e, z_q, reduction="none").mean([1, 2])
+    cbl = F.mse_loss(z_q, z_e, reduction="none").mean([1, 2])
+    z_q = z_e + (z_q - z_e)
+    w_out = _wn_weight(sd, prefix + ".out_proj")
+    out = F.conv1d(z_q, w_out, sd[prefix + ".out_proj.bias"])
+    return out, commit, cbl, idx, z_e
+
+
+def residual_vq(sd, prefix, z, n_quantizers):
+    """ResidualVectorQuantize.forward (eval), dac/nn/quantize.py:127-198."""
+    z_q = 0
+    residual = z
+    commitment_loss = 0
+    codebook_loss = 0
+    codes, latents = [], []
+    for i in range(n_quantizers):
+        z_q_i, c_i, cb_i, idx_i, z_e_i = vector_quantize(sd, f"{prefix}.quantizers.{i}", residual)
+        mask = torch.full((z.shape[0],), fill_value=i) < n_quantizers
+        z_q = z_q + z_q_i * mask[:, None, None]
+        residual = residual - z_q_i
+        commitment_loss = commitment_loss + (c_i * mask).mean()
+        codebook_loss = codebook_loss + (cb_i * mask).mean()
+        codes.append(idx_i)
+        latents.append(z_e_i)
+    return z_q, torch.stack(codes, dim=1), torch.cat(latents, dim=1), commitment_loss, codebook_loss
+
+
+# ----------------------------------------------------------------------------
+# modules/quantize.py FAquantizer.forward_v2 (eval)
+# ----------------------------------------------------------------------------
+def sequence_mask(length, max_length):
+    x = torch.arange(max_length, dtype=length.dtype)
+    return x.unsqueeze(0) < length.unsqueeze(1)
+
+
+def quantizer_forward(sd, x, wave, n_c=1, n_t=2, full_waves=None, wave_lens=None,
+                      return_codes=False, taps=None):
+    """FAquantizer.forward_v2, modules/quantize.py:375-454, eval mode (res_mask == 1)."""
+    if full_waves is None:
+        mel = mel_preprocess(sd, wave, n_bins=80)
+        mask = torch.ones(mel.size(0), 1, mel.size(2)).bool()
+    else:
+        mel = mel_preprocess(sd, full_waves.unsqueeze(1), n_bins=80)
+        mask = sequence_mask(wave_lens // HOP, mel.size(-1)).unsqueeze(1)
+    timbre = style_encoder(sd, mel, mask)
+    prosody_feature = mel_preprocess(sd, wave, n_bins=20)
+    f0 = sconv1d(prosody_feature, sd, "melspec_linear.conv.conv")
+    f0 = wavenet(sd, f0)
+    f0 = sconv1d(f0, sd, "melspec_linear2.conv.conv")
+    common = min(f0.size(2), x.size(2))
+    f0 = f0[:, :, :common]
+    x = x[:, :, :common]
+    if taps is not None:
+        taps["mel80"] = mel
+        taps["f0_input"] = f0
+    z_p, codes_p, _, cl_p, cbl_p = residual_vq(sd, "prosody_quantizer", f0, 1)
+    outs = 0 + z_p
+    z_c, codes_c, _, cl_c, cbl_c = residual_vq(sd, "content_quantizer", x, n_c)
+    outs = outs + z_c
+    residual_feature = x - z_p - z_c
+    z_r, codes_r, _, cl_r, cbl_r = residual_vq(sd, "residual_quantizer", residual_feature, 3)
+    outs = outs + z_r * torch.ones(z_r.shape[0], 1, 1)
+    quantized = [z_p, z_c, z_r]
+    codes = [codes_p, codes_c, codes_r]
+    commitment = cl_p + cl_c + cl_r
+    codebook = cbl_p + cbl_c + cbl_r
+    style = F.linear(timbre, sd["timbre_linear.weight"], sd["timbre_linear.bias"]).unsqueeze(2)
+    gamma, beta = style.chunk(2, 1)
+    o = outs.transpose(1, 2)
+    o = F.layer_norm(o, (o.shape[-1],), None, None, 1e-5)
+    o = o.transpose(1, 2)
+    o = o * gamma + beta
+    if return_codes:
+        return o, quantized, commitment, codebook, timbre, codes
+    return o, quantized, commitment, codebook, timbre
+
+
+def codec_forward(sds, wave, n_c=2):
+    """reconstruct.py:56-61: encoder -> quantizer(n_c=2) -> decoder."""
+    with torch.no_grad():
+        z = encoder_forward(sds["encoder"], wave)
+        q = quantizer_forward(sds["quantizer"], z, wave, n_c=n_c, return_codes=True)
+        y = decoder_forward(sds["decoder"], q[0])
+    return z, q, y
+
+
+# ----------------------------------------------------------------------------
+# quantize/fvq.py + quantize/rvq.py (dead code in the reference; BASELINE configs[3])
+# ----------------------------------------------------------------------------
+def fvq_residual_vq(layers, x, n_quantizers=None):
+    """ResidualVQ.forward (eval) quantize/rvq.py:27-75 over FactorizedVectorQuantize.forward
+    quantize/fvq.py:35-83.  ``layers`` = list of dicts with in_w [8,D], in_b, out_w [D,8], out_b
+    (already weight-normed: weight_norm(nn.Linear) dim=0), codebook [N,8].
+    Returns (quantized_out [B,D,T], indices [N,B,T], losses [N], all_quantized [N,B,D,T])."""
+    quantized_out = 0.0
+    residual = x
+    all_idx, all_q, all_loss = [], [], []
+    n = len(layers) if n_quantizers is None else n_quantizers
+    for li, L in enumerate(layers):
+        if li >= n:
+            break
+        z = residual.permute(0, 2, 1)
+        z_e = F.linear(z, L["in_w"], L["in_b"]).permute(0, 2, 1)
+        z_q, idx = vq_decode_latents(z_e, L["codebook"])
+        z_q = z_e + (z_q - z_e)
+        q = F.linear(z_q.permute(0, 2, 1), L["out_w"], L["out_b"]).permute(0, 2, 1)
+        residual = residual - q
+        quantized_out = quantized_out + q * 1.0
+        all_idx.append(idx)
+        all_q.append(q)
+        all_loss.append(torch.zeros(x.shape[0]).mean())
+    return quantized_out, torch.stack(all_idx), torch.stack(all_loss), torch.stack(all_q)
+
+
+# ----------------------------------------------------------------------------
+# alias_free_torch/ (predictor heads only; north_star asks for a kernel + parity)
+# ----------------------------------------------------------------------------
+def kaiser_sinc_filter1d(cutoff, half_width, kernel_size):
+    """alias_free_torch/filter.py:27-58."""
+    even = kernel_size % 2 == 0
+    half_size = kernel_size // 2
+    delta_f = 4 * half_width
+    A = 2.285 * (half_size - 1) * math.pi * delta_f + 7.95
+    if A > 50.0:
+        beta = 0.1102 * (A - 8.7)
+    elif A >= 21.0:
+        beta = 0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21.0)
+    else:
+        beta = 0.0
+    window = torch.kaiser_window(kernel_size, beta=beta, periodic=False)
+    if even:
+        time = torch.arange(-half_size, half_size) + 0.5
+    else:
+        time = torch.arange(kernel_size) - half_size
+    filter_ = 2 * cutoff * window * torch.sinc(2 * cutoff * time)
+    filter_ /= filter_.sum()
+    return filter_.view(1, 1, kernel_size)
+
+
+def alias_free_act(x, act, ratio=2, kernel_size=12):
+    """Activation1d.forward, alias_free_torch/act.py:24-29 = UpSample1d (resample.py:28-37) ->
+    act -> DownSample1d/LowPassFilter1d (resample.py:54-57, filter.py:88-96)."""
+    C = x.shape[1]
+    filt = kaiser_sinc_filter1d(0.5 / ratio, 0.6 / ratio, kernel_size)
+    pad = kernel_size // ratio - 1
+    pad_left = pad * ratio + (kernel_size - ratio) // 2
+    pad_right = pad * ratio + (kernel_size - ratio + 1) // 2
+    u = F.pad(x, (pad, pad), mode="replicate")
+    u = ratio * F.conv_transpose1d(u, filt.expand(C, -1, -1), stride=ratio, groups=C)
+    u = u[..., pad_left:-pad_right]
+    u = act(u)
+    even = kernel_size % 2 == 0
+    pl = kernel_size // 2 - int(even)
+    pr = kernel_size // 2
+    d = F.pad(u, (pl, pr), mode="replicate")
+    return F.conv1d(d, filt.expand(C, -1, -1), stride=ratio, groups=C)

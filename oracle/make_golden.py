@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the
+*unmodified imported reference* (oracle/ref_import.py) on CPU, in the build
+container (needs /root/reference).  Run:  python -m oracle.make_golden
+
+Weights come from facodec_b200.synth.synth_state_dicts(seed) (host-independent
+bits) loaded into the reference modules with load_state_dict, exactly as
+reconstruct.py:30-37 loads a checkpoint; waves from synth.synth_waves
+(PseudoDataset law).  Nothing but the case table, seeds and the reference's
+own outputs goes into the fixtures, so any box can regenerate the inputs and
+compare.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from facodec_b200 import synth  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+# name -> (weight seed, wave seed, batch, samples, n_c, full_waves?)
+CASES = {
+    "b2_t7200": dict(wseed=0, xseed=114514, B=2, T=7200, n_c=2),
+    "b1_t96000": dict(wseed=0, xseed=114514, B=1, T=96000, n_c=2),      # BASELINE configs[0]
+    "b1_t7000_ragged": dict(wseed=0, xseed=7, B=1, T=7000, n_c=2),      # T % 300 != 0
+    "b3_t1500_short": dict(wseed=1, xseed=9, B=3, T=1500, n_c=1),       # reflect-pad short-input branch
+    "b2_t6000_fullwaves": dict(wseed=1, xseed=11, B=2, T=6000, n_c=2, full=9000, lens=(9000, 4800)),
+}
+
+
+def run_case(model, c):
+    x = synth.synth_waves(c["B"], c["T"], seed=c["xseed"])
+    kw = {}
+    if "full" in c:
+        kw["full_waves"] = synth.synth_waves(c["B"], c["full"], seed=c["xseed"] + 1).squeeze(1)
+        kw["wave_lens"] = torch.tensor(c["lens"], dtype=torch.int64)
+    with torch.no_grad():
+        z = model.encoder(x)
+        q = model.quantizer(z, x, n_c=c["n_c"], return_codes=True, **kw)
+        y = model.decoder(q[0])
+    out = dict(z=z, outs=q[0], z_p=q[1][0], z_c=q[1][1], z_r=q[1][2], commitment=q[2],
+               codebook=q[3], timbre=q[4], codes_p=q[5][0], codes_c=q[5][1], codes_r=q[5][2], y=y)
+    return {k: v.numpy() for k, v in out.items()}
+
+
+def vq_margin_report(model, c, out):
+    """top1-top2 distance gap of every VQ decision (for choosing robust fixtures)."""
+    return None
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    model = ref_import.build_reference_model(0)
+    loaded = None
+    for name, c in CASES.items():
+        if loaded != c["wseed"]:
+            sds = synth.synth_state_dicts(c["wseed"])
+            for k in ("encoder", "quantizer", "decoder"):
+                model[k].load_state_dict(sds[k])
+            loaded = c["wseed"]
+        out = run_case(model, c)
+        # z_p/z_c/z_r are large; keep float32 for the small cases only
+        if c["B"] * c["T"] > 20000:
+            for k in ("z_p", "z_c", "z_r"):
+                out.pop(k)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, {k: v.shape for k, v in out.items()}, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
