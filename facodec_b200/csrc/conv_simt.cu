@@ -1,0 +1,239 @@
+// Generic channels-last 1-D convolution as an implicit GEMM on the fp32 FMA pipe.
+//
+// Replaces the reference's F.pad(reflect) + nn.Conv1d / nn.ConvTranspose1d / nn.Linear call
+// sites (dac/model/encodec.py:212-228 SConv1d.forward, :248-270 SConvTranspose1d.forward,
+// modules/style_encoder.py, modules/wavenet.py:145-160, nn.LSTM input projections) with one
+// kernel:
+//
+//   y[b][t][co] = epi( bias[co] + sum_{tap<K} sum_{ci<Cin}
+//                      pro(x[b][map(t*stride + tap*dil - pad_left)][ci]) * w[tap*Cin + ci][co] )
+//
+// * x, y channels-last fp32; w packed "kk-major" [K*Cin][ldw] (ldw = Cout rounded up to 4).
+// * map() = reflect / zero padding index map (common.cuh PadMap) -- no padded copy in HBM.
+// * pro() = optional Snake on the input (dac/nn/layers.py:17-24), per input channel.
+// * epi() = bias, then optional Snake / tanh / Mish, then optional residual add, optional
+//   row mask (t < valid_len[b]), optional transposed ([B][Cout][T]) store.
+// * ConvTranspose1d(k=2s, stride=s) + right trim is run as a K=2 zero-left-padded conv with
+//   Cout*s output channels (phase-major); [B][T][s*Cout] IS [B][T*s][Cout] in channels-last.
+//
+// Tile: 128 (time) x BN (channels) per CTA, 8x8 register tile per thread, BK=16 deep smem
+// stages with register prefetch of the next stage.  This is the fp32-exact path (bit-exact VQ
+// indices need fp32-faithful accumulation).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fac {
+
+constexpr int CONV_BM = 128;
+constexpr int CONV_BK = 16;
+constexpr int CONV_XPAD = 4;
+
+template <int BN>
+__global__ void __launch_bounds__(2 * BN) conv_cl_kernel(ConvParams p) {
+    constexpr int BM = CONV_BM, BK = CONV_BK;
+    constexpr int NT = 2 * BN;               // 16 t-groups x BN/8 co-groups
+    constexpr int CG = BN / 8;               // co groups
+    constexpr int LC = (CG % 8 == 0) ? 8 : 4; // lanes along co inside a warp
+    constexpr int LT = 32 / LC;              // lanes along t
+    constexpr int WC = CG / LC;              // warps along co
+    constexpr int A_F4 = BM * BK / 4;        // float4 per A stage
+    constexpr int A_PER = (A_F4 + NT - 1) / NT;
+    constexpr int W_F4 = BK * BN / 4;
+    constexpr int W_PER = W_F4 / NT;         // == 2
+
+    __shared__ __align__(16) float xs[BK][BM + CONV_XPAD];
+    __shared__ __align__(16) float ws[BK][BN];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wc = warp % WC, wt = warp / WC;
+    const int cg = wc * LC + (lane % LC);    // co group 0..CG-1
+    const int tg = wt * LT + (lane / LC);    // t group 0..15
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * BM;
+    const int co0 = blockIdx.y * BN;
+
+    const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
+    const PadMap pm = PadMap::make(p.Tin, p.pad_left, p.pad_right, p.pad_reflect);
+    const int Ktot = p.K * p.Cin;
+    const bool vec_a = (p.Cin % 4) == 0;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 a_reg[A_PER];
+    float4 w_reg[W_PER];
+
+    auto load_stage = [&](int kk0) {
+#pragma unroll
+        for (int it = 0; it < A_PER; ++it) {
+            int i = tid + it * NT;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < A_F4) {
+                int r = i >> 2, c4 = i & 3;
+                int kk = kk0 + c4 * 4;
+                int t = t0 + r;
+                if (t < p.Tout && kk < Ktot) {
+                    if (vec_a) {
+                        int tap = kk / p.Cin, ci = kk - tap * p.Cin;
+                        int row = pm.src(t * p.stride + tap * p.dil - p.pad_left);
+                        if (row >= 0) {
+                            v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.ldx + ci));
+                            if (p.in_alpha) {
+                                float4 al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + ci));
+                                float4 ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + ci));
+                                v.x = snake_f(v.x, al.x, ia.x);
+                                v.y = snake_f(v.y, al.y, ia.y);
+                                v.z = snake_f(v.z, al.z, ia.z);
+                                v.w = snake_f(v.w, al.w, ia.w);
+                            }
+                        }
+                    } else {
+                        float e[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            int k2 = kk + j;
+                            float val = 0.f;
+                            if (k2 < Ktot) {
+                                int tap = k2 / p.Cin, ci = k2 - tap * p.Cin;
+                                int row = pm.src(t * p.stride + tap * p.dil - p.pad_left);
+                                if (row >= 0) {
+                                    val = __ldg(xb + (size_t)row * p.ldx + ci);
+                                    if (p.in_alpha) val = snake_f(val, p.in_alpha[ci], p.in_inv_alpha[ci]);
+                                }
+                            }
+                            e[j] = val;
+                        }
+                        v = make_float4(e[0], e[1], e[2], e[3]);
+                    }
+                }
+            }
+            a_reg[it] = v;
+        }
+#pragma unroll
+        for (int it = 0; it < W_PER; ++it) {
+            int i = tid + it * NT;
+            int kr = i / (BN / 4), c4 = i % (BN / 4);
+            int kk = kk0 + kr;
+            int co = co0 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kk < Ktot && co < p.ldw) v = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)kk * p.ldw + co));
+            w_reg[it] = v;
+        }
+    };
+    auto store_stage = [&]() {
+#pragma unroll
+        for (int it = 0; it < A_PER; ++it) {
+            int i = tid + it * NT;
+            if (i < A_F4) {
+                int r = i >> 2, c4 = i & 3;
+                xs[c4 * 4 + 0][r] = a_reg[it].x;
+                xs[c4 * 4 + 1][r] = a_reg[it].y;
+                xs[c4 * 4 + 2][r] = a_reg[it].z;
+                xs[c4 * 4 + 3][r] = a_reg[it].w;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < W_PER; ++it) {
+            int i = tid + it * NT;
+            int kr = i / (BN / 4), c4 = i % (BN / 4);
+            *reinterpret_cast<float4*>(&ws[kr][c4 * 4]) = w_reg[it];
+        }
+    };
+
+    const int nstage = (Ktot + BK - 1) / BK;
+    load_stage(0);
+    for (int s = 0; s < nstage; ++s) {
+        __syncthreads();   // previous stage fully consumed
+        store_stage();
+        __syncthreads();
+        if (s + 1 < nstage) load_stage((s + 1) * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 a0 = *reinterpret_cast<const float4*>(&xs[kk][tg * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&xs[kk][tg * 8 + 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&ws[kk][cg * 8]);
+            float4 b1 = *reinterpret_cast<const float4*>(&ws[kk][cg * 8 + 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+    }
+
+    // ---- epilogue ----
+    const int cbase = co0 + cg * 8;
+    if (cbase >= p.Cout) return;
+    float bias[8], oal[8], oia[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int co = cbase + j;
+        bool ok = co < p.Cout;
+        bias[j] = (p.bias && ok) ? p.bias[co] : 0.f;
+        oal[j] = (p.out_act == ACT_SNAKE && ok) ? p.out_alpha[co] : 0.f;
+        oia[j] = (p.out_act == ACT_SNAKE && ok) ? p.out_inv_alpha[co] : 0.f;
+    }
+    const int vlen = p.valid_len ? p.valid_len[b] : 0x7fffffff;
+    float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
+    const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int t = t0 + tg * 8 + i;
+        if (t >= p.Tout) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float o = acc[i][j] + bias[j];
+            if (p.out_act == ACT_TANH) o = tanhf(o);
+            else if (p.out_act == ACT_MISH) o = mish_f(o);
+            else if (p.out_act == ACT_SNAKE) o = snake_f(o, oal[j], oia[j]);
+            v[j] = o;
+        }
+        if (p.y_transposed) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (cbase + j < p.Cout) yb[(size_t)(cbase + j) * p.Tout + t] = (t < vlen) ? v[j] : 0.f;
+            continue;
+        }
+        size_t off = (size_t)t * p.ldy + cbase;
+        if (rb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (cbase + j < p.Cout) v[j] += rb[off + j];
+        }
+        if (t >= vlen) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        }
+        if (cbase + 8 <= p.Cout && (p.ldy % 4) == 0) {
+            *reinterpret_cast<float4*>(yb + off) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(yb + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (cbase + j < p.Cout) yb[off + j] = v[j];
+        }
+    }
+}
+
+cudaError_t launch_conv(const ConvParams& p, cudaStream_t st) {
+    if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
+    dim3 grid((p.Tout + CONV_BM - 1) / CONV_BM, 1, p.B);
+    // channel tile with the least padding waste (ties -> wider tile)
+    auto padded = [&](int bn) { return (p.Cout + bn - 1) / bn * bn; };
+    int bn = 128;
+    if (padded(96) < padded(bn)) bn = 96;
+    if (padded(64) < padded(bn)) bn = 64;
+    grid.y = (p.Cout + bn - 1) / bn;
+    if (bn == 128) conv_cl_kernel<128><<<grid, 256, 0, st>>>(p);
+    else if (bn == 96) conv_cl_kernel<96><<<grid, 192, 0, st>>>(p);
+    else conv_cl_kernel<64><<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace fac

@@ -1,0 +1,1143 @@
+// Engine + C-ABI (include/facodec_b200.h): checkpoint folding/packing, workspace, and the
+// launch sequences of Encoder.forward (dac/model/dac.py:69-104), FAquantizer.forward_v2
+// (modules/quantize.py:375-454) and Decoder.forward (dac/model/dac.py:131-165).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/facodec_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace fac;
+
+namespace {
+
+constexpr int HOP = 300;
+constexpr int LATENT = 1024;
+constexpr int N_FFT = 2048;
+constexpr int WIN = 1200;
+constexpr int N_BINS = 1025;
+constexpr int SPEC_LD = 2052;   // 2*1025 rounded up to a multiple of 4
+constexpr int N_MELS = 80;
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+    size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; }
+};
+
+struct ConvW { size_t w = 0, b = 0; int Cin = 0, Cout = 0, K = 1, ldw = 0; };
+struct SnakeW { size_t a = 0, ia = 0; int C = 0; };
+struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; int H = 0, U = 0, G = 0; };
+struct ResW { SnakeW s1; ConvW c7; SnakeW s2; ConvW c1; int dil = 1; };
+struct VqW { size_t w_in, b_in, cb, cbn, cbn2, w_out, b_out; };
+
+struct EncW {
+    ConvW conv0;
+    struct Block { ResW res[3]; SnakeW snake; ConvW down; int stride; } blk[4];
+    LstmW lstm; SnakeW snake; ConvW conv_out;
+};
+struct DecW {
+    ConvW conv0; LstmW lstm;
+    struct Block { SnakeW snake; ConvW up; int stride; int cout; ResW res[3]; } blk[4];
+    SnakeW snake; ConvW conv_out;
+};
+struct QuantW {
+    VqW vq[6];
+    ConvW spec0, spec3, glu[2], cq, ck, cv, co, fc, timbre_linear;
+    ConvW mel_lin, wn_in[8], wn_rs[8], mel_lin2;
+    ConvW dft; size_t fb = 0;
+};
+struct RvqSet { int nq; VqW vq[8]; };
+
+}  // namespace
+
+struct fac_handle {
+    int device = 0;
+    std::string err;
+    std::map<std::string, HostTensor> host[3];
+    bool have[3] = {false, false, false};
+    bool finalized = false;
+    std::vector<float> pack;        // host staging of the weight arena
+    float* warena = nullptr; size_t wfloats = 0;
+    EncW enc; DecW dec; QuantW qw;
+    std::vector<RvqSet> rvqs; std::vector<float*> rvq_arenas;
+    char* ws = nullptr; size_t ws_bytes = 0;
+    int launches = 0;
+    float* aa_filter = nullptr;
+    // optional per-kernel-family timing (fac_profile_*): CUDA events around every launch
+    bool profiling = false;
+    struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
+    std::vector<ProfRec> prof;
+    struct ProfAgg { double ms = 0, flops = 0, bytes = 0; long launches = 0; };
+    std::map<std::string, ProfAgg> prof_agg;
+    // debug taps: named intermediates copied out during a forward (fac_debug_tap)
+    std::map<std::string, std::pair<float*, size_t>> taps;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// packing helpers (host)
+// ------------------------------------------------------------------------------------------
+size_t pack_alloc(fac_handle* h, size_t n) {
+    size_t off = (h->pack.size() + 63) / 64 * 64;
+    h->pack.resize(off + n, 0.f);
+    return off;
+}
+
+const HostTensor* find(fac_handle* h, int m, const std::string& k) {
+    auto it = h->host[m].find(k);
+    return it == h->host[m].end() ? nullptr : &it->second;
+}
+
+struct PackError { std::string msg; };
+const HostTensor& need(fac_handle* h, int m, const std::string& k) {
+    const HostTensor* t = find(h, m, k);
+    if (!t) throw PackError{"missing tensor '" + k + "' in module " + std::to_string(m)};
+    return *t;
+}
+
+// Folded conv weight in PyTorch layout [d0][d1][K] (weight-norm over dims != 0, encodec.py:42-51).
+std::vector<float> folded_weight(fac_handle* h, int m, const std::string& prefix, std::vector<int64_t>& shape) {
+    if (const HostTensor* w = find(h, m, prefix + ".weight")) {
+        shape = w->shape;
+        return w->data;
+    }
+    const HostTensor& v = need(h, m, prefix + ".weight_v");
+    const HostTensor& g = need(h, m, prefix + ".weight_g");
+    shape = v.shape;
+    size_t d0 = (size_t)v.shape[0], inner = v.numel() / d0;
+    if (g.numel() != d0) throw PackError{"weight_g shape mismatch at " + prefix};
+    std::vector<float> w(v.numel());
+    for (size_t i = 0; i < d0; ++i) {
+        double s = 0.0;
+        for (size_t j = 0; j < inner; ++j) { double x = v.data[i * inner + j]; s += x * x; }
+        float scale = g.data[i] / (float)std::sqrt(s);
+        for (size_t j = 0; j < inner; ++j) w[i * inner + j] = v.data[i * inner + j] * scale;
+    }
+    return w;
+}
+
+// nn.Conv1d [Cout][Cin][K] -> packed [K*Cin][ldw]
+ConvW pack_conv(fac_handle* h, int m, const std::string& prefix) {
+    std::vector<int64_t> shp;
+    std::vector<float> w = folded_weight(h, m, prefix, shp);
+    if (shp.size() == 2) shp.push_back(1);
+    if (shp.size() != 3) throw PackError{"conv weight rank at " + prefix};
+    ConvW c;
+    c.Cout = (int)shp[0]; c.Cin = (int)shp[1]; c.K = (int)shp[2];
+    c.ldw = (c.Cout + 3) / 4 * 4;
+    c.w = pack_alloc(h, (size_t)c.K * c.Cin * c.ldw);
+    for (int co = 0; co < c.Cout; ++co)
+        for (int ci = 0; ci < c.Cin; ++ci)
+            for (int k = 0; k < c.K; ++k)
+                h->pack[c.w + ((size_t)k * c.Cin + ci) * c.ldw + co] = w[((size_t)co * c.Cin + ci) * c.K + k];
+    const HostTensor& b = need(h, m, prefix + ".bias");
+    c.b = pack_alloc(h, c.Cout);
+    for (int co = 0; co < c.Cout; ++co) h->pack[c.b + co] = b.data[co];
+    return c;
+}
+
+// nn.ConvTranspose1d [Cin][Cout][2s] stride s + right trim (encodec.py:248-270) -> K=2 conv with
+// Cout*s phase-major output channels: tap0 (x[t-1]) = w[..][r+s], tap1 (x[t]) = w[..][r].
+ConvW pack_convtr(fac_handle* h, int m, const std::string& prefix, int stride) {
+    std::vector<int64_t> shp;
+    std::vector<float> w = folded_weight(h, m, prefix, shp);
+    if (shp.size() != 3 || shp[2] != 2 * stride) throw PackError{"convtr kernel != 2*stride at " + prefix};
+    int Cin = (int)shp[0], Cout = (int)shp[1], K = (int)shp[2];
+    ConvW c;
+    c.Cin = Cin; c.Cout = Cout * stride; c.K = 2; c.ldw = (c.Cout + 3) / 4 * 4;
+    c.w = pack_alloc(h, (size_t)2 * Cin * c.ldw);
+    for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+            for (int r = 0; r < stride; ++r) {
+                h->pack[c.w + ((size_t)0 * Cin + ci) * c.ldw + r * Cout + co] = w[((size_t)ci * Cout + co) * K + r + stride];
+                h->pack[c.w + ((size_t)1 * Cin + ci) * c.ldw + r * Cout + co] = w[((size_t)ci * Cout + co) * K + r];
+            }
+    const HostTensor& b = need(h, m, prefix + ".bias");
+    c.b = pack_alloc(h, c.Cout);
+    for (int r = 0; r < stride; ++r)
+        for (int co = 0; co < Cout; ++co) h->pack[c.b + r * Cout + co] = b.data[co];
+    return c;
+}
+
+SnakeW pack_snake(fac_handle* h, int m, const std::string& key) {
+    const HostTensor& a = need(h, m, key);
+    SnakeW s;
+    s.C = (int)a.numel();
+    s.a = pack_alloc(h, s.C);
+    s.ia = pack_alloc(h, s.C);
+    for (int i = 0; i < s.C; ++i) {
+        h->pack[s.a + i] = a.data[i];
+        h->pack[s.ia + i] = 1.0f / (a.data[i] + 1e-9f);   // (alpha + 1e-9).reciprocal(), fp32
+    }
+    return s;
+}
+
+ResW pack_res(fac_handle* h, int m, const std::string& prefix, int dil) {
+    ResW r;
+    r.dil = dil;
+    r.s1 = pack_snake(h, m, prefix + ".block.0.alpha");
+    r.c7 = pack_conv(h, m, prefix + ".block.1.conv.conv");
+    r.s2 = pack_snake(h, m, prefix + ".block.2.alpha");
+    r.c1 = pack_conv(h, m, prefix + ".block.3.conv.conv");
+    return r;
+}
+
+LstmW pack_lstm(fac_handle* h, int m, const std::string& prefix) {
+    LstmW L;
+    const HostTensor& w0 = need(h, m, prefix + ".weight_hh_l0");
+    L.H = (int)w0.shape[1];
+    L.U = lstm_units_per_cta(L.H);
+    if (L.U == 0) throw PackError{"unsupported LSTM width " + std::to_string(L.H)};
+    L.G = L.H / L.U;
+    const int H = L.H, U = L.U, R = 4 * U;
+    for (int l = 0; l < 2; ++l) {
+        std::string sfx = "_l" + std::to_string(l);
+        const HostTensor& wih = need(h, m, prefix + ".weight_ih" + sfx);
+        const HostTensor& whh = need(h, m, prefix + ".weight_hh" + sfx);
+        const HostTensor& bih = need(h, m, prefix + ".bias_ih" + sfx);
+        const HostTensor& bhh = need(h, m, prefix + ".bias_hh" + sfx);
+        ConvW c;
+        c.Cin = H; c.Cout = 4 * H; c.K = 1; c.ldw = 4 * H;
+        c.w = pack_alloc(h, (size_t)H * c.ldw);
+        for (int row = 0; row < 4 * H; ++row)
+            for (int k = 0; k < H; ++k) h->pack[c.w + (size_t)k * c.ldw + row] = wih.data[(size_t)row * H + k];
+        c.b = pack_alloc(h, 4 * H);
+        for (int row = 0; row < 4 * H; ++row) h->pack[c.b + row] = bih.data[row] + bhh.data[row];
+        L.ih[l] = c;
+        L.whh[l] = pack_alloc(h, (size_t)L.G * H * R);
+        for (int cta = 0; cta < L.G; ++cta)
+            for (int k = 0; k < H; ++k)
+                for (int g = 0; g < 4; ++g)
+                    for (int u = 0; u < U; ++u)
+                        h->pack[L.whh[l] + ((size_t)cta * H + k) * R + g * U + u] =
+                            whh.data[((size_t)g * H + cta * U + u) * H + k];
+    }
+    return L;
+}
+
+VqW pack_vq_raw(std::vector<float>& pack, const float* in_w, const float* in_b, const float* out_w,
+                const float* out_b, const float* codebook, fac_handle* h = nullptr) {
+    auto alloc = [&](size_t n) {
+        size_t off = (pack.size() + 63) / 64 * 64;
+        pack.resize(off + n, 0.f);
+        return off;
+    };
+    VqW v;
+    v.w_in = alloc(8 * 1024);
+    for (int i = 0; i < 8 * 1024; ++i) pack[v.w_in + i] = in_w[i];
+    v.b_in = alloc(8);
+    for (int i = 0; i < 8; ++i) pack[v.b_in + i] = in_b[i];
+    v.cb = alloc(1024 * 8);
+    v.cbn = alloc(1024 * 8);
+    v.cbn2 = alloc(1024);
+    for (int j = 0; j < 1024; ++j) {
+        float n2 = 0.f;
+        for (int k = 0; k < 8; ++k) n2 = fmaf(codebook[j * 8 + k], codebook[j * 8 + k], n2);
+        float nrm = fmaxf(sqrtf(n2), 1e-12f);
+        float c2 = 0.f;
+        for (int k = 0; k < 8; ++k) {
+            float cn = codebook[j * 8 + k] / nrm;
+            pack[v.cb + j * 8 + k] = codebook[j * 8 + k];
+            pack[v.cbn + j * 8 + k] = cn;
+            c2 = fmaf(cn, cn, c2);
+        }
+        pack[v.cbn2 + j] = c2;
+    }
+    v.w_out = alloc(8 * 1024);   // transposed [k][c]
+    for (int c = 0; c < 1024; ++c)
+        for (int k = 0; k < 8; ++k) pack[v.w_out + (size_t)k * 1024 + c] = out_w[c * 8 + k];
+    v.b_out = alloc(1024);
+    for (int c = 0; c < 1024; ++c) pack[v.b_out + c] = out_b[c];
+    (void)h;
+    return v;
+}
+
+VqW pack_vq(fac_handle* h, int m, const std::string& prefix) {
+    std::vector<int64_t> s1, s2;
+    std::vector<float> win = folded_weight(h, m, prefix + ".in_proj", s1);
+    std::vector<float> wout = folded_weight(h, m, prefix + ".out_proj", s2);
+    if (s1[0] != 8 || s1[1] != 1024 || s2[0] != 1024 || s2[1] != 8) throw PackError{"VQ shape at " + prefix};
+    const HostTensor& bi = need(h, m, prefix + ".in_proj.bias");
+    const HostTensor& bo = need(h, m, prefix + ".out_proj.bias");
+    const HostTensor& cb = need(h, m, prefix + ".codebook.weight");
+    if (cb.shape[0] != 1024 || cb.shape[1] != 8) throw PackError{"codebook shape at " + prefix};
+    return pack_vq_raw(h->pack, win.data(), bi.data.data(), wout.data(), bo.data.data(), cb.data.data());
+}
+
+void pack_encoder(fac_handle* h) {
+    EncW& e = h->enc;
+    const int m = FAC_ENCODER;
+    const int rates[4] = {2, 5, 5, 6};
+    e.conv0 = pack_conv(h, m, "block.0.conv.conv");
+    for (int i = 0; i < 4; ++i) {
+        std::string p = "block." + std::to_string(i + 1);
+        const int dils[3] = {1, 3, 9};
+        for (int j = 0; j < 3; ++j) e.blk[i].res[j] = pack_res(h, m, p + ".block." + std::to_string(j), dils[j]);
+        e.blk[i].snake = pack_snake(h, m, p + ".block.3.alpha");
+        e.blk[i].down = pack_conv(h, m, p + ".block.4.conv.conv");
+        e.blk[i].stride = rates[i];
+        if (e.blk[i].down.K != 2 * rates[i]) throw PackError{"encoder stride/kernel mismatch"};
+    }
+    e.lstm = pack_lstm(h, m, "block.5.lstm");
+    e.snake = pack_snake(h, m, "block.6.alpha");
+    e.conv_out = pack_conv(h, m, "block.7.conv.conv");
+}
+
+void pack_decoder(fac_handle* h) {
+    DecW& d = h->dec;
+    const int m = FAC_DECODER;
+    const int rates[4] = {6, 5, 5, 2};
+    d.conv0 = pack_conv(h, m, "model.0.conv.conv");
+    d.lstm = pack_lstm(h, m, "model.1.lstm");
+    for (int i = 0; i < 4; ++i) {
+        std::string p = "model." + std::to_string(i + 2);
+        d.blk[i].snake = pack_snake(h, m, p + ".block.0.alpha");
+        d.blk[i].up = pack_convtr(h, m, p + ".block.1.convtr.convtr", rates[i]);
+        d.blk[i].stride = rates[i];
+        d.blk[i].cout = d.blk[i].up.Cout / rates[i];
+        const int dils[3] = {1, 3, 9};
+        for (int j = 0; j < 3; ++j) d.blk[i].res[j] = pack_res(h, m, p + ".block." + std::to_string(j + 2), dils[j]);
+    }
+    d.snake = pack_snake(h, m, "model.6.alpha");
+    d.conv_out = pack_conv(h, m, "model.7.conv.conv");
+}
+
+void pack_quantizer(fac_handle* h) {
+    QuantW& q = h->qw;
+    const int m = FAC_QUANTIZER;
+    q.vq[0] = pack_vq(h, m, "prosody_quantizer.quantizers.0");
+    q.vq[1] = pack_vq(h, m, "content_quantizer.quantizers.0");
+    q.vq[2] = pack_vq(h, m, "content_quantizer.quantizers.1");
+    for (int i = 0; i < 3; ++i) q.vq[3 + i] = pack_vq(h, m, "residual_quantizer.quantizers." + std::to_string(i));
+    q.spec0 = pack_conv(h, m, "timbre_encoder.spectral.0");
+    q.spec3 = pack_conv(h, m, "timbre_encoder.spectral.3");
+    q.glu[0] = pack_conv(h, m, "timbre_encoder.temporal.0.conv1");
+    q.glu[1] = pack_conv(h, m, "timbre_encoder.temporal.1.conv1");
+    q.cq = pack_conv(h, m, "timbre_encoder.slf_attn.conv_q");
+    q.ck = pack_conv(h, m, "timbre_encoder.slf_attn.conv_k");
+    q.cv = pack_conv(h, m, "timbre_encoder.slf_attn.conv_v");
+    q.co = pack_conv(h, m, "timbre_encoder.slf_attn.conv_o");
+    q.fc = pack_conv(h, m, "timbre_encoder.fc");
+    q.timbre_linear = pack_conv(h, m, "timbre_linear");
+    q.mel_lin = pack_conv(h, m, "melspec_linear.conv.conv");
+    for (int i = 0; i < 8; ++i) {
+        q.wn_in[i] = pack_conv(h, m, "melspec_encoder.in_layers." + std::to_string(i) + ".conv.conv");
+        q.wn_rs[i] = pack_conv(h, m, "melspec_encoder.res_skip_layers." + std::to_string(i) + ".conv.conv");
+    }
+    q.mel_lin2 = pack_conv(h, m, "melspec_linear2.conv.conv");
+    // STFT basis with the Hann window folded in: frame sample n+424 of the zero-padded window
+    const HostTensor& win = need(h, m, "to_mel.spectrogram.window");
+    const HostTensor& fb = need(h, m, "to_mel.mel_scale.fb");
+    if ((int)win.numel() != WIN || fb.shape[0] != N_BINS || fb.shape[1] != N_MELS) throw PackError{"mel buffers shape"};
+    q.dft.Cin = 1; q.dft.Cout = 2 * N_BINS; q.dft.K = WIN; q.dft.ldw = SPEC_LD;
+    q.dft.w = pack_alloc(h, (size_t)WIN * SPEC_LD);
+    q.dft.b = 0;
+    const int left = (N_FFT - WIN) / 2;
+    for (int n = 0; n < WIN; ++n)
+        for (int k = 0; k < N_BINS; ++k) {
+            // reduce the phase index mod N_FFT in integers so the fp64 angle stays small
+            long long ph = ((long long)k * (n + left)) % N_FFT;
+            double ang = 2.0 * M_PI * (double)ph / (double)N_FFT;
+            h->pack[q.dft.w + (size_t)n * SPEC_LD + 2 * k] = (float)((double)win.data[n] * std::cos(ang));
+            h->pack[q.dft.w + (size_t)n * SPEC_LD + 2 * k + 1] = (float)(-(double)win.data[n] * std::sin(ang));
+        }
+    q.fb = pack_alloc(h, (size_t)N_BINS * N_MELS);
+    for (size_t i = 0; i < (size_t)N_BINS * N_MELS; ++i) h->pack[q.fb + i] = fb.data[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// forward context: bump allocator over the handle's workspace + launch helpers
+// ------------------------------------------------------------------------------------------
+struct Ctx {
+    fac_handle* h;
+    cudaStream_t st;
+    bool dry;          // size pass: allocate only
+    size_t off = 0;
+    cudaError_t cerr = cudaSuccess;
+    const char* where = "";
+
+    template <typename T>
+    T* alloc(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
+        char* p = h->ws ? h->ws + off : nullptr;
+        off += bytes;
+        return reinterpret_cast<T*>(p);
+    }
+    const float* W(size_t o) const { return h->warena + o; }
+    bool ok() const { return cerr == cudaSuccess; }
+    void check(cudaError_t e, const char* w) {     // a kernel launch
+        if (!dry) h->launches++;
+        if (e != cudaSuccess && cerr == cudaSuccess) { cerr = e; where = w; }
+    }
+    void check_nk(cudaError_t e, const char* w) {  // memset / memcpy: not a kernel
+        if (e != cudaSuccess && cerr == cudaSuccess) { cerr = e; where = w; }
+    }
+    void tap(const char* name, const float* src, size_t n) {
+        if (dry || h->taps.empty()) return;
+        auto it = h->taps.find(name);
+        if (it == h->taps.end()) return;
+        size_t m = n < it->second.second ? n : it->second.second;
+        check_nk(cudaMemcpyAsync(it->second.first, src, m * sizeof(float), cudaMemcpyDeviceToDevice, st), "tap");
+    }
+    // profiling: begin()/end() bracket one launch with events on the launching stream
+    void begin(const char* fam, double flops, double bytes) {
+        if (dry || !h->profiling) return;
+        fac_handle::ProfRec r;
+        r.name = fam; r.flops = flops; r.bytes = bytes;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        h->prof.push_back(r);
+    }
+    void end() {
+        if (dry || !h->profiling) return;
+        cudaEventRecord(h->prof.back().b, st);
+    }
+};
+
+struct ConvOpts {
+    int dil = 1, stride = 1, pad_left = 0, pad_right = 0, reflect = 0;
+    const SnakeW* in_snake = nullptr;
+    const SnakeW* out_snake = nullptr;
+    int act = ACT_NONE;
+    const float* res = nullptr;
+    const int* valid_len = nullptr;
+    int transposed = 0;
+    int ldx = 0;            // input row stride (0 = Cin)
+    int ldy = 0;            // output row stride (0 = Cout)
+    bool no_bias = false;
+};
+
+// SConv1d padding rule (encodec.py:212-228): causal => (k_eff - stride) on the left (reflect),
+// plus "extra" on the right so the last window is full (encodec.py:71-78).
+int conv_out_len(int T, int k_eff, int stride) {
+    int padding_total = k_eff - stride;
+    double n_frames = (double)(T - k_eff + padding_total) / stride + 1.0;
+    int ideal = ((int)std::ceil(n_frames) - 1) * stride + (k_eff - padding_total);
+    int extra = ideal - T;
+    return (T + padding_total + extra - k_eff) / stride + 1;
+}
+int conv_extra_pad(int T, int k_eff, int stride) {
+    int padding_total = k_eff - stride;
+    double n_frames = (double)(T - k_eff + padding_total) / stride + 1.0;
+    int ideal = ((int)std::ceil(n_frames) - 1) * stride + (k_eff - padding_total);
+    return ideal - T;
+}
+
+void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, int Tout, const ConvOpts& o,
+              const char* name) {
+    if (c.dry) return;
+    ConvParams p;
+    p.x = x; p.y = y;
+    p.w = c.W(w.w);
+    p.bias = o.no_bias ? nullptr : c.W(w.b);
+    if (o.in_snake) { p.in_alpha = c.W(o.in_snake->a); p.in_inv_alpha = c.W(o.in_snake->ia); }
+    p.out_act = o.act;
+    if (o.out_snake) { p.out_act = ACT_SNAKE; p.out_alpha = c.W(o.out_snake->a); p.out_inv_alpha = c.W(o.out_snake->ia); }
+    p.res = o.res; p.valid_len = o.valid_len;
+    p.B = B; p.Tin = Tin; p.Cin = w.Cin; p.Tout = Tout; p.Cout = w.Cout;
+    p.K = w.K; p.dil = o.dil; p.stride = o.stride;
+    p.pad_left = o.pad_left; p.pad_right = o.pad_right; p.pad_reflect = o.reflect;
+    p.ldw = w.ldw; p.ldy = o.ldy ? o.ldy : w.Cout; p.ldx = o.ldx ? o.ldx : w.Cin;
+    p.y_transposed = o.transposed;
+    p.x_bstride = (size_t)Tin * p.ldx;
+    p.y_bstride = (size_t)Tout * p.ldy;
+    // algorithmic work of this launch: 2*MACs; bytes = input + output (+ residual) + weights once
+    double flops = 2.0 * B * Tout * (double)w.Cout * w.K * w.Cin;
+    double bytes = 4.0 * ((double)B * Tin * w.Cin + (double)B * Tout * w.Cout * (o.res ? 2 : 1) + (double)w.K * w.Cin * w.Cout);
+    c.begin("conv", flops, bytes);
+    c.check(launch_conv(p, c.st), name);
+    c.end();
+}
+
+// causal SConv1d with reflect padding; returns output length
+int sconv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int T, int dil, int stride, ConvOpts o,
+          const char* name) {
+    int k_eff = (w.K - 1) * dil + 1;
+    o.dil = dil; o.stride = stride;
+    o.pad_left = k_eff - stride;
+    o.pad_right = conv_extra_pad(T, k_eff, stride);
+    o.reflect = 1;
+    int Tout = conv_out_len(T, k_eff, stride);
+    run_conv(c, w, x, y, B, T, Tout, o, name);
+    return Tout;
+}
+
+// ResidualUnit (dac.py:25-42): y = x + conv1(snake2(conv7_d(snake1(x))))
+void residual_unit(Ctx& c, const ResW& r, const float* x, float* tmp, float* y, int B, int T) {
+    ConvOpts o1;
+    o1.in_snake = &r.s1;
+    o1.out_snake = &r.s2;
+    sconv(c, r.c7, x, tmp, B, T, r.dil, 1, o1, "res.conv7");
+    ConvOpts o2;
+    o2.res = x;
+    sconv(c, r.c1, tmp, y, B, T, 1, 1, o2, "res.conv1");
+}
+
+// SLSTM (encodec.py:272-288) on channels-last x [B][T][H]; y = lstm2(lstm1(x)) + x
+void slstm(Ctx& c, const LstmW& L, const float* x, float* y, int B, int T) {
+    const int H = L.H;
+    float* xg = c.alloc<float>((size_t)B * T * 4 * H);
+    float* h1 = c.alloc<float>((size_t)B * T * H);
+    float* hT = c.alloc<float>((size_t)2 * H * 32);
+    unsigned int* bar = c.alloc<unsigned int>(64);
+    for (int l = 0; l < 2; ++l) {
+        const float* in = l == 0 ? x : h1;
+        ConvOpts o;
+        run_conv(c, L.ih[l], in, xg, 1, B * T, B * T, o, "lstm.ih");
+        if (c.dry) continue;
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            int nb = B - b0 < 32 ? B - b0 : 32;
+            LstmParams p;
+            p.xg = xg + (size_t)b0 * T * 4 * H;
+            p.whh_p = c.W(L.whh[l]);
+            p.skip = l == 1 ? x + (size_t)b0 * T * H : nullptr;
+            p.y = (l == 0 ? h1 : y) + (size_t)b0 * T * H;
+            p.hT = hT; p.bar = bar;
+            p.B = nb; p.T = T; p.H = H; p.U = L.U; p.G = L.G;
+            c.begin("lstm_rec", 2.0 * nb * T * 4.0 * H * H, 4.0 * ((double)nb * T * 5 * H + 4.0 * H * H));
+            c.check(launch_lstm_layer(p, c.st), "lstm.rec");
+            c.end();
+        }
+    }
+}
+
+size_t enc_stage_floats(int B, int T) {
+    // largest activation of the encoder: [B][T][64] (== [B][T/2][128])
+    return (size_t)B * ((size_t)T + 16) * 64;
+}
+
+// Encoder.forward (dac.py:69-104): x [B][T][1] -> z channels-last [B][Tz][1024] (or NCT when z_nct)
+int encoder_forward(Ctx& c, const float* x, int B, int T, float* z_out, bool z_nct) {
+    const EncW& e = c.h->enc;
+    size_t stage = enc_stage_floats(B, T);
+    float* buf[3] = {c.alloc<float>(stage), c.alloc<float>(stage), c.alloc<float>(stage)};
+    int cur = 0;
+    int t = sconv(c, e.conv0, x, buf[0], B, T, 1, 1, ConvOpts(), "enc.conv0");
+    c.tap("enc_conv0", buf[0], (size_t)B * t * 64);
+    static const char* blk_names[4] = {"enc_block1", "enc_block2", "enc_block3", "enc_block4"};
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            int tmp = (cur + 1) % 3, nxt = (cur + 2) % 3;
+            residual_unit(c, e.blk[i].res[j], buf[cur], buf[tmp], buf[nxt], B, t);
+            cur = nxt;
+        }
+        ConvOpts o;
+        o.in_snake = &e.blk[i].snake;
+        int nxt = (cur + 1) % 3;
+        t = sconv(c, e.blk[i].down, buf[cur], buf[nxt], B, t, 1, e.blk[i].stride, o, "enc.down");
+        cur = nxt;
+        c.tap(blk_names[i], buf[cur], (size_t)B * t * e.blk[i].down.Cout);
+    }
+    int nxt = (cur + 1) % 3;
+    slstm(c, e.lstm, buf[cur], buf[nxt], B, t);
+    cur = nxt;
+    c.tap("enc_lstm", buf[cur], (size_t)B * t * 1024);
+    ConvOpts o;
+    o.in_snake = &e.snake;
+    o.transposed = z_nct ? 1 : 0;
+    sconv(c, e.conv_out, buf[cur], z_out, B, t, 1, 1, o, "enc.conv_out");
+    return t;
+}
+
+// Decoder.forward (dac.py:131-165): z channels-last [B][Tf][1024] -> y [B][300 Tf][1]
+void decoder_forward(Ctx& c, const float* z, int B, int Tf, float* y) {
+    const DecW& d = c.h->dec;
+    size_t stage = (size_t)B * (size_t)Tf * 28800 + 1024;   // largest: [B][Tf*150][192] == [B][Tf*300][96]
+    size_t first = (size_t)B * Tf * 1536;
+    if (first > stage) stage = first;
+    float* buf[3] = {c.alloc<float>(stage), c.alloc<float>(stage), c.alloc<float>(stage)};
+    int cur = 0;
+    int t = sconv(c, d.conv0, z, buf[0], B, Tf, 1, 1, ConvOpts(), "dec.conv0");
+    c.tap("dec_conv0", buf[0], (size_t)B * t * 1536);
+    slstm(c, d.lstm, buf[0], buf[1], B, t);
+    cur = 1;
+    c.tap("dec_lstm", buf[1], (size_t)B * t * 1536);
+    static const char* dblk_names[4] = {"dec_block1", "dec_block2", "dec_block3", "dec_block4"};
+    for (int i = 0; i < 4; ++i) {
+        // Snake -> SConvTranspose1d(k=2s, stride s) as a K=2 zero-left-padded conv with s*Cout channels
+        ConvOpts o;
+        o.in_snake = &d.blk[i].snake;
+        o.pad_left = 1; o.reflect = 0;
+        int nxt = (cur + 1) % 3;
+        run_conv(c, d.blk[i].up, buf[cur], buf[nxt], B, t, t, o, "dec.up");
+        cur = nxt;
+        t *= d.blk[i].stride;
+        for (int j = 0; j < 3; ++j) {
+            int tmp = (cur + 1) % 3, nx2 = (cur + 2) % 3;
+            residual_unit(c, d.blk[i].res[j], buf[cur], buf[tmp], buf[nx2], B, t);
+            cur = nx2;
+        }
+        c.tap(dblk_names[i], buf[cur], (size_t)B * t * d.blk[i].cout);
+    }
+    ConvOpts o;
+    o.in_snake = &d.snake;
+    o.act = ACT_TANH;
+    sconv(c, d.conv_out, buf[cur], y, B, t, 1, 1, o, "dec.conv_out");
+}
+
+// mel [B][Tm][80] from wave [B][T] (Tm = T/300), preprocess modules/quantize.py:239-242
+float* mel_forward(Ctx& c, const float* wave, int B, int T, int Tm) {
+    const QuantW& q = c.h->qw;
+    float* spec = c.alloc<float>((size_t)B * Tm * SPEC_LD);
+    float* mel = c.alloc<float>((size_t)B * Tm * N_MELS);
+    ConvOpts o;
+    o.stride = HOP;
+    o.pad_left = N_FFT / 2 - (N_FFT - WIN) / 2;   // 1024 - 424 = 600
+    o.pad_right = 600;
+    o.reflect = 1;
+    o.no_bias = true;
+    o.ldy = SPEC_LD;
+    run_conv(c, q.dft, wave, spec, B, T, Tm, o, "mel.dft");
+    if (!c.dry) c.check(launch_mel_from_spec(spec, SPEC_LD, c.W(q.fb), mel, B, Tm, Tm, c.st), "mel.fb");
+    c.tap("mel80", mel, (size_t)B * Tm * N_MELS);
+    return mel;
+}
+
+// StyleEncoder.forward (modules/style_encoder.py:63-81): mel80 [B][Tm][80] -> timbre [B][1024]
+void style_encoder(Ctx& c, const float* mel, int B, int Tm, const int* vlen, float* timbre) {
+    const QuantW& q = c.h->qw;
+    float* a = c.alloc<float>((size_t)B * Tm * 512);
+    float* x = c.alloc<float>((size_t)B * Tm * 512);
+    float* y2 = c.alloc<float>((size_t)B * Tm * 1024);
+    float* qb = c.alloc<float>((size_t)B * Tm * 512);
+    float* kb = c.alloc<float>((size_t)B * Tm * 512);
+    float* vb = c.alloc<float>((size_t)B * Tm * 512);
+    float* ob = c.alloc<float>((size_t)B * Tm * 512);
+    ConvOpts o;
+    o.act = ACT_MISH;
+    run_conv(c, q.spec0, mel, a, B, Tm, Tm, o, "se.spec0");
+    o.valid_len = vlen;
+    run_conv(c, q.spec3, a, x, B, Tm, Tm, o, "se.spec3");
+    for (int i = 0; i < 2; ++i) {
+        ConvOpts g;
+        g.pad_left = 2; g.pad_right = 2; g.reflect = 0;
+        run_conv(c, q.glu[i], x, y2, B, Tm, Tm, g, "se.glu");
+        if (!c.dry) c.check(launch_glu_res(y2, x, B, Tm, 512, i == 1 ? vlen : nullptr, c.st), "se.glu_res");
+    }
+    ConvOpts p;
+    run_conv(c, q.cq, x, qb, B, Tm, Tm, p, "se.q");
+    run_conv(c, q.ck, x, kb, B, Tm, Tm, p, "se.k");
+    run_conv(c, q.cv, x, vb, B, Tm, Tm, p, "se.v");
+    if (!c.dry) c.check(launch_attention(qb, kb, vb, ob, B, Tm, 2, 256, vlen, c.st), "se.attn");
+    ConvOpts r;
+    r.res = x;
+    run_conv(c, q.co, ob, a, B, Tm, Tm, r, "se.o");          // a = x + conv_o(attn)
+    run_conv(c, q.fc, a, y2, B, Tm, Tm, ConvOpts(), "se.fc");
+    if (!c.dry) c.check(launch_mean_pool(y2, timbre, B, Tm, 1024, vlen, c.st), "se.pool");
+}
+
+__global__ void lens_to_frames_kernel(const int64_t* lens, int* out, int B, int hop, int maxf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        long long f = lens[i] / hop;
+        out[i] = (int)(f < maxf ? f : maxf);
+    }
+}
+
+struct QuantOut {
+    float* outs_cl; float* zp_cl; float* zc_cl; float* zr_cl; int Tq;
+};
+
+// FAquantizer.forward_v2 on channels-last z; returns channels-last outputs in workspace
+QuantOut quantizer_forward(Ctx& c, const float* z_cl, const float* wave, int B, int T, int Tz, int n_c,
+                           const float* full_waves, int T_full, const int64_t* wave_lens, float* losses2,
+                           float* timbre, int64_t* codes_p, int64_t* codes_c, int64_t* codes_r, bool want_parts) {
+    const QuantW& q = c.h->qw;
+    const int Tm = T / HOP;
+    const int Tq = Tm < Tz ? Tm : Tz;
+    // --- timbre ---
+    float* mel = mel_forward(c, wave, B, T, Tm);
+    float* timbre_ws = c.alloc<float>((size_t)B * 1024);
+    if (!timbre) timbre = timbre_ws;
+    if (full_waves) {
+        int Tmf = T_full / HOP;
+        float* melf = mel_forward(c, full_waves, B, T_full, Tmf);
+        int* vlen = c.alloc<int>(B);
+        if (!c.dry) {
+            lens_to_frames_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(wave_lens, vlen, B, HOP, Tmf);
+            c.check(cudaGetLastError(), "lens");
+        }
+        style_encoder(c, melf, B, Tmf, vlen, timbre);
+    } else {
+        style_encoder(c, mel, B, Tm, nullptr, timbre);
+    }
+    float* gb = c.alloc<float>((size_t)B * 2048);
+    run_conv(c, q.timbre_linear, timbre, gb, 1, B, B, ConvOpts(), "timbre_linear");
+    c.tap("gamma_beta", gb, (size_t)B * 2048);
+    // --- prosody branch: mel[:, :20] -> melspec_linear -> WN -> melspec_linear2 ---
+    float* px = c.alloc<float>((size_t)B * Tm * 256);
+    float* pin = c.alloc<float>((size_t)B * Tm * 512);
+    float* acts = c.alloc<float>((size_t)B * Tm * 256);
+    float* rs = c.alloc<float>((size_t)B * Tm * 512);
+    float* skip = c.alloc<float>((size_t)B * Tm * 256);
+    float* f0 = c.alloc<float>((size_t)B * Tm * 1024);
+    {
+        ConvW lin = q.mel_lin;
+        ConvOpts o;
+        o.ldx = N_MELS;
+        run_conv(c, lin, mel, px, B, Tm, Tm, o, "melspec_linear");
+        if (!c.dry) c.check_nk(cudaMemsetAsync(skip, 0, sizeof(float) * (size_t)B * Tm * 256, c.st), "wn.zero");
+        for (int i = 0; i < 8; ++i) {
+            sconv(c, q.wn_in[i], px, pin, B, Tm, 1, 1, ConvOpts(), "wn.in");
+            if (!c.dry) c.check(launch_wn_gate(pin, acts, (size_t)B * Tm, 256, c.st), "wn.gate");
+            sconv(c, q.wn_rs[i], acts, rs, B, Tm, 1, 1, ConvOpts(), "wn.rs");
+            if (!c.dry) c.check(launch_wn_update(rs, px, skip, (size_t)B * Tm, 256, i == 7, c.st), "wn.upd");
+        }
+        sconv(c, q.mel_lin2, skip, f0, B, Tm, 1, 1, ConvOpts(), "melspec_linear2");
+        c.tap("f0_input", f0, (size_t)B * Tm * 1024);
+    }
+    // --- fused per-frame VQ + AdaLN ---
+    QuantOut out;
+    out.Tq = Tq;
+    out.outs_cl = c.alloc<float>((size_t)B * Tq * 1024);
+    out.zp_cl = want_parts ? c.alloc<float>((size_t)B * Tq * 1024) : nullptr;
+    out.zc_cl = want_parts ? c.alloc<float>((size_t)B * Tq * 1024) : nullptr;
+    out.zr_cl = want_parts ? c.alloc<float>((size_t)B * Tq * 1024) : nullptr;
+    float* sqerr = c.alloc<float>((size_t)6 * B * Tq);
+    int64_t* cp = c.alloc<int64_t>((size_t)B * Tq);
+    int64_t* cc = c.alloc<int64_t>((size_t)B * 2 * Tq);
+    int64_t* cr = c.alloc<int64_t>((size_t)B * 3 * Tq);
+    float* loss_ws = c.alloc<float>(2);
+    if (c.dry) return out;
+    FaqParams fp;
+    fp.f0 = f0; fp.z = z_cl;
+    for (int i = 0; i < 6; ++i) {
+        const VqW& v = q.vq[i];
+        fp.vq[i] = VqWeights{c.W(v.w_in), c.W(v.b_in), c.W(v.cb), c.W(v.cbn), c.W(v.cbn2), c.W(v.w_out), c.W(v.b_out)};
+    }
+    fp.n_c = n_c;
+    fp.gamma_beta = gb;
+    fp.outs = out.outs_cl; fp.zp = out.zp_cl; fp.zc = out.zc_cl; fp.zr = out.zr_cl;
+    fp.codes_p = codes_p ? codes_p : cp;
+    fp.codes_c = codes_c ? codes_c : cc;
+    fp.codes_r = codes_r ? codes_r : cr;
+    fp.sqerr = sqerr;
+    fp.B = B; fp.Tq = Tq; fp.Tz = Tz; fp.Tf0 = Tm;
+    c.begin("fa_quantize", 2.0 * B * Tq * (3 + n_c + 1) * (8.0 * 1024 * 3), 4.0 * (double)B * Tq * 1024 * (3 + (want_parts ? 3 : 0)));
+    c.check(launch_fa_quantize(fp, c.st), "fa_quantize");
+    c.end();
+    c.check(launch_vq_loss_reduce(sqerr, 6, B, Tq, losses2 ? losses2 : loss_ws, c.st), "vq_loss");
+    return out;
+}
+
+int ensure_ws(fac_handle* h, size_t bytes) {
+    if (bytes <= h->ws_bytes) return FAC_OK;
+    if (h->ws) { cudaDeviceSynchronize(); cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
+    size_t want = bytes + (bytes >> 4) + (1 << 20);
+    cudaError_t e = cudaMalloc(&h->ws, want);
+    if (e != cudaSuccess) {
+        h->err = std::string("workspace cudaMalloc failed: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return FAC_ERR_CUDA;
+    }
+    h->ws_bytes = want;
+    return FAC_OK;
+}
+
+int finish(fac_handle* h, Ctx& c) {
+    if (c.cerr != cudaSuccess) {
+        h->err = std::string("CUDA error at ") + c.where + ": " + cudaGetErrorString(c.cerr);
+        return FAC_ERR_CUDA;
+    }
+    return FAC_OK;
+}
+
+// run `body` twice: size pass, then for real
+template <typename F>
+int two_pass(fac_handle* h, cudaStream_t st, F body) {
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    Ctx dry{h, st, true};
+    body(dry);
+    int rc = ensure_ws(h, dry.off);
+    if (rc != FAC_OK) return rc;
+    h->launches = 0;
+    Ctx c{h, st, false};
+    body(c);
+    return finish(h, c);
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C-ABI
+// ==========================================================================================
+extern "C" {
+
+int fac_abi_version(void) { return 1; }
+
+int fac_create(fac_handle** out, int device) {
+    if (!out) return FAC_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return FAC_ERR_CUDA; }
+    fac_handle* h = new fac_handle();
+    h->device = device;
+    *out = h;
+    return FAC_OK;
+}
+
+int fac_destroy(fac_handle* h) {
+    if (!h) return FAC_OK;
+    cudaSetDevice(h->device);
+    if (h->warena) cudaFree(h->warena);
+    if (h->ws) cudaFree(h->ws);
+    if (h->aa_filter) cudaFree(h->aa_filter);
+    for (float* p : h->rvq_arenas) cudaFree(p);
+    delete h;
+    return FAC_OK;
+}
+
+const char* fac_last_error(const fac_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int fac_load_tensor(fac_handle* h, int module, const char* key, const float* data_host, const int64_t* shape, int ndim) {
+    if (!h || !key || !data_host || module < 0 || module > 2 || ndim < 0 || ndim > 4) return FAC_ERR_INVALID;
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) { if (shape[i] < 0) return FAC_ERR_INVALID; t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+    t.data.assign(data_host, data_host + n);
+    h->host[module][key] = std::move(t);
+    h->have[module] = true;
+    h->finalized = false;
+    return FAC_OK;
+}
+
+int fac_finalize(fac_handle* h) {
+    if (!h) return FAC_ERR_INVALID;
+    h->pack.clear();
+    h->pack.reserve(160u << 20);
+    try {
+        if (h->have[FAC_ENCODER]) pack_encoder(h);
+        if (h->have[FAC_QUANTIZER]) pack_quantizer(h);
+        if (h->have[FAC_DECODER]) pack_decoder(h);
+    } catch (const PackError& e) {
+        h->err = e.msg;
+        return FAC_ERR_STATE;
+    }
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess && h->warena) { cudaDeviceSynchronize(); cudaFree(h->warena); h->warena = nullptr; }
+    size_t n = h->pack.size() + 64;
+    if (e == cudaSuccess) e = cudaMalloc(&h->warena, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->warena, h->pack.data(), h->pack.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->err = std::string("weight upload: ") + cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
+    h->wfloats = n;
+    h->pack.clear(); h->pack.shrink_to_fit();
+    for (int m = 0; m < 3; ++m) h->host[m].clear();
+    h->finalized = true;
+    return FAC_OK;
+}
+
+int fac_encode_frames(int T) {
+    const int rates[4] = {2, 5, 5, 6};
+    int t = T;
+    for (int i = 0; i < 4; ++i) t = conv_out_len(t, 2 * rates[i], rates[i]);
+    return t;
+}
+
+static int check_ready(fac_handle* h, int m) {
+    if (!h) return FAC_ERR_INVALID;
+    if (!h->finalized || !h->have[m]) { h->err = "module weights not loaded/finalized"; return FAC_ERR_STATE; }
+    return FAC_OK;
+}
+
+int fac_encode(fac_handle* h, const float* x, int B, int T, float* z, void* stream) {
+    int rc = check_ready(h, FAC_ENCODER);
+    if (rc) return rc;
+    if (!x || !z || B <= 0 || T <= 0) { h->err = "fac_encode: bad arguments"; return FAC_ERR_INVALID; }
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) { encoder_forward(c, x, B, T, z, true); });
+}
+
+int fac_decode(fac_handle* h, const float* z, int B, int Tf, float* y, void* stream) {
+    int rc = check_ready(h, FAC_DECODER);
+    if (rc) return rc;
+    if (!z || !y || B <= 0 || Tf <= 0) { h->err = "fac_decode: bad arguments"; return FAC_ERR_INVALID; }
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        float* zcl = c.alloc<float>((size_t)B * Tf * LATENT);
+        if (!c.dry) c.check(launch_transpose(z, zcl, B, LATENT, Tf, c.st), "dec.z_transpose");
+        decoder_forward(c, zcl, B, Tf, y);
+    });
+}
+
+int fac_quantize(fac_handle* h, const float* z, const float* wave, int B, int T, int Tz, int n_c,
+                 const float* full_waves, int T_full, const int64_t* wave_lens, float* outs, float* zp, float* zc,
+                 float* zr, float* losses2, float* timbre, int64_t* codes_p, int64_t* codes_c, int64_t* codes_r,
+                 void* stream) {
+    int rc = check_ready(h, FAC_QUANTIZER);
+    if (rc) return rc;
+    if (!z || !wave || !outs || B <= 0 || Tz <= 0 || n_c < 1 || n_c > 2) { h->err = "fac_quantize: bad arguments"; return FAC_ERR_INVALID; }
+    if (T <= N_FFT / 2 || (full_waves && (T_full <= N_FFT / 2 || !wave_lens))) {
+        h->err = "fac_quantize: wave shorter than the STFT reflect padding (1024), as torch.stft";
+        return FAC_ERR_INVALID;
+    }
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        float* zcl = c.alloc<float>((size_t)B * Tz * LATENT);
+        if (!c.dry) c.check(launch_transpose(z, zcl, B, LATENT, Tz, c.st), "q.z_transpose");
+        QuantOut o = quantizer_forward(c, zcl, wave, B, T, Tz, n_c, full_waves, T_full, wave_lens, losses2, timbre,
+                                       codes_p, codes_c, codes_r, zp || zc || zr);
+        if (c.dry) return;
+        c.check(launch_transpose(o.outs_cl, outs, B, o.Tq, LATENT, c.st), "q.outs_T");
+        if (zp) c.check(launch_transpose(o.zp_cl, zp, B, o.Tq, LATENT, c.st), "q.zp_T");
+        if (zc) c.check(launch_transpose(o.zc_cl, zc, B, o.Tq, LATENT, c.st), "q.zc_T");
+        if (zr) c.check(launch_transpose(o.zr_cl, zr, B, o.Tq, LATENT, c.st), "q.zr_T");
+    });
+}
+
+int fac_codec_forward(fac_handle* h, const float* x, int B, int T, int n_c, float* y, int64_t* codes_p,
+                      int64_t* codes_c, int64_t* codes_r, float* timbre, void* stream) {
+    for (int m = 0; m < 3; ++m) { int rc = check_ready(h, m); if (rc) return rc; }
+    if (!x || !y || B <= 0 || T <= N_FFT / 2 || n_c < 1 || n_c > 2) { h->err = "fac_codec_forward: bad arguments"; return FAC_ERR_INVALID; }
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        int Tz = fac_encode_frames(T);
+        float* zcl = c.alloc<float>((size_t)B * Tz * LATENT);
+        encoder_forward(c, x, B, T, zcl, false);
+        QuantOut o = quantizer_forward(c, zcl, x, B, T, Tz, n_c, nullptr, 0, nullptr, nullptr, timbre, codes_p,
+                                       codes_c, codes_r, false);
+        decoder_forward(c, o.outs_cl, B, o.Tq, y);
+    });
+}
+
+int fac_codec_forward_host(fac_handle* h, const float* x_host, int B, int T, int n_c, float* y_host,
+                           int64_t* codes_p_host, int64_t* codes_c_host, int64_t* codes_r_host, void* stream) {
+    for (int m = 0; m < 3; ++m) { int rc = check_ready(h, m); if (rc) return rc; }
+    if (!x_host || !y_host || B <= 0 || T <= N_FFT / 2 || n_c < 1 || n_c > 2) { h->err = "fac_codec_forward_host: bad arguments"; return FAC_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int Tq = 0;
+    int rc = two_pass(h, st, [&](Ctx& c) {
+        int Tz = fac_encode_frames(T);
+        int Tm = T / HOP;
+        Tq = Tm < Tz ? Tm : Tz;
+        float* xd = c.alloc<float>((size_t)B * T);
+        float* yd = c.alloc<float>((size_t)B * Tq * HOP);
+        int64_t* cp = c.alloc<int64_t>((size_t)B * Tq);
+        int64_t* cc = c.alloc<int64_t>((size_t)B * 2 * Tq);
+        int64_t* cr = c.alloc<int64_t>((size_t)B * 3 * Tq);
+        float* zcl = c.alloc<float>((size_t)B * Tz * LATENT);
+        if (!c.dry) c.check_nk(cudaMemcpyAsync(xd, x_host, sizeof(float) * (size_t)B * T, cudaMemcpyHostToDevice, c.st), "h2d");
+        encoder_forward(c, xd, B, T, zcl, false);
+        QuantOut o = quantizer_forward(c, zcl, xd, B, T, Tz, n_c, nullptr, 0, nullptr, nullptr, nullptr, cp, cc, cr, false);
+        decoder_forward(c, o.outs_cl, B, o.Tq, yd);
+        if (c.dry) return;
+        c.check_nk(cudaMemcpyAsync(y_host, yd, sizeof(float) * (size_t)B * Tq * HOP, cudaMemcpyDeviceToHost, c.st), "d2h.y");
+        if (codes_p_host) c.check_nk(cudaMemcpyAsync(codes_p_host, cp, sizeof(int64_t) * (size_t)B * Tq, cudaMemcpyDeviceToHost, c.st), "d2h.cp");
+        if (codes_c_host) c.check_nk(cudaMemcpyAsync(codes_c_host, cc, sizeof(int64_t) * (size_t)B * n_c * Tq, cudaMemcpyDeviceToHost, c.st), "d2h.cc");
+        if (codes_r_host) c.check_nk(cudaMemcpyAsync(codes_r_host, cr, sizeof(int64_t) * (size_t)B * 3 * Tq, cudaMemcpyDeviceToHost, c.st), "d2h.cr");
+    });
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { h->err = std::string("stream sync: ") + cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
+}
+
+int fac_rvq_create(fac_handle* h, int nq, const float* const* in_w, const float* const* in_b, const float* const* out_w,
+                   const float* const* out_b, const float* const* codebook) {
+    if (!h || nq < 1 || nq > 8) return FAC_ERR_INVALID;
+    std::vector<float> pack;
+    RvqSet s;
+    s.nq = nq;
+    for (int q = 0; q < nq; ++q) s.vq[q] = pack_vq_raw(pack, in_w[q], in_b[q], out_w[q], out_b[q], codebook[q]);
+    cudaSetDevice(h->device);
+    float* dev = nullptr;
+    cudaError_t e = cudaMalloc(&dev, (pack.size() + 64) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(dev, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
+    h->rvqs.push_back(s);
+    h->rvq_arenas.push_back(dev);
+    return (int)h->rvqs.size() - 1;
+}
+
+int fac_rvq_forward(fac_handle* h, int rvq_id, const float* x, int B, int T, int x_channels_last, float* quantized_out,
+                    int64_t* indices, float* all_quantized, void* stream) {
+    if (!h || rvq_id < 0 || rvq_id >= (int)h->rvqs.size() || !x || !quantized_out || !indices || B <= 0 || T <= 0) return FAC_ERR_INVALID;
+    const RvqSet& s = h->rvqs[rvq_id];
+    const float* base = h->rvq_arenas[rvq_id];
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        size_t n = (size_t)B * T * 1024;
+        float* xcl = x_channels_last ? nullptr : c.alloc<float>(n);
+        float* qcl = x_channels_last ? nullptr : c.alloc<float>(n);
+        float* acl = (x_channels_last || !all_quantized) ? nullptr : c.alloc<float>(n * s.nq);
+        if (c.dry) return;
+        RvqParams p;
+        if (!x_channels_last) c.check(launch_transpose(x, xcl, B, 1024, T, c.st), "rvq.xT");
+        p.x = x_channels_last ? x : xcl;
+        p.qout = x_channels_last ? quantized_out : qcl;
+        p.allq = all_quantized ? (x_channels_last ? all_quantized : acl) : nullptr;
+        p.idx = indices;
+        p.nq = s.nq; p.B = B; p.T = T;
+        for (int q = 0; q < s.nq; ++q) {
+            const VqW& v = s.vq[q];
+            p.vq[q] = VqWeights{base + v.w_in, base + v.b_in, base + v.cb, base + v.cbn, base + v.cbn2, base + v.w_out, base + v.b_out};
+        }
+        c.check(launch_rvq(p, c.st), "rvq");
+        if (!x_channels_last) {
+            c.check(launch_transpose(qcl, quantized_out, B, T, 1024, c.st), "rvq.qT");
+            if (all_quantized) c.check(launch_transpose(acl, all_quantized, B * s.nq, T, 1024, c.st), "rvq.aT");
+        }
+    });
+}
+
+int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int act, const float* alpha,
+                       const float* beta, float* y, void* stream) {
+    if (!h || !x || !y || B <= 0 || C <= 0 || T <= 0 || (act == 1 && (!alpha || !beta))) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    if (!h->aa_filter) {
+        // kaiser_sinc_filter1d(cutoff=0.25, half_width=0.3, kernel_size=12), alias_free_torch/filter.py:27-58
+        const int ks = 12, half = 6;
+        const double cutoff = 0.25, half_width = 0.3;
+        double delta_f = 4 * half_width;
+        double A = 2.285 * (half - 1) * M_PI * delta_f + 7.95;
+        double beta_k = A > 50.0 ? 0.1102 * (A - 8.7) : (A >= 21.0 ? 0.5842 * std::pow(A - 21, 0.4) + 0.07886 * (A - 21.0) : 0.0);
+        auto i0 = [](double v) { double s = 1, t = 1; for (int k = 1; k < 60; ++k) { t *= (v / (2 * k)) * (v / (2 * k)); s += t; } return s; };
+        float f[12];
+        double sum = 0;
+        double tmp[12];
+        for (int i = 0; i < ks; ++i) {
+            double r = 2.0 * i / (ks - 1) - 1.0;                       // torch.kaiser_window(periodic=False)
+            double w = i0(beta_k * std::sqrt(std::max(0.0, 1 - r * r))) / i0(beta_k);
+            double tm = (i - half) + 0.5;
+            double xx = 2 * cutoff * tm;
+            double sinc = xx == 0 ? 1.0 : std::sin(M_PI * xx) / (M_PI * xx);
+            tmp[i] = 2 * cutoff * w * sinc;
+            sum += tmp[i];
+        }
+        for (int i = 0; i < ks; ++i) f[i] = (float)(tmp[i] / sum);
+        cudaError_t e = cudaMalloc(&h->aa_filter, sizeof(f));
+        if (e == cudaSuccess) e = cudaMemcpy(h->aa_filter, f, sizeof(f), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
+    }
+    cudaError_t e = launch_alias_free_act(x, y, B, C, T, h->aa_filter, act == 1 ? alpha : nullptr, act == 1 ? beta : nullptr,
+                                          (cudaStream_t)stream);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
+}
+
+int fac_debug_conv(fac_handle* h, const float* x, const float* w_host, const float* bias_host, int B, int Tin, int Cin,
+                   int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,
+                   const float* in_alpha_host, const float* out_alpha_host, int act, const float* res, float* y,
+                   int Tout, void* stream) {
+    if (!h || !x || !w_host || !y) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int ldw = (Cout + 3) / 4 * 4;
+    std::vector<float> pk((size_t)K * Cin * ldw + Cout + 2 * Cin + 2 * Cout + 96, 0.f);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int k = 0; k < K; ++k) pk[((size_t)k * Cin + ci) * ldw + co] = w_host[((size_t)co * Cin + ci) * K + k];
+    auto al4 = [](size_t v) { return (v + 3) / 4 * 4; };
+    size_t o_b = (size_t)K * Cin * ldw, o_ia = al4(o_b + Cout), o_iia = al4(o_ia + Cin), o_oa = al4(o_iia + Cin), o_oia = al4(o_oa + Cout);
+    for (int i = 0; i < Cout; ++i) pk[o_b + i] = bias_host ? bias_host[i] : 0.f;
+    for (int i = 0; i < Cin; ++i) { pk[o_ia + i] = in_alpha_host ? in_alpha_host[i] : 1.f; pk[o_iia + i] = 1.0f / (pk[o_ia + i] + 1e-9f); }
+    for (int i = 0; i < Cout; ++i) { pk[o_oa + i] = out_alpha_host ? out_alpha_host[i] : 1.f; pk[o_oia + i] = 1.0f / (pk[o_oa + i] + 1e-9f); }
+    float* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, pk.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
+    ConvParams p;
+    p.x = x; p.y = y; p.w = d; p.bias = bias_host ? d + o_b : nullptr;
+    if (in_alpha_host) { p.in_alpha = d + o_ia; p.in_inv_alpha = d + o_iia; }
+    p.out_act = act;
+    if (out_alpha_host) { p.out_act = ACT_SNAKE; p.out_alpha = d + o_oa; p.out_inv_alpha = d + o_oia; }
+    p.res = res;
+    p.B = B; p.Tin = Tin; p.Cin = Cin; p.Tout = Tout; p.Cout = Cout; p.K = K; p.dil = dil; p.stride = stride;
+    p.pad_left = pad_left; p.pad_right = pad_right; p.pad_reflect = reflect;
+    p.ldw = ldw; p.ldy = Cout; p.ldx = Cin;
+    p.x_bstride = (size_t)Tin * Cin; p.y_bstride = (size_t)Tout * Cout;
+    e = launch_conv(p, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) { h->err = std::string("fac_debug_conv: ") + cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
+}
+
+int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, int B, int T, int H, float* y, void* stream) {
+    if (!h || !x || !w_host || !y || B <= 0 || T <= 0) return FAC_ERR_INVALID;
+    // build a private handle holding only this LSTM, reuse the packing + slstm code path
+    fac_handle tmp;
+    tmp.device = h->device;
+    const char* names[8] = {"weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0", "weight_ih_l1", "weight_hh_l1", "bias_ih_l1", "bias_hh_l1"};
+    for (int i = 0; i < 8; ++i) {
+        HostTensor t;
+        bool mat = (i % 4) < 2;
+        if (mat) t.shape = {4 * H, H}; else t.shape = {4 * H};
+        t.data.assign(w_host[i], w_host[i] + t.numel());
+        tmp.host[0][std::string("l.") + names[i]] = std::move(t);
+    }
+    LstmW L;
+    try { L = pack_lstm(&tmp, 0, "l"); } catch (const PackError& e) { h->err = e.msg; return FAC_ERR_UNSUPPORTED; }
+    cudaSetDevice(h->device);
+    cudaError_t e = cudaMalloc(&tmp.warena, (tmp.pack.size() + 64) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(tmp.warena, tmp.pack.data(), tmp.pack.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    Ctx dry{&tmp, st, true};
+    slstm(dry, L, x, y, B, T);
+    int rc = ensure_ws(&tmp, dry.off);
+    if (rc == FAC_OK) {
+        Ctx c{&tmp, st, false};
+        slstm(c, L, x, y, B, T);
+        rc = finish(&tmp, c);
+        cudaStreamSynchronize(st);
+    }
+    if (rc != FAC_OK) h->err = tmp.err;
+    cudaFree(tmp.warena);
+    if (tmp.ws) cudaFree(tmp.ws);
+    return rc;
+}
+
+int fac_debug_tap(fac_handle* h, const char* name, float* dst, size_t capacity_floats) {
+    if (!h || !name) return FAC_ERR_INVALID;
+    if (!dst) h->taps.erase(name);
+    else h->taps[name] = std::make_pair(dst, capacity_floats);
+    return FAC_OK;
+}
+
+int fac_profile_enable(fac_handle* h, int on) {
+    if (!h) return FAC_ERR_INVALID;
+    h->profiling = on != 0;
+    return FAC_OK;
+}
+
+// Resolves pending event pairs (synchronises the device) and folds them into per-family totals.
+static void profile_collect(fac_handle* h) {
+    if (h->prof.empty()) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& a = h->prof_agg[r.name];
+        a.ms += ms; a.flops += r.flops; a.bytes += r.bytes; a.launches++;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    h->prof.clear();
+}
+
+int fac_profile_reset(fac_handle* h) {
+    if (!h) return FAC_ERR_INVALID;
+    profile_collect(h);
+    h->prof_agg.clear();
+    return FAC_OK;
+}
+
+int fac_profile_get(fac_handle* h, const char* family, double* ms, double* flops, double* bytes, long long* launches) {
+    if (!h || !family) return FAC_ERR_INVALID;
+    profile_collect(h);
+    auto it = h->prof_agg.find(family);
+    if (it == h->prof_agg.end()) { if (ms) *ms = 0; if (flops) *flops = 0; if (bytes) *bytes = 0; if (launches) *launches = 0; return FAC_OK; }
+    if (ms) *ms = it->second.ms;
+    if (flops) *flops = it->second.flops;
+    if (bytes) *bytes = it->second.bytes;
+    if (launches) *launches = it->second.launches;
+    return FAC_OK;
+}
+
+size_t fac_workspace_bytes(const fac_handle* h) { return h ? h->ws_bytes : 0; }
+int fac_last_launch_count(const fac_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

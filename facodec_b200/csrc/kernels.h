@@ -1,0 +1,101 @@
+// Internal kernel launch interfaces (C++ only; the public C-ABI is include/facodec_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fac {
+
+struct ConvParams {
+    const float* x = nullptr;          // [B][Tin][Cin]
+    const float* w = nullptr;          // [K*Cin][ldw]
+    const float* bias = nullptr;       // [Cout] or null
+    const float* in_alpha = nullptr;   // [Cin] snake on input, or null
+    const float* in_inv_alpha = nullptr;
+    const float* out_alpha = nullptr;  // [Cout] when out_act == ACT_SNAKE
+    const float* out_inv_alpha = nullptr;
+    const float* res = nullptr;        // residual, same layout as y, or null
+    const int* valid_len = nullptr;    // [B] rows >= valid_len[b] are written as 0, or null
+    float* y = nullptr;                // [B][Tout][ldy] (or [B][Cout][Tout] when y_transposed)
+    int B = 0, Tin = 0, Cin = 0, Tout = 0, Cout = 0;
+    int K = 1, dil = 1, stride = 1, pad_left = 0, pad_right = 0, pad_reflect = 0;
+    int ldw = 0, ldy = 0, ldx = 0;   // ldx = input row stride (>= Cin)
+    int out_act = 0;
+    int y_transposed = 0;
+    size_t x_bstride = 0, y_bstride = 0;
+};
+cudaError_t launch_conv(const ConvParams& p, cudaStream_t st);
+
+// ---- LSTM recurrence (lstm.cu) -----------------------------------------------------------
+// One nn.LSTM layer over all T steps for up to 32 sequences (dac/model/encodec.py:272-288).
+struct LstmParams {
+    const float* xg = nullptr;    // [B][T][4H] = x W_ih^T + b_ih + b_hh, gate order i,f,g,o
+    const float* whh_p = nullptr; // packed per CTA: [G][H][4U]  (r = gate*U + u)
+    const float* skip = nullptr;  // [B][T][H] added to the output (SLSTM skip) or null
+    float* y = nullptr;           // [B][T][H]
+    float* hT = nullptr;          // scratch [2][H][32]
+    unsigned int* bar = nullptr;  // grid barrier counter (zeroed by the launcher)
+    int B = 0, T = 0, H = 0, U = 0, G = 0;
+};
+cudaError_t launch_lstm_layer(const LstmParams& p, cudaStream_t st);
+int lstm_units_per_cta(int H);  // U such that H % U == 0 and H / U <= resident CTAs
+
+// ---- mel front-end (frontend.cu) -----------------------------------------------------------
+// spec [B][F][ldspec] (re at 2*bin, im at 2*bin+1) -> mel [B][Tm][80] = (log(1e-5 + |.|^2 fb)+4)/4
+cudaError_t launch_mel_from_spec(const float* spec, int ldspec, const float* fb /*[1025][80]*/, float* mel,
+                                 int B, int F, int Tm, cudaStream_t st);
+
+// ---- quantizer-side kernels (quant.cu) -----------------------------------------------------
+struct VqWeights {           // one dac/nn/quantize.py VectorQuantize, folded
+    const float* w_in;       // [8][1024]
+    const float* b_in;       // [8]
+    const float* cb;         // [1024][8] raw codebook
+    const float* cbn;        // [1024][8] F.normalize(codebook)
+    const float* cbn2;       // [1024] sum(cbn^2)
+    const float* w_out;      // [8][1024]  (transposed for coalescing: w_out_t[k][c])
+    const float* b_out;      // [1024]
+};
+struct FaqParams {
+    const float* f0 = nullptr;   // [B][Tq][1024] prosody features (channels-last)
+    const float* z = nullptr;    // [B][Tz][1024] encoder latents (channels-last)
+    VqWeights vq[6];             // prosody, content0, content1, residual0..2
+    int n_c = 1;
+    const float* gamma_beta = nullptr;  // [B][2048] timbre_linear(timbre)
+    float* outs = nullptr;       // [B][Tq][1024]
+    float* zp = nullptr, *zc = nullptr, *zr = nullptr;  // [B][Tq][1024] each (may be null)
+    int64_t* codes_p = nullptr;  // [B][1][Tq]
+    int64_t* codes_c = nullptr;  // [B][n_c][Tq]
+    int64_t* codes_r = nullptr;  // [B][3][Tq]
+    float* sqerr = nullptr;      // [6][B*Tq] per-frame sum (z_e - z_q)^2
+    int B = 0, Tq = 0, Tz = 0, Tf0 = 0;   // Tz / Tf0 = frames per utterance of z / f0 (>= Tq)
+};
+cudaError_t launch_fa_quantize(const FaqParams& p, cudaStream_t st);
+// losses[0] = commitment, losses[1] = codebook (identical in forward), from sqerr
+cudaError_t launch_vq_loss_reduce(const float* sqerr, int nq, int B, int Tq, float* losses2, cudaStream_t st);
+
+// generic residual VQ over [N frames][D] with D == 1024, codebook_dim == 8 (quantize/rvq.py)
+struct RvqParams {
+    const float* x = nullptr;    // [B][T][1024] channels-last
+    VqWeights vq[8];
+    int nq = 0;
+    float* qout = nullptr;       // [B][T][1024] quantized_out
+    float* allq = nullptr;       // [nq][B][T][1024] or null
+    int64_t* idx = nullptr;      // [nq][B][T]
+    int B = 0, T = 0;
+};
+cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st);
+
+// elementwise / small ops
+cudaError_t launch_transpose(const float* in, float* out, int B, int R, int C, cudaStream_t st);  // [B][R][C]->[B][C][R]
+cudaError_t launch_wn_gate(const float* xin, float* acts, size_t n_rows, int hidden, cudaStream_t st);  // tanh(a)*sigmoid(b)
+cudaError_t launch_wn_update(const float* rs, float* x, float* out, size_t n_rows, int hidden, int last, cudaStream_t st);
+cudaError_t launch_glu_res(const float* y, float* x, int B, int T, int C, const int* valid_len, cudaStream_t st);  // x = x + y1*sig(y2) (masked)
+cudaError_t launch_attention(const float* q, const float* k, const float* v, float* o, int B, int T, int heads,
+                             int dk, const int* valid_len, cudaStream_t st);
+cudaError_t launch_mean_pool(const float* x, float* out, int B, int T, int C, const int* valid_len, cudaStream_t st);
+cudaError_t launch_fill_u32(unsigned int* p, unsigned int v, size_t n, cudaStream_t st);
+
+// alias-free activation (alias_free_torch/act.py:24-29): up x2 -> snake-beta/identity -> down x2
+cudaError_t launch_alias_free_act(const float* x, float* y, int B, int C, int T, const float* filt12,
+                                  const float* alpha, const float* inv_beta, cudaStream_t st);
+
+}  // namespace fac

@@ -1,0 +1,437 @@
+"""Reference-facing call surface:  model.encoder(x) / model.quantizer(z, wave, ...) /
+model.decoder(z)  on the Munch returned by build_model (reference modules/commons.py:283-348),
+backed by the C-ABI library (include/facodec_b200.h).  PyTorch here is plumbing only: it owns
+the device tensors and the CUDA stream; all arithmetic happens in libfacodec_b200.so.
+
+Drop-in contract:
+* ``Encoder`` / ``FAquantizer`` / ``Decoder`` are nn.Modules whose ``state_dict()`` /
+  ``load_state_dict()`` use the reference's key names (legacy weight-norm ``weight_g`` /
+  ``weight_v`` included), so reference checkpoints load unchanged (reconstruct.py:30-34).
+* forward signatures and returns are those of dac/model/dac.py:103-104, :164-165 and
+  modules/quantize.py:375-454 (forward_v2).  Inference only (eval mode, no autograd): the
+  training-time branches (quantizer dropout, random residual mask) are out of scope.
+* There is no CPU fallback: CPU tensors or a missing library raise.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import _lib, synth
+
+MOD_ENCODER, MOD_QUANTIZER, MOD_DECODER = 0, 1, 2
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One fac_handle (one CUDA device).  The three modules of a build_model() share it so that
+    codec_forward can run encoder -> quantizer -> decoder inside one C call."""
+
+    def __init__(self):
+        self.L = _lib.load()
+        self.handle = None
+        self.device_index = None
+        self.loaded_version = {}
+        self.modules = {}
+
+    def _ensure(self, device):
+        if device.type != "cuda":
+            raise _lib.FacError("facodec_b200 runs on CUDA tensors only (no CPU fallback); got " + str(device))
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self.handle is None:
+            h = ctypes.c_void_p()
+            rc = self.L.fac_create(ctypes.byref(h), idx)
+            if rc < 0:
+                raise _lib.FacError(f"fac_create(device={idx}) failed with status {rc}")
+            self.handle, self.device_index = h, idx
+        elif idx != self.device_index:
+            raise _lib.FacError("engine is bound to cuda:%d, got cuda:%d" % (self.device_index, idx))
+
+    def register(self, module_id, module):
+        self.modules[module_id] = module
+
+    def sync_weights(self, device):
+        """(Re)uploads the weights of every registered module whose parameters changed."""
+        self._ensure(device)
+        dirty = [m for m, mod in self.modules.items() if self.loaded_version.get(m) != mod._version_tag()]
+        if not dirty:
+            return
+        # fac_finalize repacks everything it holds, so push all registered modules again
+        for m, mod in self.modules.items():
+            for key, t in mod.state_dict().items():
+                t = t.detach().to("cpu", torch.float32).contiguous()
+                shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                rc = self.L.fac_load_tensor(self.handle, m, key.encode(), _ptr(t), shape, t.dim())
+                _lib.check(self.handle, rc, "fac_load_tensor(%s)" % key)
+        _lib.check(self.handle, self.L.fac_finalize(self.handle), "fac_finalize")
+        for m, mod in self.modules.items():
+            self.loaded_version[m] = mod._version_tag()
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                self.L.fac_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class _RefKeyModule(nn.Module):
+    """nn.Module whose parameters are stored flat but exposed under the reference's dotted keys."""
+
+    _module_id = None
+    _buffer_keys = ()
+
+    def __init__(self, init_sd, engine=None):
+        super().__init__()
+        self._keys = list(init_sd.keys())
+        self._p = nn.ParameterDict()
+        for k, v in init_sd.items():
+            if k in self._buffer_keys:
+                self.register_buffer(self._safe(k), v.clone(), persistent=True)
+            else:
+                self._p[self._safe(k)] = nn.Parameter(v.clone(), requires_grad=False)
+        self._load_count = 0
+        self._engine = engine if engine is not None else Engine()
+        self._engine.register(self._module_id, self)
+
+    @staticmethod
+    def _safe(k):
+        return k.replace(".", "/")
+
+    def _get(self, k):
+        s = self._safe(k)
+        return self._p[s] if s in self._p else getattr(self, s)
+
+    def _version_tag(self):
+        return (self._load_count,) + tuple(self._get(k)._version for k in self._keys)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False, **kw):
+        out = destination if destination is not None else OrderedDict()
+        for k in self._keys:
+            t = self._get(k)
+            out[prefix + k] = t if keep_vars else t.detach()
+        return out
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        missing = [k for k in self._keys if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._keys]
+        if strict and (missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict for %s: missing %s unexpected %s"
+                               % (type(self).__name__, missing[:5], unexpected[:5]))
+        with torch.no_grad():
+            for k in self._keys:
+                if k in state_dict:
+                    dst = self._get(k)
+                    src = state_dict[k]
+                    if tuple(src.shape) != tuple(dst.shape):
+                        raise RuntimeError("size mismatch for %s: %s vs %s" % (k, tuple(src.shape), tuple(dst.shape)))
+                    dst.copy_(src)
+        self._load_count += 1
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def _prep(self, *tensors):
+        if self.training:
+            raise NotImplementedError("facodec_b200 implements the eval-mode forward only; call .eval()")
+        dev = tensors[0].device
+        self._engine.sync_weights(dev)
+        return self._engine.L, self._engine.handle
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class Encoder(_RefKeyModule):
+    """dac/model/dac.py:69-104 Encoder(d_model=64, strides=[2,5,5,6], d_latent=1024, causal=True, lstm=2)."""
+    _module_id = MOD_ENCODER
+
+    def __init__(self, d_model=64, strides=(2, 5, 5, 6), d_latent=1024, causal=True, lstm=2, engine=None):
+        if (d_model, tuple(strides), d_latent, bool(causal), lstm) != (64, (2, 5, 5, 6), 1024, True, 2):
+            raise NotImplementedError("only the configs/config.yml encoder geometry is built")
+        super().__init__(synth.synth_encoder(1), engine)
+        self.enc_dim = 1024
+
+    def forward(self, x):
+        L, h = self._prep(x)
+        x = _f32c(x)
+        B, C, T = x.shape
+        assert C == 1, "encoder expects [B,1,T]"
+        z = torch.empty(B, 1024, L.fac_encode_frames(T), device=x.device, dtype=torch.float32)
+        _lib.check(h, L.fac_encode(h, _ptr(x), B, T, _ptr(z), _stream()), "fac_encode")
+        return z
+
+
+class Decoder(_RefKeyModule):
+    """dac/model/dac.py:131-165 Decoder(1024, 1536, [6,5,5,2], causal=True, lstm=2)."""
+    _module_id = MOD_DECODER
+
+    def __init__(self, input_channel=1024, channels=1536, rates=(6, 5, 5, 2), d_out=1, causal=True, lstm=2, engine=None):
+        if (input_channel, channels, tuple(rates), d_out, bool(causal), lstm) != (1024, 1536, (6, 5, 5, 2), 1, True, 2):
+            raise NotImplementedError("only the configs/config.yml decoder geometry is built")
+        super().__init__(synth.synth_decoder(3), engine)
+
+    def forward(self, z):
+        L, h = self._prep(z)
+        z = _f32c(z)
+        B, C, Tf = z.shape
+        assert C == 1024
+        y = torch.empty(B, 1, Tf * 300, device=z.device, dtype=torch.float32)
+        _lib.check(h, L.fac_decode(h, _ptr(z), B, Tf, _ptr(y), _stream()), "fac_decode")
+        return y
+
+
+class FAquantizer(_RefKeyModule):
+    """modules/quantize.py:156-454 FAquantizer(..., separate_prosody_encoder=True, timbre_norm=True);
+    forward == forward_v2 (:375-454)."""
+    _module_id = MOD_QUANTIZER
+    _buffer_keys = ("to_mel.spectrogram.window", "to_mel.mel_scale.fb")
+
+    def __init__(self, in_dim=1024, n_p_codebooks=1, n_c_codebooks=2, n_t_codebooks=2, n_r_codebooks=3,
+                 codebook_size=1024, codebook_dim=8, quantizer_dropout=0.5, causal=True,
+                 separate_prosody_encoder=True, timbre_norm=True, engine=None):
+        cfg = (in_dim, n_p_codebooks, n_c_codebooks, n_r_codebooks, codebook_size, codebook_dim, bool(causal),
+               bool(separate_prosody_encoder), bool(timbre_norm))
+        if cfg != (1024, 1, 2, 3, 1024, 8, True, True, True):
+            raise NotImplementedError("only the configs/config.yml quantizer geometry is built")
+        super().__init__(synth.synth_quantizer(2), engine)
+        self.hop_length = 300
+        self.is_timbre_norm = True
+
+    def forward(self, x, wave_segments, n_c=1, n_t=2, full_waves=None, wave_lens=None, return_codes=False):
+        L, h = self._prep(x)
+        x = _f32c(x)
+        wave = _f32c(wave_segments)
+        B, C, Tz = x.shape
+        T = wave.shape[-1]
+        Tq = min(T // 300, Tz)
+        dev = x.device
+        outs = torch.empty(B, 1024, Tq, device=dev)
+        zp, zc, zr = (torch.empty(B, 1024, Tq, device=dev) for _ in range(3))
+        losses = torch.empty(2, device=dev)
+        timbre = torch.empty(B, 1024, device=dev)
+        cp = torch.empty(B, 1, Tq, device=dev, dtype=torch.int64)
+        cc = torch.empty(B, n_c, Tq, device=dev, dtype=torch.int64)
+        cr = torch.empty(B, 3, Tq, device=dev, dtype=torch.int64)
+        fw = wl = None
+        tfull = 0
+        if full_waves is not None:
+            fw = _f32c(full_waves)
+            wl = wave_lens.detach().to(dev, torch.int64).contiguous()
+            tfull = fw.shape[-1]
+        rc = L.fac_quantize(h, _ptr(x), _ptr(wave), B, T, Tz, int(n_c), _ptr(fw), tfull, _ptr(wl), _ptr(outs), _ptr(zp),
+                            _ptr(zc), _ptr(zr), _ptr(losses), _ptr(timbre), _ptr(cp), _ptr(cc), _ptr(cr), _stream())
+        _lib.check(h, rc, "fac_quantize")
+        quantized = [zp, zc, zr]
+        if return_codes:
+            return outs, quantized, losses[0], losses[1], timbre, [cp, cc, cr]
+        return outs, quantized, losses[0], losses[1], timbre
+
+    forward_v2 = forward
+
+
+class Munch(dict):
+    """Attribute dict (the reference returns munch.Munch from build_model)."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class Codec:
+    """reconstruct.py:56-61 as one C call: encoder -> quantizer(n_c) -> decoder, latents resident."""
+
+    def __init__(self, model):
+        self.model = model
+        self.engine = model.encoder._engine
+
+    def forward(self, x, n_c=2):
+        """x [B,1,T] on the GPU -> (y [B,1,T'], [codes_p, codes_c, codes_r], timbre)."""
+        e = self.engine
+        for m in (self.model.encoder, self.model.quantizer, self.model.decoder):
+            if m.training:
+                raise NotImplementedError("eval mode only")
+        e.sync_weights(x.device)
+        x = _f32c(x)
+        B, _, T = x.shape
+        Tq = min(T // 300, e.L.fac_encode_frames(T))
+        dev = x.device
+        y = torch.empty(B, 1, Tq * 300, device=dev)
+        cp = torch.empty(B, 1, Tq, device=dev, dtype=torch.int64)
+        cc = torch.empty(B, n_c, Tq, device=dev, dtype=torch.int64)
+        cr = torch.empty(B, 3, Tq, device=dev, dtype=torch.int64)
+        timbre = torch.empty(B, 1024, device=dev)
+        rc = e.L.fac_codec_forward(e.handle, _ptr(x), B, T, n_c, _ptr(y), _ptr(cp), _ptr(cc), _ptr(cr), _ptr(timbre), _stream())
+        _lib.check(e.handle, rc, "fac_codec_forward")
+        return y, [cp, cc, cr], timbre
+
+    def forward_host(self, x_host, n_c=2, out=None):
+        """End-to-end with HOST tensors (pinned recommended): H2D, forward, D2H inside the call.
+        x_host [B,1,T] float32 CPU -> (y_host [B,1,T'], [codes_p, codes_c, codes_r]) CPU tensors."""
+        e = self.engine
+        dev = torch.device("cuda", torch.cuda.current_device() if e.device_index is None else e.device_index)
+        e.sync_weights(dev)
+        assert x_host.device.type == "cpu" and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        B, _, T = x_host.shape
+        Tq = min(T // 300, e.L.fac_encode_frames(T))
+        if out is None:
+            pin = torch.cuda.is_available()
+            out = (torch.empty(B, 1, Tq * 300, pin_memory=pin),
+                   torch.empty(B, 1, Tq, dtype=torch.int64, pin_memory=pin),
+                   torch.empty(B, n_c, Tq, dtype=torch.int64, pin_memory=pin),
+                   torch.empty(B, 3, Tq, dtype=torch.int64, pin_memory=pin))
+        y, cp, cc, cr = out
+        with torch.cuda.device(dev):
+            rc = e.L.fac_codec_forward_host(e.handle, _ptr(x_host), B, T, n_c, _ptr(y), _ptr(cp), _ptr(cc), _ptr(cr), _stream())
+        _lib.check(e.handle, rc, "fac_codec_forward_host")
+        return y, [cp, cc, cr]
+
+    def launch_count(self):
+        return self.engine.L.fac_last_launch_count(self.engine.handle)
+
+
+def build_model(args=None, stage="codec"):
+    """Mirror of modules/commons.py:283-348 build_model(args, stage='codec') for the hot-path
+    modules: returns Munch(encoder, quantizer, decoder) (discriminator / fa_predictors are training-only
+    and out of scope).  ``args`` may be the reference's recursive_munch(config['model_params']) or None."""
+    if stage != "codec":
+        raise NotImplementedError("only stage='codec' is built")
+
+    def g(obj, name, default):
+        if obj is None:
+            return default
+        return obj[name] if isinstance(obj, dict) and name in obj else getattr(obj, name, default)
+
+    dac = g(args, "DAC", None)
+    eng = Engine()
+    encoder = Encoder(d_model=g(dac, "encoder_dim", 64), strides=tuple(g(dac, "encoder_rates", (2, 5, 5, 6))),
+                      d_latent=1024, causal=g(args, "causal", True), lstm=g(args, "lstm", 2), engine=eng)
+    quantizer = FAquantizer(in_dim=1024, n_p_codebooks=1, n_c_codebooks=g(args, "n_c_codebooks", 2), n_t_codebooks=2,
+                            n_r_codebooks=3, codebook_size=1024, codebook_dim=8, quantizer_dropout=0.5,
+                            causal=g(args, "causal", True),
+                            separate_prosody_encoder=g(args, "separate_prosody_encoder", True),
+                            timbre_norm=g(args, "timbre_norm", True), engine=eng)
+    decoder = Decoder(input_channel=1024, channels=g(dac, "decoder_dim", 1536),
+                      rates=tuple(g(dac, "decoder_rates", (6, 5, 5, 2))), causal=g(args, "causal", True),
+                      lstm=g(args, "lstm", 2), engine=eng)
+    return Munch(encoder=encoder, quantizer=quantizer, decoder=decoder)
+
+
+class ResidualVQ(nn.Module):
+    """quantize/rvq.py:12-87 ResidualVQ over quantize/fvq.py:16-116 FactorizedVectorQuantize
+    (eval forward), dim=1024 -> codebook_dim=8, 2**codebook_size entries (must be 1024).
+    state_dict keys follow the reference: layers.{i}.in_proj.weight_g/_v/bias, out_proj..., _codebook.weight."""
+
+    def __init__(self, *, num_quantizers, codebook_size=10, dim=1024, codebook_dim=8, commitment=0.25, seed=0, **kw):
+        super().__init__()
+        if dim != 1024 or codebook_dim != 8 or 2 ** int(codebook_size) != 1024 or not (1 <= num_quantizers <= 8):
+            raise NotImplementedError("built for dim=1024, codebook_dim=8, 2**10 entries, <= 8 quantizers")
+        self.num_quantizers = num_quantizers
+        g = synth._Gen(1000 + seed)
+        sd = OrderedDict()
+        for i in range(num_quantizers):
+            tmp = {}
+            synth._conv(g, tmp, "in_proj", 8, 1024, 1)
+            synth._conv(g, tmp, "out_proj", 1024, 8, 1)
+            for k, v in tmp.items():
+                v = v.squeeze(-1) if k.endswith("weight_v") else (v.reshape(-1, 1) if k.endswith("weight_g") else v)
+                sd[f"layers.{i}.{k}"] = v
+            sd[f"layers.{i}._codebook.weight"] = g.normal((1024, 8))
+        self._keys = list(sd.keys())
+        self._p = nn.ParameterDict({k.replace(".", "/"): nn.Parameter(v, requires_grad=False) for k, v in sd.items()})
+        self._engine = Engine()
+        self._rvq_id = None
+        self._tag = None
+
+    def state_dict(self, *a, prefix="", **kw):
+        return OrderedDict((prefix + k, self._p[k.replace(".", "/")].detach()) for k in self._keys)
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        with torch.no_grad():
+            for k in self._keys:
+                self._p[k.replace(".", "/")].copy_(sd[k])
+        self._tag = None
+
+    def _folded(self, i, name):
+        v = self._p[f"layers/{i}/{name}/weight_v"].detach().cpu().double()
+        g = self._p[f"layers/{i}/{name}/weight_g"].detach().cpu().double()
+        # weight_norm(nn.Linear) default dim=0: per output row
+        w = (v * (g / v.norm(dim=1, keepdim=True))).float().contiguous()
+        return w
+
+    def _sync(self, device):
+        e = self._engine
+        e._ensure(device)
+        tag = tuple(p._version for p in self._p.values())
+        if self._tag == tag:
+            return
+        n = self.num_quantizers
+        keep = []
+
+        def arr(ts):
+            keep.extend(ts)
+            return (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+        in_w = arr([self._folded(i, "in_proj") for i in range(n)])
+        in_b = arr([self._p[f"layers/{i}/in_proj/bias"].detach().cpu().contiguous() for i in range(n)])
+        out_w = arr([self._folded(i, "out_proj") for i in range(n)])
+        out_b = arr([self._p[f"layers/{i}/out_proj/bias"].detach().cpu().contiguous() for i in range(n)])
+        cb = arr([self._p[f"layers/{i}/_codebook/weight"].detach().cpu().contiguous() for i in range(n)])
+        rid = e.L.fac_rvq_create(e.handle, n, in_w, in_b, out_w, out_b, cb)
+        _lib.check(e.handle, rid, "fac_rvq_create")
+        self._rvq_id, self._tag = rid, tag
+
+    def forward(self, x, n_quantizers=None, channels_last=False, return_all=True):
+        """x [B,1024,T] -> (quantized_out, indices [N,B,T], losses [N] (zeros in eval), all_quantized [N,B,1024,T])."""
+        if self.training:
+            raise NotImplementedError("eval mode only")
+        if n_quantizers is not None and n_quantizers != self.num_quantizers:
+            raise NotImplementedError("n_quantizers must equal num_quantizers")
+        self._sync(x.device)
+        e = self._engine
+        x = _f32c(x)
+        if channels_last:
+            B, T, D = x.shape
+        else:
+            B, D, T = x.shape
+        n = self.num_quantizers
+        q = torch.empty_like(x)
+        idx = torch.empty(n, B, T, device=x.device, dtype=torch.int64)
+        allq = torch.empty((n,) + tuple(x.shape), device=x.device) if return_all else None
+        rc = e.L.fac_rvq_forward(e.handle, self._rvq_id, _ptr(x), B, T, 1 if channels_last else 0, _ptr(q), _ptr(idx),
+                                 _ptr(allq), _stream())
+        _lib.check(e.handle, rc, "fac_rvq_forward")
+        return q, idx, torch.zeros(n, device=x.device), allq
+
+
+class Activation1d(nn.Module):
+    """alias_free_torch/act.py:7-29 Activation1d(activation, up_ratio=2, down_ratio=2, 12, 12) with
+    activation = SnakeBeta(alpha_logscale) (modules/quantize.py:29-88) or identity (activation=None)."""
+
+    def __init__(self, channels=None, alpha_logscale=True, identity=False):
+        super().__init__()
+        self.identity = identity
+        self.alpha_logscale = alpha_logscale
+        if not identity:
+            init = torch.zeros(channels) if alpha_logscale else torch.ones(channels)
+            self.alpha = nn.Parameter(init.clone(), requires_grad=False)
+            self.beta = nn.Parameter(init.clone(), requires_grad=False)
+        self._engine = Engine()
+
+    def forward(self, x):
+        e = self._engine
+        e._ensure(x.device)
+        x = _f32c(x)
+        B, C, T = x.shape
+        y = torch.empty_like(x)
+        a = b = None
+        if not self.identity:
+            a = (torch.exp(self.alpha) if self.alpha_logscale else self.alpha).detach().to(x.device, torch.float32).contiguous()
+            b = (torch.exp(self.beta) if self.alpha_logscale else self.beta).detach().to(x.device, torch.float32).contiguous()
+        rc = e.L.fac_alias_free_act(e.handle, _ptr(x), B, C, T, 0 if self.identity else 1, _ptr(a), _ptr(b), _ptr(y), _stream())
+        _lib.check(e.handle, rc, "fac_alias_free_act")
+        return y

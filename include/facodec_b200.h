@@ -1,0 +1,143 @@
+/* facodec_b200 -- C-ABI of the B200-native FAcodec encode -> quantize -> decode hot path.
+ *
+ * The reference (Plachtaa/FAcodec) has no FFI layer: its boundary is the Python nn.Module call
+ * surface  model.encoder(x) / model.quantizer(z, wave, ...) / model.decoder(z)  on the Munch
+ * returned by build_model (modules/commons.py:283-348).  Each entry point below names the
+ * reference interface it replaces; facodec_b200/modules.py is the thin ctypes shim that puts the
+ * nn.Module surface back on top (INTEGRATION.md shows the binding).
+ *
+ * Conventions: plain pointers and sizes only; every tensor argument is a DEVICE pointer in the
+ * reference's own layout (float32 [B, C, T] contiguous, int64 codes) unless the name ends in
+ * _host; outputs are caller-allocated; `stream` is a cudaStream_t (0 = legacy default stream);
+ * calls on one handle must be serialised by the caller.  Every function returns 0 on success or
+ * a negative fac_status; fac_last_error() gives the text.  No exceptions cross the ABI.
+ * Scratch memory is a grow-only device arena owned by the handle (fac_workspace_bytes).
+ */
+#ifndef FACODEC_B200_H
+#define FACODEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fac_handle fac_handle;
+
+enum fac_status {
+    FAC_OK = 0,
+    FAC_ERR_INVALID = -1,   /* bad argument / shape */
+    FAC_ERR_STATE = -2,     /* weights missing or not finalized */
+    FAC_ERR_CUDA = -3,      /* CUDA runtime error (text in fac_last_error) */
+    FAC_ERR_UNSUPPORTED = -4
+};
+
+enum fac_module { FAC_ENCODER = 0, FAC_QUANTIZER = 1, FAC_DECODER = 2 };
+
+/* Library/ABI version (bumped on any signature change). */
+int fac_abi_version(void);
+
+/* Create / destroy an engine bound to CUDA device `device`. */
+int fac_create(fac_handle** out, int device);
+int fac_destroy(fac_handle* h);
+const char* fac_last_error(const fac_handle* h);
+
+/* Checkpoint loading.  Replaces  model[key].load_state_dict(ckpt[key])  (reconstruct.py:30-34,
+ * modules/commons.py:446-471): feed every tensor of the reference state_dict of `module`
+ * (reference key names, e.g. "block.1.block.0.block.1.conv.conv.weight_v"), HOST float32 data,
+ * then call fac_finalize once.  fac_finalize folds weight-norm (g * v / ||v||, encodec.py:42-51),
+ * Snake 1/(alpha+1e-9), LSTM biases, normalises the VQ codebooks, builds the STFT basis from
+ * "to_mel.spectrogram.window", packs everything into kernel layouts and uploads it.
+ * Modules whose tensors were never loaded stay unavailable (their entry points return
+ * FAC_ERR_STATE). */
+int fac_load_tensor(fac_handle* h, int module, const char* key, const float* data_host,
+                    const int64_t* shape, int ndim);
+int fac_finalize(fac_handle* h);
+
+/* Replicated deployment (one process per GPU): rank 0 reads the checkpoint and broadcasts the raw
+ * tensors as ONE flat fp32 buffer (ncclBroadcast through torch.distributed, see
+ * facodec_b200/distributed.py); every rank then runs fac_load_tensor + fac_finalize locally.
+ * There is no collective on the hot path. */
+
+/* model.encoder(x): dac/model/dac.py:103-104 Encoder.forward.
+ * x [B,1,T] -> z [B,1024,ceil(T/300)]. */
+int fac_encode(fac_handle* h, const float* x, int B, int T, float* z, void* stream);
+int fac_encode_frames(int T);   /* ceil-div chain of the strided convs = output frames */
+
+/* model.quantizer(z, wave, n_c, n_t, full_waves, wave_lens, return_codes):
+ * modules/quantize.py:375-454 FAquantizer.forward_v2 in eval mode.
+ * z [B,1024,Tz], wave [B,1,T]; Tq = min(T/300, Tz).  full_waves [B,T_full] + wave_lens[B]
+ * (int64, device) may be NULL (then the timbre comes from `wave`).  Outputs (any of zp/zc/zr/
+ * codes_* may be NULL): outs, zp, zc, zr [B,1024,Tq]; losses2[2] = {commitment, codebook};
+ * timbre [B,1024]; codes_p [B,1,Tq], codes_c [B,n_c,Tq], codes_r [B,3,Tq] int64. */
+int fac_quantize(fac_handle* h, const float* z, const float* wave, int B, int T, int Tz, int n_c,
+                 const float* full_waves, int T_full, const int64_t* wave_lens,
+                 float* outs, float* zp, float* zc, float* zr, float* losses2, float* timbre,
+                 int64_t* codes_p, int64_t* codes_c, int64_t* codes_r, void* stream);
+
+/* model.decoder(z): dac/model/dac.py:164-165 Decoder.forward.  z [B,1024,Tf] -> y [B,1,300*Tf]. */
+int fac_decode(fac_handle* h, const float* z, int B, int Tf, float* y, void* stream);
+
+/* reconstruct.py:56-61 in one call, device buffers: encoder -> quantizer(n_c) -> decoder with the
+ * latents kept channels-last on the device (no boundary transposes).  codes_* / timbre may be NULL. */
+int fac_codec_forward(fac_handle* h, const float* x, int B, int T, int n_c, float* y,
+                      int64_t* codes_p, int64_t* codes_c, int64_t* codes_r, float* timbre, void* stream);
+
+/* Same, HOST buffers (pinned recommended): H2D of x, forward, D2H of y + codes, stream sync. */
+int fac_codec_forward_host(fac_handle* h, const float* x_host, int B, int T, int n_c, float* y_host,
+                           int64_t* codes_p_host, int64_t* codes_c_host, int64_t* codes_r_host, void* stream);
+
+/* quantize/rvq.py:27-75 ResidualVQ.forward (eval) over quantize/fvq.py FactorizedVectorQuantize,
+ * dim=1024, codebook_dim=8, 2^10 entries (BASELINE configs[3]).  Parameters are passed directly
+ * (already weight-normed, HOST): per quantizer q: in_w [8,1024], in_b [8], out_w [1024,8],
+ * out_b [1024], codebook [1024,8].  fac_rvq_create returns an id usable with fac_rvq_forward:
+ * x [B,1024,T] -> quantized_out [B,1024,T], indices [nq,B,T] int64, all_quantized [nq,B,1024,T]
+ * (may be NULL).  x_channels_last != 0 means x / outputs are [B,T,1024] (no transposes). */
+int fac_rvq_create(fac_handle* h, int nq, const float* const* in_w, const float* const* in_b,
+                   const float* const* out_w, const float* const* out_b, const float* const* codebook);
+int fac_rvq_forward(fac_handle* h, int rvq_id, const float* x, int B, int T, int x_channels_last,
+                    float* quantized_out, int64_t* indices, float* all_quantized, void* stream);
+
+/* alias_free_torch/act.py:24-29 Activation1d.forward with up/down ratio 2, 12-tap Kaiser-sinc
+ * filters (filter.py:27-58).  x, y [B,C,T].  act: 0 = identity, 1 = SnakeBeta with per-channel
+ * alpha / beta given as already-exponentiated values (modules/quantize.py:29-79). */
+int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int act,
+                       const float* alpha, const float* beta, float* y, void* stream);
+
+/* Kernel-level test hooks (used by tests/test_gpu_kernels.py; not part of the drop-in surface).
+ * fac_debug_conv runs the generic channels-last conv kernel on one layer: x [B,Tin,Cin] and
+ * y [B,Tout,Cout] are DEVICE channels-last buffers, w_host is a HOST nn.Conv1d weight
+ * [Cout,Cin,K] (already weight-normed), bias/in_alpha/out_alpha HOST vectors or NULL,
+ * res a DEVICE tensor like y or NULL; act: 0 none, 1 tanh, 2 mish.
+ * fac_debug_slstm runs SLSTM (2 layers + skip) on x [B,T,H] DEVICE with HOST nn.LSTM weights
+ * w[8] = {w_ih_l0, w_hh_l0, b_ih_l0, b_hh_l0, w_ih_l1, ...}. */
+int fac_debug_conv(fac_handle* h, const float* x, const float* w_host, const float* bias_host, int B, int Tin,
+                   int Cin, int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,
+                   const float* in_alpha_host, const float* out_alpha_host, int act, const float* res,
+                   float* y, int Tout, void* stream);
+int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, int B, int T, int H, float* y,
+                    void* stream);
+/* Registers (dst != NULL) or clears a named tap: the next forward copies that channels-last
+ * intermediate into dst (DEVICE, up to capacity_floats).  Names: enc_conv0, enc_block1..4,
+ * enc_lstm, mel80, f0_input, gamma_beta, dec_conv0, dec_lstm, dec_block1..4. */
+int fac_debug_tap(fac_handle* h, const char* name, float* dst, size_t capacity_floats);
+
+/* Per-kernel-family device timing for bench.py's roofline object: when enabled, every launch of
+ * the forward paths is bracketed by CUDA events on the launching stream.  Families: "conv"
+ * (conv_cl_kernel, all conv / linear layers), "lstm_rec", "fa_quantize".  fac_profile_get returns
+ * the accumulated device milliseconds, ALGORITHMIC flops (2*MACs) and bytes (in + out + weights
+ * once) and launch count since the last fac_profile_reset (it synchronises the device). */
+int fac_profile_enable(fac_handle* h, int on);
+int fac_profile_reset(fac_handle* h);
+int fac_profile_get(fac_handle* h, const char* family, double* ms, double* flops, double* bytes,
+                    long long* launches);
+
+size_t fac_workspace_bytes(const fac_handle* h);
+/* number of kernel launches issued by the last forward call (bench.py "gpu_launches") */
+int fac_last_launch_count(const fac_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACODEC_B200_H */

@@ -1,0 +1,209 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (via the thin ctypes module
+shim), against (a) the committed golden fixtures made from the imported unmodified reference,
+(b) the oracle restatement run live on this box's CPU, (c) size-independent properties at
+BASELINE configs[1] size (B=32 x 4 s).
+
+Bars (BASELINE.json north_star): VQ code indices bit-exact; waveform RMS error <= 1e-4.
+Float tensors upstream of the VQ are compared with tolerances stated inline.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, case_inputs, load_golden, state_dicts
+
+pytestmark = pytest.mark.gpu
+
+RMS_TOL = 1e-4          # north_star: reconstructed waveform within 1e-4 RMS
+Z_RTOL = 2e-5           # encoder latents: max |dz| <= Z_RTOL * max |z| (fp32 re-association only)
+
+
+def rms(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float(((a - b) ** 2).mean().sqrt())
+
+
+_MODEL = {}
+
+
+def model_for(seed):
+    import facodec_b200 as fb
+    if seed not in _MODEL:
+        _MODEL.clear()
+        m = fb.build_model()
+        sds = state_dicts(seed)
+        for k in ("encoder", "quantizer", "decoder"):
+            m[k].load_state_dict(sds[k])
+            m[k].eval()
+        _MODEL[seed] = m
+    return _MODEL[seed]
+
+
+def run_model(m, x, n_c, kw):
+    dev = torch.device("cuda:0")
+    xd = x.to(dev)
+    kwd = {k: v.to(dev) for k, v in kw.items()}
+    z = m.encoder(xd)
+    q = m.quantizer(z, xd, n_c=n_c, return_codes=True, **kwd)
+    y = m.decoder(q[0])
+    torch.cuda.synchronize()
+    return z, q, y
+
+
+@pytest.mark.parametrize("name", ["b2_t7200", "b1_t7000_ragged", "b3_t1500_short", "b2_t6000_fullwaves", "b1_t96000"])
+def test_golden_end_to_end(name, built_lib):
+    c = GOLDEN_CASES[name]
+    g = load_golden(name)
+    m = model_for(c["wseed"])
+    x, kw = case_inputs(c)
+    z, q, y = run_model(m, x, c["n_c"], kw)
+    assert tuple(z.shape) == g["z"].shape and tuple(y.shape) == g["y"].shape
+    zerr = np.abs(z.cpu().numpy() - g["z"]).max()
+    assert zerr <= Z_RTOL * np.abs(g["z"]).max(), f"z max err {zerr}"
+    for k, t in zip(("codes_p", "codes_c", "codes_r"), q[5]):
+        assert t.dtype == torch.int64 and tuple(t.shape) == g[k].shape
+        assert np.array_equal(t.cpu().numpy(), g[k]), f"{k}: {(t.cpu().numpy() != g[k]).sum()} indices differ"
+    assert np.abs(q[4].cpu().numpy() - g["timbre"]).max() <= 1e-5 * max(1.0, np.abs(g["timbre"]).max())
+    assert np.abs(q[0].cpu().numpy() - g["outs"]).max() <= 2e-4       # AdaLN output, |outs| ~ 1
+    assert abs(float(q[2]) - float(g["commitment"])) <= 1e-5 * abs(float(g["commitment"]))
+    assert abs(float(q[3]) - float(g["codebook"])) <= 1e-5 * abs(float(g["codebook"]))
+    if "z_p" in g:
+        for k, t in zip(("z_p", "z_c", "z_r"), q[1]):
+            assert np.abs(t.cpu().numpy() - g[k]).max() <= 1e-5 * max(1.0, np.abs(g[k]).max()), k
+    e = rms(y, g["y"])
+    assert e <= RMS_TOL, f"waveform RMS error {e}"
+    assert float(y.abs().max()) < 1.0
+
+
+@pytest.mark.parametrize("name", ["b2_t7200", "b3_t1500_short"])
+def test_golden_teacher_forced_stages(name, built_lib):
+    """Each module on the reference's own inputs (isolates the three entry points)."""
+    c = GOLDEN_CASES[name]
+    g = load_golden(name)
+    m = model_for(c["wseed"])
+    x, kw = case_inputs(c)
+    dev = torch.device("cuda:0")
+    zg = torch.from_numpy(g["z"]).to(dev)
+    q = m.quantizer(zg, x.to(dev), n_c=c["n_c"], return_codes=True)
+    for k, t in zip(("codes_p", "codes_c", "codes_r"), q[5]):
+        assert np.array_equal(t.cpu().numpy(), g[k]), k
+    y = m.decoder(torch.from_numpy(g["outs"]).to(dev))
+    assert rms(y, g["y"]) <= RMS_TOL
+
+
+def test_live_oracle_new_seed(built_lib):
+    """Fresh weights + waves, oracle run on this box's CPU."""
+    from facodec_b200 import synth
+    from oracle import facodec_oracle as O
+    seed = 5
+    sds = state_dicts(seed)
+    m = model_for(seed)
+    x = synth.synth_waves(2, 9000, seed=77)
+    zo, qo, yo = O.codec_forward(sds, x, n_c=2)
+    z, q, y = run_model(m, x, 2, {})
+    assert (z.cpu() - zo).abs().max() <= Z_RTOL * zo.abs().max()
+    for a, b in zip(q[5], qo[5]):
+        assert torch.equal(a.cpu(), b)
+    assert rms(y, yo) <= RMS_TOL
+
+
+def test_fused_codec_forward_equals_three_calls(built_lib):
+    import facodec_b200 as fb
+    from facodec_b200 import synth
+    m = model_for(0)
+    x = synth.synth_waves(3, 6000, seed=4).cuda()
+    z, q, y = run_model(m, x.cpu(), 2, {})
+    codec = fb.Codec(m)
+    y2, codes2, timbre2 = codec.forward(x, n_c=2)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)
+    for a, b in zip(q[5], codes2):
+        assert torch.equal(a, b)
+    assert torch.equal(q[4], timbre2)
+    yh, codes_h = codec.forward_host(x.cpu().contiguous(), n_c=2)
+    assert torch.equal(yh, y.cpu())
+    for a, b in zip(q[5], codes_h):
+        assert torch.equal(a.cpu(), b)
+    assert codec.launch_count() > 50
+
+
+def test_full_size_properties(built_lib):
+    """BASELINE configs[1]: B=32 x 4 s.  (1) utterance 0 == golden b1_t96000 (same PseudoDataset
+    stream); (2) batch invariance: an utterance decodes to the same bits alone or inside the batch;
+    (3) range/shape invariants."""
+    import facodec_b200 as fb
+    from facodec_b200 import synth
+    m = model_for(0)
+    codec = fb.Codec(m)
+    x = synth.synth_waves(32, 96000).cuda()
+    y, codes, timbre = codec.forward(x, n_c=2)
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (32, 1, 96000)
+    assert torch.isfinite(y).all() and float(y.abs().max()) < 1.0
+    for c_, n in zip(codes, (1, 2, 3)):
+        assert tuple(c_.shape) == (32, n, 320) and int(c_.min()) >= 0 and int(c_.max()) < 1024
+    g = load_golden("b1_t96000")
+    assert np.array_equal(codes[0][0].cpu().numpy(), g["codes_p"][0])
+    assert np.array_equal(codes[1][0].cpu().numpy(), g["codes_c"][0])
+    assert np.array_equal(codes[2][0].cpu().numpy(), g["codes_r"][0])
+    assert rms(y[0], g["y"][0]) <= RMS_TOL
+    for i in (0, 17, 31):
+        yi, ci, ti = codec.forward(x[i:i + 1].contiguous(), n_c=2)
+        assert torch.equal(yi[0], y[i]), f"utterance {i}: batch-dependent result"
+        for a, b in zip(ci, codes):
+            assert torch.equal(a[0], b[i])
+
+
+def test_rvq_against_oracle_and_properties(built_lib):
+    """quantize/rvq.py ResidualVQ (BASELINE configs[3] geometry: 4 x 1024 entries, 1024 -> 8)."""
+    import facodec_b200 as fb
+    from oracle import facodec_oracle as O
+    rvq = fb.ResidualVQ(num_quantizers=4, codebook_size=10, dim=1024, codebook_dim=8, commitment=0.25).eval()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 1024, 41, generator=g)
+    layers = []
+    for i in range(4):
+        layers.append(dict(in_w=rvq._folded(i, "in_proj"), in_b=rvq._p[f"layers/{i}/in_proj/bias"].detach(),
+                           out_w=rvq._folded(i, "out_proj"), out_b=rvq._p[f"layers/{i}/out_proj/bias"].detach(),
+                           codebook=rvq._p[f"layers/{i}/_codebook/weight"].detach()))
+    with torch.no_grad():
+        qo, io, lo, ao = O.fvq_residual_vq(layers, x)
+    q, idx, loss, allq = rvq(x.cuda())
+    assert torch.equal(idx.cpu(), io)
+    assert (q.cpu() - qo).abs().max() <= 1e-5 and (allq.cpu() - ao).abs().max() <= 1e-5
+    assert float(loss.abs().sum()) == 0.0
+    # larger, channels-last, properties: quantized_out == sum of stages; indices in range
+    xb = torch.randn(64, 256, 1024, generator=g).cuda()
+    q2, idx2, _, allq2 = rvq(xb, channels_last=True)
+    assert int(idx2.min()) >= 0 and int(idx2.max()) < 1024
+    assert (allq2.sum(0) - q2).abs().max() <= 1e-5
+    q3, idx3, _, _ = rvq(xb.transpose(1, 2).contiguous())
+    assert torch.equal(idx3, idx2) and torch.equal(q3.transpose(1, 2), q2)
+
+
+def test_alias_free_activation(built_lib):
+    import facodec_b200 as fb
+    from oracle import facodec_oracle as O
+    g = torch.Generator().manual_seed(2)
+    for (B, C, T) in ((2, 5, 50), (1, 3, 700), (2, 2, 1)):
+        x = torch.randn(B, C, T, generator=g)
+        ident = fb.Activation1d(identity=True)
+        y = ident(x.cuda()).cpu()
+        assert (y - O.alias_free_act(x, lambda u: u)).abs().max() <= 2e-6
+        act = fb.Activation1d(C, alpha_logscale=True)
+        with torch.no_grad():
+            act.alpha.copy_(torch.randn(C, generator=g) * 0.3)
+            act.beta.copy_(torch.randn(C, generator=g) * 0.3)
+        a, b = torch.exp(act.alpha).view(1, C, 1), torch.exp(act.beta).view(1, C, 1)
+        ref = O.alias_free_act(x, lambda u: u + (1.0 / (b + 1e-9)) * torch.sin(u * a).pow(2))
+        assert (act(x.cuda()).cpu() - ref).abs().max() <= 5e-6
+
+
+def test_error_paths(built_lib):
+    import facodec_b200 as fb
+    m = model_for(0)
+    with pytest.raises(fb.FacError):
+        m.encoder(torch.zeros(1, 1, 3000))                       # CPU tensor: no fallback
+    with pytest.raises(fb.FacError):
+        m.quantizer(torch.zeros(1, 1024, 2).cuda(), torch.zeros(1, 1, 600).cuda())   # shorter than STFT padding

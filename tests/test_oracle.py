@@ -1,0 +1,127 @@
+"""CPU: the oracle restatement against (a) the committed golden fixtures generated from the
+imported unmodified reference and (b) the imported reference itself when /root/reference exists."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, case_inputs, load_golden, state_dicts
+from oracle import facodec_oracle as O
+from oracle import ref_import
+
+# Bit-exact in the build container (same CPU, same ATen kernels as when the fixtures were made);
+# on another host CPU oneDNN may pick other kernels, so floats get a tight tolerance there.
+SAME_HOST = ref_import.available()
+ATOL = 0.0 if SAME_HOST else 2e-5
+
+
+def _close(a, b, name):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, name
+    if ATOL == 0.0:
+        assert np.array_equal(a, b), f"{name}: max diff {np.abs(a - b).max()}"
+    else:
+        assert np.abs(a - b).max() <= ATOL * max(1.0, np.abs(b).max()), name
+
+
+def test_case_table():
+    from oracle import make_golden
+    assert make_golden.CASES == GOLDEN_CASES
+    for name in GOLDEN_CASES:
+        assert os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+
+
+def test_synth_is_host_independent():
+    """Synthetic checkpoints must be the same bits everywhere (golden fixtures depend on it)."""
+    from facodec_b200 import synth
+    sd = synth.synth_encoder(1)
+    h = hashlib.sha256()
+    for k in ("block.0.conv.conv.weight_g", "block.1.block.0.block.1.conv.conv.weight_v", "block.6.alpha"):
+        h.update(sd[k].numpy().tobytes())
+    assert h.hexdigest() == "db65aa08d774396d996e318b9407e70d4417e942368011e08c72c2d351e27314"
+    w = synth.synth_waves(1, 1000, seed=3)
+    assert abs(float(w.abs().max()) - 1.0) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["b2_t7200", "b1_t7000_ragged", "b3_t1500_short", "b2_t6000_fullwaves", "b1_t96000"])
+def test_oracle_matches_golden(name):
+    c = GOLDEN_CASES[name]
+    g = load_golden(name)
+    sds = state_dicts(c["wseed"])
+    x, kw = case_inputs(c)
+    with torch.no_grad():
+        z = O.encoder_forward(sds["encoder"], x)
+        q = O.quantizer_forward(sds["quantizer"], z, x, n_c=c["n_c"], return_codes=True, **kw)
+        y = O.decoder_forward(sds["decoder"], q[0])
+    _close(z, g["z"], "z")
+    _close(q[0], g["outs"], "outs")
+    _close(q[4], g["timbre"], "timbre")
+    _close(y, g["y"], "y")
+    for k, t in zip(("codes_p", "codes_c", "codes_r"), q[5]):
+        if SAME_HOST:
+            assert np.array_equal(t.numpy(), g[k]), k
+        else:
+            assert (t.numpy() != g[k]).mean() < 0.02, k
+    assert abs(float(q[2]) - float(g["commitment"])) <= 1e-5 * abs(float(g["commitment"]))
+    if "z_p" in g:
+        for k, t in zip(("z_p", "z_c", "z_r"), q[1]):
+            _close(t, g[k], k)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+def test_oracle_matches_imported_reference():
+    """Pins the restatement to the real thing: bit-identical tensors from the unmodified reference."""
+    import warnings
+    warnings.simplefilter("ignore")
+    model = ref_import.build_reference_model(0)
+    sds = state_dicts(1)
+    for k in ("encoder", "quantizer", "decoder"):
+        model[k].load_state_dict(sds[k])
+    x, _ = case_inputs(dict(B=2, T=4500, xseed=21))
+    with torch.no_grad():
+        z = model.encoder(x)
+        q = model.quantizer(z, x, n_c=2, return_codes=True)
+        y = model.decoder(q[0])
+        z2, q2, y2 = O.codec_forward(sds, x, n_c=2)
+    assert torch.equal(z, z2) and torch.equal(q[0], q2[0]) and torch.equal(y, y2)
+    assert torch.equal(q[4], q2[4])
+    for a, b in zip(q[5], q2[5]):
+        assert torch.equal(a, b)
+    for a, b in zip(q[1], q2[1]):
+        assert torch.equal(a, b)
+    assert float(q[2]) == float(q2[2]) and float(q[3]) == float(q2[3])
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+def test_fvq_rvq_and_alias_free_match_reference():
+    import sys
+    import warnings
+    warnings.simplefilter("ignore")
+    ref_import.import_reference()
+    from quantize.rvq import ResidualVQ as RefRVQ
+    from alias_free_torch import Activation1d as RefAct
+    torch.manual_seed(3)
+    rvq = RefRVQ(num_quantizers=4, codebook_size=10, dim=1024, codebook_dim=8, commitment=0.25).eval()
+    x = torch.randn(2, 1024, 17)
+    layers = []
+    for l in rvq.layers:
+        layers.append(dict(in_w=l.in_proj.weight.detach(), in_b=l.in_proj.bias.detach(),
+                           out_w=l.out_proj.weight.detach(), out_b=l.out_proj.bias.detach(),
+                           codebook=l.codebook.weight.detach()))
+    with torch.no_grad():
+        a = rvq(x)
+        b = O.fvq_residual_vq(layers, x)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0]) and torch.equal(a[3], b[3])
+    act = RefAct(activation=torch.nn.Identity())
+    xx = torch.randn(2, 5, 50)
+    assert torch.allclose(act(xx), O.alias_free_act(xx, lambda u: u), atol=0, rtol=0)
+
+
+def test_reflect_pad_short_branch():
+    """encodec.py:96-113: length <= pad => zero-extend, reflect, truncate."""
+    x = torch.arange(1, 4, dtype=torch.float32).reshape(1, 1, 3)
+    y = O._pad1d_reflect(x, 5, 0)
+    assert y.shape[-1] == 8
+    assert y.flatten().tolist() == [0.0, 0.0, 0.0, 3.0, 2.0, 1.0, 2.0, 3.0]
