@@ -221,8 +221,77 @@ __global__ void __launch_bounds__(2 * BN) conv_cl_kernel(ConvParams p) {
     }
 }
 
+// ---- Cout == 1 (decoder's last conv, dac.py:158-160: Snake -> SConv1d(96 -> 1, k=7) -> tanh) -------
+// A dot product of K*Cin per output sample: HBM-bound (reads the widest activation of the model once).
+// CTA = 128 output samples: stage the (128 + halo) x Cin input tile in shared memory with Snake applied
+// (coalesced 16-byte loads), then one warp per 16 outputs, lanes split the channels, shuffle-reduce.
+constexpr int C1_TILE = 128;
+__global__ void __launch_bounds__(256) conv_cout1_kernel(ConvParams p) {
+    extern __shared__ __align__(16) float c1_smem[];
+    const int Cin = p.Cin;
+    const int halo = (p.K - 1) * p.dil;
+    const int rows = C1_TILE + halo;
+    float* xs = c1_smem;                       // [rows][Cin]
+    float* wsm = c1_smem + (size_t)rows * Cin; // [K][Cin]
+    const int b = blockIdx.y, t0 = blockIdx.x * C1_TILE;
+    const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
+    const PadMap pm = PadMap::make(p.Tin, p.pad_left, p.pad_right, p.pad_reflect);
+    const int c4n = Cin / 4;
+    for (int i = threadIdx.x; i < rows * c4n; i += blockDim.x) {
+        int r = i / c4n, c4 = i - r * c4n;
+        int row = pm.src(t0 + r - p.pad_left);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row >= 0 && t0 + r - halo < p.Tout + 0) {
+            v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.ldx + c4 * 4));
+            if (p.in_alpha) {
+                float4 al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + c4 * 4));
+                float4 ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + c4 * 4));
+                v.x = snake_f(v.x, al.x, ia.x); v.y = snake_f(v.y, al.y, ia.y);
+                v.z = snake_f(v.z, al.z, ia.z); v.w = snake_f(v.w, al.w, ia.w);
+            }
+        }
+        *reinterpret_cast<float4*>(xs + (size_t)r * Cin + c4 * 4) = v;
+    }
+    for (int i = threadIdx.x; i < p.K * Cin; i += blockDim.x) wsm[i] = p.w[(size_t)i * p.ldw];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float bias = p.bias ? p.bias[0] : 0.f;
+    float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
+    for (int o = 0; o < C1_TILE / 8; ++o) {
+        int tl = warp * (C1_TILE / 8) + o;
+        float acc = 0.f;
+        for (int tap = 0; tap < p.K; ++tap) {
+            const float* xr = xs + (size_t)(tl + tap * p.dil) * Cin;
+            const float* wr = wsm + tap * Cin;
+            for (int ci = lane; ci < Cin; ci += 32) acc = fmaf(xr[ci], wr[ci], acc);
+        }
+        acc = warp_sum(acc);
+        int t = t0 + tl;
+        if (lane == 0 && t < p.Tout) {
+            float v = acc + bias;
+            if (p.out_act == ACT_TANH) v = tanhf(v);
+            yb[(size_t)t * p.ldy] = v;
+        }
+    }
+}
+
 cudaError_t launch_conv(const ConvParams& p, cudaStream_t st) {
     if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
+    if (p.Cout == 1 && p.stride == 1 && (p.Cin % 4) == 0 && !p.res && !p.valid_len && !p.y_transposed &&
+        (p.out_act == ACT_NONE || p.out_act == ACT_TANH)) {
+        size_t smem = sizeof(float) * ((size_t)(C1_TILE + (p.K - 1) * p.dil) * p.Cin + (size_t)p.K * p.Cin);
+        if (smem <= 200 * 1024) {
+            static bool configured = false;
+            if (!configured) {
+                cudaError_t e = cudaFuncSetAttribute(conv_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                if (e != cudaSuccess) return e;
+                configured = true;
+            }
+            dim3 grid((p.Tout + C1_TILE - 1) / C1_TILE, p.B);
+            conv_cout1_kernel<<<grid, 256, smem, st>>>(p);
+            return cudaGetLastError();
+        }
+    }
     dim3 grid((p.Tout + CONV_BM - 1) / CONV_BM, 1, p.B);
     // channel tile with the least padding waste (ties -> wider tile)
     auto padded = [&](int bn) { return (p.Cout + bn - 1) / bn * bn; };

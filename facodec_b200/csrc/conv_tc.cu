@@ -1,0 +1,697 @@
+// Channels-last 1-D convolution on the 5th-gen tensor cores (tcgen05, sm_100a), fp32-faithful.
+//
+// Same contract as conv_simt.cu (SConv1d / SConvTranspose1d / Linear call sites of the
+// reference), restricted to stride-1 convs in "rows" (a strided down-conv with kernel 2s is a
+// 2-tap conv over rows of s consecutive samples, see `vf`), Cin*vf % 16 == 0, Cout % 16 == 0.
+//
+//   D[t][co] = sum_tap sum_j  A[t - PLr + tap*dil][j] * W[tap][j][co]
+//
+// Precision: bit-exact VQ indices need fp32-faithful sums, so every product is
+// formed as 3 TF32 MMAs (x = hi + lo, both exactly representable in TF32):
+//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi     (dropped term a_lo*b_lo ~ 2^-24 |ab|)
+// with fp32 accumulation in TMEM.  Weights are split offline; activations are split in-kernel.
+//
+// CTA = 6 warps, one 128*MT-row x N-channel output tile (MT accumulators in TMEM share every
+// weight tile, which halves/quarters the L2->SMEM weight traffic per MMA):
+//   warp 0    : weight producer -- one elected lane streams pre-arranged [tap][16 ci] weight
+//               blobs (hi|lo, already in the UMMA K-major core-matrix layout) with 1-D bulk
+//               TMA copies (cp.async.bulk, UBLKCP) into a 4-deep mbarrier ring.
+//   warp 1    : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma.kind::tf32
+//               (M=128, N, K=8) and tcgen05.commit's to free ring slots.
+//   warps 2-5 : activation producers, then epilogue.  Per 16-channel chunk they load the UNION
+//               of the rows all taps need (128*MT + (K-1)*dil rows) once from HBM with 16-byte
+//               loads (reflect/zero padding = index map, no padded copy), apply Snake, split into
+//               hi/lo and store them in a no-swizzle K-major layout whose row pitch is a uniform
+//               16 bytes, so each tap is just a descriptor start-address offset of tap*dil rows
+//               (taps are never re-loaded or im2col'ed).  Epilogue: tcgen05.ld -> bias ->
+//               Snake/tanh/Mish -> residual -> 128-byte row stores.
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fac {
+
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kChunk = 16;        // K elements (channels) per pipeline chunk
+constexpr int kMaxStagesB = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel aborts with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes stored as
+// 128 contiguous bytes; SBO = byte pitch between 8-row groups, LBO = byte pitch between the two
+// 16-byte K halves of one K=8 (tf32) MMA; version = 1 (sm_100).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct Smem {
+    uint64_t b_full[kMaxStagesB];
+    uint64_t b_empty[kMaxStagesB];
+    uint64_t a_full[2];
+    uint64_t a_empty[2];
+    uint64_t acc_full;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+}  // namespace tc
+
+__global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p) {
+    using namespace tc;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Smem* sm = reinterpret_cast<Smem*>(smem_raw);
+    const int N = p.N, MT = p.MT;
+    const int R = 128 * MT + (p.Kr - 1) * p.dil;            // union of rows all taps touch
+    const int Rpad = p.Rpad;                                // R rounded so that Rpad % 8 == 2
+    const uint32_t a_half = (uint32_t)Rpad * 16 * 4;        // bytes of one hi (or lo) A buffer
+    const uint32_t b_half = (uint32_t)N * 16 * 4;           // bytes of one hi (or lo) weight tile
+    uint8_t* a_base = smem_raw + 128;                       // [2 bufs][hi|lo][4 k4][Rpad][16B]
+    uint8_t* b_base = a_base + 4 * a_half;                  // [S][hi|lo][4 k4][N][16B]
+    const int S = p.stagesB;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * 128 * MT;
+    const int ntile = blockIdx.y;
+    const int b = blockIdx.z;
+    const int nchunk = p.nchunk, Kr = p.Kr;
+    const uint32_t ncols = p.tmem_cols;
+
+    if (tid == 0) {
+        for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
+        mbar_init(&sm->acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&sm->tmem_base, ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    if (warp == 0) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            const float* wsrc = p.wblob + (size_t)ntile * nchunk * Kr * (size_t)(2 * b_half / 4);
+            int it = 0;
+            for (int c = 0; c < nchunk; ++c)
+                for (int tap = 0; tap < Kr; ++tap, ++it) {
+                    int s = it % S;
+                    mbar_wait(&sm->b_empty[s], ((it / S) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&sm->b_full[s], 2 * b_half);
+                    bulk_g2s(b_base + (size_t)s * 2 * b_half, wsrc + (size_t)it * (2 * b_half / 4), 2 * b_half, &sm->b_full[s]);
+                }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, K-major both, N>>3, M=128>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_lbo = (uint32_t)Rpad * 16, b_lbo = (uint32_t)N * 16;
+            int it = 0;
+            for (int c = 0; c < nchunk; ++c) {
+                const int buf = c & 1;
+                mbar_wait(&sm->a_full[buf], (c >> 1) & 1);
+                const uint32_t a_hi = smem_u32(a_base + (size_t)buf * 2 * a_half);
+                const uint32_t a_lo = a_hi + a_half;
+                for (int tap = 0; tap < Kr; ++tap, ++it) {
+                    const int s = it % S;
+                    mbar_wait(&sm->b_full[s], (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
+                    const uint32_t b_lo = b_hi + b_half;
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil) * 16;
+                        const uint32_t d_tmem = tmem + (uint32_t)(mt * N);
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
+                            const uint32_t bb = (pass == 1 ? b_lo : b_hi);
+#pragma unroll
+                            for (int ks = 0; ks < kChunk / 8; ++ks) {
+                                uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
+                                uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
+                                uint32_t accum = (c | tap | pass | ks) != 0;
+                                umma_tf32(d_tmem, ad, bd, idesc, accum);
+                            }
+                        }
+                    }
+                    umma_commit(&sm->b_empty[s]);       // weight slot free once these MMAs retire
+                }
+                umma_commit(&sm->a_empty[buf]);         // activation buffer free
+            }
+            umma_commit(&sm->acc_full);
+        }
+    } else {
+        // ================= activation producers (warps 2..5) =================
+        const int ptid = tid - 64;                                  // 0..127
+        const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
+        const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
+        const int npieces = R * 4;
+        for (int c = 0; c < nchunk; ++c) {
+            const int buf = c & 1;
+            mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+            uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
+            uint8_t* alo = ahi + a_half;
+            for (int base = 0; base < npieces; base += 128 * 8) {
+                float4 v[8];
+                int ci_[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    int idx = base + u * 128 + ptid;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ci_[u] = -1;
+                    if (idx < npieces) {
+                        int r = idx >> 2, pc = idx & 3;
+                        int j = c * kChunk + pc * 4;
+                        int soff = j / p.Cin, ci = j - soff * p.Cin;
+                        int vrow = t0 - p.PLr + r;
+                        int src = -1;
+                        if (vrow < p.Tout + (Kr - 1) * p.dil) src = pm.src(vrow * p.vf + soff);
+                        if (src >= 0) {
+                            v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)src * p.ldx + ci));
+                            ci_[u] = ci;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    int idx = base + u * 128 + ptid;
+                    if (idx < npieces) {
+                        float4 x4 = v[u];
+                        if (p.in_alpha && ci_[u] >= 0) {
+                            float4 al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + ci_[u]));
+                            float4 ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + ci_[u]));
+                            x4.x = snake_f(x4.x, al.x, ia.x);
+                            x4.y = snake_f(x4.y, al.y, ia.y);
+                            x4.z = snake_f(x4.z, al.z, ia.z);
+                            x4.w = snake_f(x4.w, al.w, ia.w);
+                        }
+                        float4 hi, lo;
+                        hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
+                        hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
+                        hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
+                        hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
+                        int r = idx >> 2, pc = idx & 3;
+                        size_t off = ((size_t)pc * Rpad + r) * 16;
+                        *reinterpret_cast<float4*>(ahi + off) = hi;
+                        *reinterpret_cast<float4*>(alo + off) = lo;
+                    }
+                }
+            }
+            fence_proxy_async();        // make the generic-proxy stores visible to the tensor core
+            mbar_arrive(&sm->a_full[buf]);
+        }
+        // ================= epilogue =================
+        mbar_wait(&sm->acc_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;                                     // TMEM lane quarter of this warp
+        const int row = q * 32 + lane;
+        float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
+        const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
+        for (int mt = 0; mt < MT; ++mt) {
+            const int t = t0 + mt * 128 + row;
+            const bool row_ok = t < p.Tout;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
+                if (!row_ok) continue;
+                const int co0 = ntile * N + c0;
+                const int ncol = (N - c0) < 32 ? (N - c0) : 32;
+                const size_t off = (size_t)t * p.ldy + co0;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    if (j4 * 4 >= ncol) break;
+                    float o[4];
+                    float4 bi = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    o[0] = __uint_as_float(acc[j4 * 4 + 0]) + bi.x;
+                    o[1] = __uint_as_float(acc[j4 * 4 + 1]) + bi.y;
+                    o[2] = __uint_as_float(acc[j4 * 4 + 2]) + bi.z;
+                    o[3] = __uint_as_float(acc[j4 * 4 + 3]) + bi.w;
+                    if (p.out_act == ACT_SNAKE) {
+                        float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co0 + j4 * 4));
+                        float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co0 + j4 * 4));
+                        o[0] = snake_f(o[0], al.x, ia.x);
+                        o[1] = snake_f(o[1], al.y, ia.y);
+                        o[2] = snake_f(o[2], al.z, ia.z);
+                        o[3] = snake_f(o[3], al.w, ia.w);
+                    } else if (p.out_act == ACT_TANH) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = tanhf(o[e]);
+                    } else if (p.out_act == ACT_MISH) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = mish_f(o[e]);
+                    }
+                    if (rb) {
+                        float4 rr = *reinterpret_cast<const float4*>(rb + off + j4 * 4);
+                        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+                    }
+                    *reinterpret_cast<float4*>(yb + off + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, ncols);
+}
+
+
+// ================================================================================================
+// conv_tcp_kernel: same math, with PROMOTED accumulation for the layers upstream of the VQ.
+//
+// The tensor core adds into its fp32 TMEM accumulator with truncation (measured: ~0.5 ulp of
+// one-sided error per chained MMA, i.e. ~1e-5 relative after a few hundred MMAs), which is enough
+// to flip near-tied VQ decisions.  Here each TMEM accumulator only lives for `promote_every`
+// chunks (~48 MMAs); 8 worker warps then pull it out with tcgen05.ld and add it into fp32
+// REGISTER accumulators with round-to-nearest (128 registers per thread hold the 128 x 256 tile),
+// while the MMA warp already fills the other TMEM buffer.  The same 8 warps are the activation
+// producers: produce(chunk c) ; promote(group of chunk c-1) ; ...
+// ================================================================================================
+namespace tc {
+constexpr int kThreadsP = 320;     // warp 0: weights, warp 1: MMA, warps 2..9: workers
+struct SmemP {
+    uint64_t b_full[kMaxStagesB];
+    uint64_t b_empty[kMaxStagesB];
+    uint64_t a_full[2];
+    uint64_t a_empty[2];
+    uint64_t acc_ready[2];
+    uint64_t acc_free[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+}  // namespace tc
+
+__global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams p) {
+    using namespace tc;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SmemP* sm = reinterpret_cast<SmemP*>(smem_raw);
+    const int N = p.N, MT = p.MT;
+    const int ncols = MT * N;                               // <= 256 columns per TMEM buffer
+    const int R = 128 * MT + (p.Kr - 1) * p.dil;
+    const int Rpad = p.Rpad;
+    const uint32_t a_half = (uint32_t)Rpad * 16 * 4;
+    const uint32_t b_half = (uint32_t)N * 16 * 4;
+    uint8_t* a_base = smem_raw + 128;
+    uint8_t* b_base = a_base + 4 * a_half;
+    const int S = p.stagesB;
+    const int P = p.promote_every;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * 128 * MT;
+    const int ntile = blockIdx.y;
+    const int b = blockIdx.z;
+    const int nchunk = p.nchunk, Kr = p.Kr;
+
+    if (tid == 0) {
+        for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm->a_full[i], 256); mbar_init(&sm->a_empty[i], 1);
+            mbar_init(&sm->acc_ready[i], 1); mbar_init(&sm->acc_free[i], 256);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&sm->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const float* wsrc = p.wblob + (size_t)ntile * nchunk * Kr * (size_t)(2 * b_half / 4);
+            int it = 0;
+            for (int c = 0; c < nchunk; ++c)
+                for (int tap = 0; tap < Kr; ++tap, ++it) {
+                    int s = it % S;
+                    mbar_wait(&sm->b_empty[s], ((it / S) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&sm->b_full[s], 2 * b_half);
+                    bulk_g2s(b_base + (size_t)s * 2 * b_half, wsrc + (size_t)it * (2 * b_half / 4), 2 * b_half, &sm->b_full[s]);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_lbo = (uint32_t)Rpad * 16, b_lbo = (uint32_t)N * 16;
+            int it = 0;
+            const int G = (nchunk + P - 1) / P;
+            for (int g = 0; g < G; ++g) {
+                const int abuf = g & 1;
+                mbar_wait(&sm->acc_free[abuf], ((g >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const int c_begin = g * P, c_end = (c_begin + P < nchunk) ? c_begin + P : nchunk;
+                for (int c = c_begin; c < c_end; ++c) {
+                    const int buf = c & 1;
+                    mbar_wait(&sm->a_full[buf], (c >> 1) & 1);
+                    const uint32_t a_hi = smem_u32(a_base + (size_t)buf * 2 * a_half);
+                    const uint32_t a_lo = a_hi + a_half;
+                    for (int tap = 0; tap < Kr; ++tap, ++it) {
+                        const int s = it % S;
+                        mbar_wait(&sm->b_full[s], (it / S) & 1);
+                        tc_fence_after();
+                        const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
+                        const uint32_t b_lo = b_hi + b_half;
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil) * 16;
+                            const uint32_t d_tmem = tmem + (uint32_t)(abuf * 256 + mt * N);
+#pragma unroll
+                            for (int pass = 0; pass < 3; ++pass) {
+                                const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
+                                const uint32_t bb = (pass == 1 ? b_lo : b_hi);
+#pragma unroll
+                                for (int ks = 0; ks < kChunk / 8; ++ks) {
+                                    uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
+                                    uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
+                                    uint32_t accum = ((c - c_begin) | tap | pass | ks) != 0;
+                                    umma_tf32(d_tmem, ad, bd, idesc, accum);
+                                }
+                            }
+                        }
+                        umma_commit(&sm->b_empty[s]);
+                    }
+                    umma_commit(&sm->a_empty[buf]);
+                }
+                umma_commit(&sm->acc_ready[abuf]);
+            }
+        }
+    } else {
+        // ================= workers: activation producers + promoters + epilogue =================
+        const int wtid = tid - 64;                                  // 0..255
+        const int q = warp & 3;                                     // TMEM lane quarter
+        const int half = (warp - 2) >> 2;                           // column half of the tile set
+        int split = ((ncols / 2 + 15) / 16) * 16;
+        if (split > ncols) split = ncols;
+        const int mycol0 = half ? split : 0;
+        const int mycols = half ? ncols - split : split;
+        const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
+        const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
+        const int npieces = R * 4;
+        float acc[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+
+        for (int c = 0; c <= nchunk; ++c) {
+            if (c < nchunk) {
+                const int buf = c & 1;
+                mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
+                uint8_t* alo = ahi + a_half;
+                for (int base = 0; base < npieces; base += 256 * 4) {
+                    float4 v[4];
+                    int ci_[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int idx = base + u * 256 + wtid;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        ci_[u] = -1;
+                        if (idx < npieces) {
+                            int r = idx >> 2, pc = idx & 3;
+                            int j = c * kChunk + pc * 4;
+                            int soff = j / p.Cin, ci = j - soff * p.Cin;
+                            int vrow = t0 - p.PLr + r;
+                            int src = -1;
+                            if (vrow < p.Tout + (Kr - 1) * p.dil) src = pm.src(vrow * p.vf + soff);
+                            if (src >= 0) {
+                                v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)src * p.ldx + ci));
+                                ci_[u] = ci;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int idx = base + u * 256 + wtid;
+                        if (idx < npieces) {
+                            float4 x4 = v[u];
+                            if (p.in_alpha && ci_[u] >= 0) {
+                                float4 al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + ci_[u]));
+                                float4 ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + ci_[u]));
+                                x4.x = snake_f(x4.x, al.x, ia.x);
+                                x4.y = snake_f(x4.y, al.y, ia.y);
+                                x4.z = snake_f(x4.z, al.z, ia.z);
+                                x4.w = snake_f(x4.w, al.w, ia.w);
+                            }
+                            float4 hi, lo;
+                            hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
+                            hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
+                            hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
+                            hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
+                            int r = idx >> 2, pc = idx & 3;
+                            size_t off = ((size_t)pc * Rpad + r) * 16;
+                            *reinterpret_cast<float4*>(ahi + off) = hi;
+                            *reinterpret_cast<float4*>(alo + off) = lo;
+                        }
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&sm->a_full[buf]);
+            }
+            if (c >= 1 && ((c % P) == 0 || c == nchunk)) {
+                // ---- promote the group that ended with chunk c-1 ----
+                const int g = (c - 1) / P;
+                const int abuf = g & 1;
+                mbar_wait(&sm->acc_ready[abuf], (g >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + mycol0);
+#pragma unroll
+                for (int grp = 0; grp < 8; ++grp) {
+                    if (grp * 16 < mycols) {
+                        uint32_t v[16];
+                        tmem_ld16(tbase + grp * 16, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[grp * 16 + i] += __uint_as_float(v[i]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&sm->acc_free[abuf]);
+            }
+        }
+        // ================= epilogue from registers =================
+        float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
+        const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
+#pragma unroll
+        for (int grp = 0; grp < 8; ++grp) {
+            if (grp * 16 >= mycols) continue;
+            const int j0 = mycol0 + grp * 16;
+            const int mt = j0 / N, col = j0 - mt * N;
+            const int t = t0 + mt * 128 + q * 32 + lane;
+            if (t >= p.Tout) continue;
+            const int co0 = ntile * N + col;
+            const size_t off = (size_t)t * p.ldy + co0;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                float o[4];
+                float4 bi = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[0] = acc[grp * 16 + j4 * 4 + 0] + bi.x;
+                o[1] = acc[grp * 16 + j4 * 4 + 1] + bi.y;
+                o[2] = acc[grp * 16 + j4 * 4 + 2] + bi.z;
+                o[3] = acc[grp * 16 + j4 * 4 + 3] + bi.w;
+                if (p.out_act == ACT_SNAKE) {
+                    float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co0 + j4 * 4));
+                    float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co0 + j4 * 4));
+                    o[0] = snake_f(o[0], al.x, ia.x);
+                    o[1] = snake_f(o[1], al.y, ia.y);
+                    o[2] = snake_f(o[2], al.z, ia.z);
+                    o[3] = snake_f(o[3], al.w, ia.w);
+                } else if (p.out_act == ACT_TANH) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = tanhf(o[e]);
+                } else if (p.out_act == ACT_MISH) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = mish_f(o[e]);
+                }
+                if (rb) {
+                    float4 rr = *reinterpret_cast<const float4*>(rb + off + j4 * 4);
+                    o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+                }
+                *reinterpret_cast<float4*>(yb + off + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+bool tc_conv_plan(TcConvParams& p) {
+    // p.Cin, p.vf, p.Kr, p.dil, p.Cout, p.promoted must be set; fills N, MT, nchunk, Rpad, stagesB, ...
+    if ((p.Cin % 4) != 0 || ((p.Cin * p.vf) % tc::kChunk) != 0 || (p.Cout % 16) != 0) return false;
+    int N = 0;
+    for (int cand = p.promoted ? 128 : 256; cand >= 16; cand -= 16)
+        if (p.Cout % cand == 0) { N = cand; break; }
+    if (N < 32) return false;
+    p.N = N;
+    if (p.promoted) {
+        p.MT = (N <= 64) ? 4 : 2;              // MT * N <= 256 columns per TMEM buffer
+        p.promote_every = 8 / p.Kr < 1 ? 1 : 8 / p.Kr;
+    } else {
+        p.MT = (N <= 128) ? 4 : 2;
+    }
+    p.nchunk = p.Cin * p.vf / tc::kChunk;
+    int R = 128 * p.MT + (p.Kr - 1) * p.dil;
+    int Rpad = R;
+    while (Rpad % 8 != 2) ++Rpad;
+    p.Rpad = Rpad;
+    int cols = p.MT * N, pow2 = 32;
+    while (pow2 < cols) pow2 <<= 1;
+    if (pow2 > 512 || (p.promoted && cols > 256)) return false;
+    p.tmem_cols = p.promoted ? 512 : pow2;
+    size_t a_bytes = (size_t)4 * Rpad * 16 * 4;         // 2 bufs x (hi,lo)
+    size_t b_stage = (size_t)2 * N * 16 * 4;
+    int S = tc::kMaxStagesB;
+    while (S > 2 && 128 + a_bytes + S * b_stage > 225 * 1024) --S;
+    if (128 + a_bytes + S * b_stage > 225 * 1024) return false;
+    p.stagesB = S;
+    p.smem_bytes = 128 + a_bytes + S * b_stage;
+    return true;
+}
+
+size_t tc_blob_floats(const TcConvParams& p) {
+    return (size_t)(p.Cout / p.N) * p.nchunk * p.Kr * 2 * 4 * p.N * 4;
+}
+
+// wp: packed generic weights [Kr * vf*Cin][ldw] (conv_simt layout).  blob: see file header.
+void tc_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob) {
+    const int Cw = p.Cin * p.vf;   // columns per row-tap
+    size_t o = 0;
+    for (int nt = 0; nt < p.Cout / p.N; ++nt)
+        for (int c = 0; c < p.nchunk; ++c)
+            for (int tap = 0; tap < p.Kr; ++tap)
+                for (int hl = 0; hl < 2; ++hl)
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        for (int n = 0; n < p.N; ++n)
+                            for (int e = 0; e < 4; ++e) {
+                                int kk = tap * Cw + c * tc::kChunk + k4 * 4 + e;
+                                float w = wp[(size_t)kk * ldw + nt * p.N + n];
+                                // round-to-nearest-even-ish TF32 split (ties away, like cvt.rna)
+                                uint32_t u;
+                                memcpy(&u, &w, 4);
+                                uint32_t hu = (u + 0x1000u) & 0xFFFFE000u;
+                                float hi;
+                                memcpy(&hi, &hu, 4);
+                                float lo = w - hi;
+                                uint32_t lu;
+                                memcpy(&lu, &lo, 4);
+                                lu = (lu + 0x1000u) & 0xFFFFE000u;
+                                float lo_r;
+                                memcpy(&lo_r, &lu, 4);
+                                blob[o++] = hl == 0 ? hi : lo_r;
+                            }
+}
+
+cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
+    if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
+    static size_t configured = 0;
+    if (p.smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        if (e != cudaSuccess) return e;
+        configured = 225 * 1024;
+    }
+    dim3 grid((p.Tout + 128 * p.MT - 1) / (128 * p.MT), p.Cout / p.N, p.B);
+    if (p.promoted) {
+        static bool configured_p = false;
+        if (!configured_p) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+            if (e != cudaSuccess) return e;
+            configured_p = true;
+        }
+        conv_tcp_kernel<<<grid, tc::kThreadsP, p.smem_bytes, st>>>(p);
+    } else {
+        conv_tc_kernel<<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace fac

@@ -30,7 +30,12 @@ struct HostTensor {
     size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; }
 };
 
-struct ConvW { size_t w = 0, b = 0; int Cin = 0, Cout = 0, K = 1, ldw = 0; };
+struct ConvW {
+    size_t w = 0, b = 0; int Cin = 0, Cout = 0, K = 1, ldw = 0;
+    // tensor-core blob (conv_tc.cu): present when the layer is eligible
+    bool tc = false; size_t tcw = 0; int vf = 1, Kr = 0;
+    bool promoted = false;   // blob built for conv_tcp_kernel (layers upstream of the VQ)
+};
 struct SnakeW { size_t a = 0, ia = 0; int C = 0; };
 struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; int H = 0, U = 0, G = 0; };
 struct ResW { SnakeW s1; ConvW c7; SnakeW s2; ConvW c1; int dil = 1; };
@@ -68,6 +73,9 @@ struct fac_handle {
     std::vector<RvqSet> rvqs; std::vector<float*> rvq_arenas;
     char* ws = nullptr; size_t ws_bytes = 0;
     int launches = 0;
+    // tcgen05 3xTF32 path (fac_set_option "tensor_cores"): 0 = never, 1 = layers downstream of the VQ only
+    // (decoder, timbre branch), 2 = every eligible layer (default; promoted accumulation upstream of the VQ)
+    int use_tc = 2;
     float* aa_filter = nullptr;
     // optional per-kernel-family timing (fac_profile_*): CUDA events around every launch
     bool profiling = false;
@@ -123,8 +131,24 @@ std::vector<float> folded_weight(fac_handle* h, int m, const std::string& prefix
     return w;
 }
 
+// Builds the tcgen05 weight blob for a packed conv (stride-1 in rows; `stride` > 1 means the
+// kernel-2*stride down-conv viewed as a 2-tap conv over rows of `stride` samples).
+void attach_tc(fac_handle* h, ConvW& c, int stride, bool promoted) {
+    TcConvParams tp;
+    tp.Cin = c.Cin; tp.Cout = c.Cout; tp.dil = 1; tp.promoted = promoted ? 1 : 0;
+    if (stride == 1) { tp.vf = 1; tp.Kr = c.K; }
+    else if (c.K == 2 * stride) { tp.vf = stride; tp.Kr = 2; }
+    else return;
+    if (!tc_conv_plan(tp)) return;
+    c.vf = tp.vf; c.Kr = tp.Kr; c.promoted = promoted;
+    size_t n = tc_blob_floats(tp);
+    c.tcw = pack_alloc(h, n);
+    tc_pack_blob(tp, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw);
+    c.tc = true;
+}
+
 // nn.Conv1d [Cout][Cin][K] -> packed [K*Cin][ldw]
-ConvW pack_conv(fac_handle* h, int m, const std::string& prefix) {
+ConvW pack_conv(fac_handle* h, int m, const std::string& prefix, int stride = 1, bool promoted = false) {
     std::vector<int64_t> shp;
     std::vector<float> w = folded_weight(h, m, prefix, shp);
     if (shp.size() == 2) shp.push_back(1);
@@ -140,6 +164,7 @@ ConvW pack_conv(fac_handle* h, int m, const std::string& prefix) {
     const HostTensor& b = need(h, m, prefix + ".bias");
     c.b = pack_alloc(h, c.Cout);
     for (int co = 0; co < c.Cout; ++co) h->pack[c.b + co] = b.data[co];
+    attach_tc(h, c, stride, promoted);
     return c;
 }
 
@@ -163,6 +188,7 @@ ConvW pack_convtr(fac_handle* h, int m, const std::string& prefix, int stride) {
     c.b = pack_alloc(h, c.Cout);
     for (int r = 0; r < stride; ++r)
         for (int co = 0; co < Cout; ++co) h->pack[c.b + r * Cout + co] = b.data[co];
+    attach_tc(h, c, 1, false);
     return c;
 }
 
@@ -179,17 +205,17 @@ SnakeW pack_snake(fac_handle* h, int m, const std::string& key) {
     return s;
 }
 
-ResW pack_res(fac_handle* h, int m, const std::string& prefix, int dil) {
+ResW pack_res(fac_handle* h, int m, const std::string& prefix, int dil, bool promoted = false) {
     ResW r;
     r.dil = dil;
     r.s1 = pack_snake(h, m, prefix + ".block.0.alpha");
-    r.c7 = pack_conv(h, m, prefix + ".block.1.conv.conv");
+    r.c7 = pack_conv(h, m, prefix + ".block.1.conv.conv", 1, promoted);
     r.s2 = pack_snake(h, m, prefix + ".block.2.alpha");
-    r.c1 = pack_conv(h, m, prefix + ".block.3.conv.conv");
+    r.c1 = pack_conv(h, m, prefix + ".block.3.conv.conv", 1, promoted);
     return r;
 }
 
-LstmW pack_lstm(fac_handle* h, int m, const std::string& prefix) {
+LstmW pack_lstm(fac_handle* h, int m, const std::string& prefix, bool promoted = false) {
     LstmW L;
     const HostTensor& w0 = need(h, m, prefix + ".weight_hh_l0");
     L.H = (int)w0.shape[1];
@@ -210,6 +236,7 @@ LstmW pack_lstm(fac_handle* h, int m, const std::string& prefix) {
             for (int k = 0; k < H; ++k) h->pack[c.w + (size_t)k * c.ldw + row] = wih.data[(size_t)row * H + k];
         c.b = pack_alloc(h, 4 * H);
         for (int row = 0; row < 4 * H; ++row) h->pack[c.b + row] = bih.data[row] + bhh.data[row];
+        attach_tc(h, c, 1, promoted);
         L.ih[l] = c;
         L.whh[l] = pack_alloc(h, (size_t)L.G * H * R);
         for (int cta = 0; cta < L.G; ++cta)
@@ -279,15 +306,15 @@ void pack_encoder(fac_handle* h) {
     for (int i = 0; i < 4; ++i) {
         std::string p = "block." + std::to_string(i + 1);
         const int dils[3] = {1, 3, 9};
-        for (int j = 0; j < 3; ++j) e.blk[i].res[j] = pack_res(h, m, p + ".block." + std::to_string(j), dils[j]);
+        for (int j = 0; j < 3; ++j) e.blk[i].res[j] = pack_res(h, m, p + ".block." + std::to_string(j), dils[j], true);
         e.blk[i].snake = pack_snake(h, m, p + ".block.3.alpha");
-        e.blk[i].down = pack_conv(h, m, p + ".block.4.conv.conv");
+        e.blk[i].down = pack_conv(h, m, p + ".block.4.conv.conv", rates[i], true);
         e.blk[i].stride = rates[i];
         if (e.blk[i].down.K != 2 * rates[i]) throw PackError{"encoder stride/kernel mismatch"};
     }
-    e.lstm = pack_lstm(h, m, "block.5.lstm");
+    e.lstm = pack_lstm(h, m, "block.5.lstm", true);
     e.snake = pack_snake(h, m, "block.6.alpha");
-    e.conv_out = pack_conv(h, m, "block.7.conv.conv");
+    e.conv_out = pack_conv(h, m, "block.7.conv.conv", 1, true);
 }
 
 void pack_decoder(fac_handle* h) {
@@ -316,22 +343,22 @@ void pack_quantizer(fac_handle* h) {
     q.vq[1] = pack_vq(h, m, "content_quantizer.quantizers.0");
     q.vq[2] = pack_vq(h, m, "content_quantizer.quantizers.1");
     for (int i = 0; i < 3; ++i) q.vq[3 + i] = pack_vq(h, m, "residual_quantizer.quantizers." + std::to_string(i));
-    q.spec0 = pack_conv(h, m, "timbre_encoder.spectral.0");
-    q.spec3 = pack_conv(h, m, "timbre_encoder.spectral.3");
-    q.glu[0] = pack_conv(h, m, "timbre_encoder.temporal.0.conv1");
-    q.glu[1] = pack_conv(h, m, "timbre_encoder.temporal.1.conv1");
-    q.cq = pack_conv(h, m, "timbre_encoder.slf_attn.conv_q");
-    q.ck = pack_conv(h, m, "timbre_encoder.slf_attn.conv_k");
-    q.cv = pack_conv(h, m, "timbre_encoder.slf_attn.conv_v");
-    q.co = pack_conv(h, m, "timbre_encoder.slf_attn.conv_o");
-    q.fc = pack_conv(h, m, "timbre_encoder.fc");
-    q.timbre_linear = pack_conv(h, m, "timbre_linear");
+    q.spec0 = pack_conv(h, m, "timbre_encoder.spectral.0", 1, true);
+    q.spec3 = pack_conv(h, m, "timbre_encoder.spectral.3", 1, true);
+    q.glu[0] = pack_conv(h, m, "timbre_encoder.temporal.0.conv1", 1, true);
+    q.glu[1] = pack_conv(h, m, "timbre_encoder.temporal.1.conv1", 1, true);
+    q.cq = pack_conv(h, m, "timbre_encoder.slf_attn.conv_q", 1, true);
+    q.ck = pack_conv(h, m, "timbre_encoder.slf_attn.conv_k", 1, true);
+    q.cv = pack_conv(h, m, "timbre_encoder.slf_attn.conv_v", 1, true);
+    q.co = pack_conv(h, m, "timbre_encoder.slf_attn.conv_o", 1, true);
+    q.fc = pack_conv(h, m, "timbre_encoder.fc", 1, true);
+    q.timbre_linear = pack_conv(h, m, "timbre_linear", 1, true);
     q.mel_lin = pack_conv(h, m, "melspec_linear.conv.conv");
     for (int i = 0; i < 8; ++i) {
-        q.wn_in[i] = pack_conv(h, m, "melspec_encoder.in_layers." + std::to_string(i) + ".conv.conv");
-        q.wn_rs[i] = pack_conv(h, m, "melspec_encoder.res_skip_layers." + std::to_string(i) + ".conv.conv");
+        q.wn_in[i] = pack_conv(h, m, "melspec_encoder.in_layers." + std::to_string(i) + ".conv.conv", 1, true);
+        q.wn_rs[i] = pack_conv(h, m, "melspec_encoder.res_skip_layers." + std::to_string(i) + ".conv.conv", 1, true);
     }
-    q.mel_lin2 = pack_conv(h, m, "melspec_linear2.conv.conv");
+    q.mel_lin2 = pack_conv(h, m, "melspec_linear2.conv.conv", 1, true);
     // STFT basis with the Hann window folded in: frame sample n+424 of the zero-padded window
     const HostTensor& win = need(h, m, "to_mel.spectrogram.window");
     const HostTensor& fb = need(h, m, "to_mel.mel_scale.fb");
@@ -359,6 +386,7 @@ struct Ctx {
     fac_handle* h;
     cudaStream_t st;
     bool dry;          // size pass: allocate only
+    bool vq_critical = false;   // inside the encoder / prosody branch: feeds the bit-exact VQ argmin
     size_t off = 0;
     cudaError_t cerr = cudaSuccess;
     const char* where = "";
@@ -387,10 +415,11 @@ struct Ctx {
         check_nk(cudaMemcpyAsync(it->second.first, src, m * sizeof(float), cudaMemcpyDeviceToDevice, st), "tap");
     }
     // profiling: begin()/end() bracket one launch with events on the launching stream
-    void begin(const char* fam, double flops, double bytes) {
+    void begin(const char* fam, double flops, double bytes, const char* detail = nullptr) {
         if (dry || !h->profiling) return;
         fac_handle::ProfRec r;
         r.name = fam; r.flops = flops; r.bytes = bytes;
+        if (detail) { r.name += ":"; r.name += detail; }
         cudaEventCreate(&r.a); cudaEventCreate(&r.b);
         cudaEventRecord(r.a, st);
         h->prof.push_back(r);
@@ -433,6 +462,32 @@ int conv_extra_pad(int T, int k_eff, int stride) {
 void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, int Tout, const ConvOpts& o,
               const char* name) {
     if (c.dry) return;
+    if (c.h->use_tc >= (c.vq_critical ? 2 : 1) && w.tc && !o.transposed && !o.valid_len && (o.ldx == 0 || o.ldx == w.Cin) &&
+        (o.ldy == 0 || o.ldy == w.Cout) && o.stride == w.vf && (w.vf == 1 || o.dil == 1) && !o.no_bias) {
+        TcConvParams tp;
+        tp.Cin = w.Cin; tp.Cout = w.Cout; tp.vf = w.vf; tp.Kr = w.Kr; tp.promoted = w.promoted ? 1 : 0;
+        tp.dil = w.vf == 1 ? o.dil : 1;
+        if (tc_conv_plan(tp)) {
+            tp.x = x; tp.y = y; tp.wblob = c.W(w.tcw); tp.bias = c.W(w.b);
+            if (o.in_snake) { tp.in_alpha = c.W(o.in_snake->a); tp.in_inv_alpha = c.W(o.in_snake->ia); }
+            tp.out_act = o.act;
+            if (o.out_snake) { tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(o.out_snake->a); tp.out_inv_alpha = c.W(o.out_snake->ia); }
+            tp.res = o.res;
+            tp.B = B; tp.Tin = Tin; tp.ldx = w.Cin;
+            tp.PLr = o.pad_left / w.vf;
+            tp.pad_left_s = o.pad_left; tp.pad_right_s = o.pad_right; tp.reflect = o.reflect;
+            tp.Tout = Tout; tp.ldy = w.Cout;
+            tp.x_bstride = (size_t)Tin * w.Cin; tp.y_bstride = (size_t)Tout * w.Cout;
+            double flops = 2.0 * B * Tout * (double)w.Cout * w.K * w.Cin;
+            double bytes = 4.0 * ((double)B * Tin * w.Cin + (double)B * Tout * w.Cout * (o.res ? 2 : 1) + (double)w.K * w.Cin * w.Cout);
+            char det[96];
+            snprintf(det, sizeof det, "%s Cin%d Cout%d K%d d%d T%d", name, w.Cin, w.Cout, w.K, o.dil, Tout);
+            c.begin(w.promoted ? "conv_tcp" : "conv_tc", flops, bytes, det);
+            c.check(launch_conv_tc(tp, c.st), name);
+            c.end();
+            return;
+        }
+    }
     ConvParams p;
     p.x = x; p.y = y;
     p.w = c.W(w.w);
@@ -451,7 +506,9 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
     // algorithmic work of this launch: 2*MACs; bytes = input + output (+ residual) + weights once
     double flops = 2.0 * B * Tout * (double)w.Cout * w.K * w.Cin;
     double bytes = 4.0 * ((double)B * Tin * w.Cin + (double)B * Tout * w.Cout * (o.res ? 2 : 1) + (double)w.K * w.Cin * w.Cout);
-    c.begin("conv", flops, bytes);
+    char det[96];
+    snprintf(det, sizeof det, "%s Cin%d Cout%d K%d d%d T%d", name, w.Cin, w.Cout, w.K, o.dil, Tout);
+    c.begin("conv", flops, bytes, det);
     c.check(launch_conv(p, c.st), name);
     c.end();
 }
@@ -516,6 +573,7 @@ size_t enc_stage_floats(int B, int T) {
 // Encoder.forward (dac.py:69-104): x [B][T][1] -> z channels-last [B][Tz][1024] (or NCT when z_nct)
 int encoder_forward(Ctx& c, const float* x, int B, int T, float* z_out, bool z_nct) {
     const EncW& e = c.h->enc;
+    c.vq_critical = true;
     size_t stage = enc_stage_floats(B, T);
     float* buf[3] = {c.alloc<float>(stage), c.alloc<float>(stage), c.alloc<float>(stage)};
     int cur = 0;
@@ -541,8 +599,15 @@ int encoder_forward(Ctx& c, const float* x, int B, int T, float* z_out, bool z_n
     c.tap("enc_lstm", buf[cur], (size_t)B * t * 1024);
     ConvOpts o;
     o.in_snake = &e.snake;
-    o.transposed = z_nct ? 1 : 0;
-    sconv(c, e.conv_out, buf[cur], z_out, B, t, 1, 1, o, "enc.conv_out");
+    if (z_nct) {
+        // same kernel as the channels-last path (bit-identical z), then a [B][T][C] -> [B][C][T] transpose
+        int nx2 = (cur + 1) % 3;
+        sconv(c, e.conv_out, buf[cur], buf[nx2], B, t, 1, 1, o, "enc.conv_out");
+        if (!c.dry) c.check(launch_transpose(buf[nx2], z_out, B, t, LATENT, c.st), "enc.z_T");
+    } else {
+        sconv(c, e.conv_out, buf[cur], z_out, B, t, 1, 1, o, "enc.conv_out");
+    }
+    c.vq_critical = false;
     return t;
 }
 
@@ -652,6 +717,7 @@ QuantOut quantizer_forward(Ctx& c, const float* z_cl, const float* wave, int B, 
     const QuantW& q = c.h->qw;
     const int Tm = T / HOP;
     const int Tq = Tm < Tz ? Tm : Tz;
+    c.vq_critical = true;      // quantizer-side layers are tiny: all of them use the promoted kernel
     // --- timbre ---
     float* mel = mel_forward(c, wave, B, T, Tm);
     float* timbre_ws = c.alloc<float>((size_t)B * 1024);
@@ -705,6 +771,7 @@ QuantOut quantizer_forward(Ctx& c, const float* z_cl, const float* wave, int B, 
     int64_t* cc = c.alloc<int64_t>((size_t)B * 2 * Tq);
     int64_t* cr = c.alloc<int64_t>((size_t)B * 3 * Tq);
     float* loss_ws = c.alloc<float>(2);
+    c.vq_critical = false;
     if (c.dry) return out;
     FaqParams fp;
     fp.f0 = f0; fp.z = z_cl;
@@ -1090,6 +1157,60 @@ int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, i
     return rc;
 }
 
+int fac_set_option(fac_handle* h, const char* name, int value) {
+    if (!h || !name) return FAC_ERR_INVALID;
+    if (std::string(name) == "tensor_cores") { h->use_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
+    h->err = std::string("unknown option ") + name;
+    return FAC_ERR_INVALID;
+}
+
+int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const float* bias_host, int B, int Tin, int Cin,
+                      int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,
+                      const float* in_alpha_host, const float* out_alpha_host, int act, const float* res, float* y,
+                      int Tout, int promoted, void* stream) {
+    if (!h || !x || !w_host || !y) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    TcConvParams tp;
+    tp.Cin = Cin; tp.Cout = Cout; tp.promoted = promoted ? 1 : 0;
+    if (stride == 1) { tp.vf = 1; tp.Kr = K; tp.dil = dil; }
+    else if (K == 2 * stride && dil == 1) { tp.vf = stride; tp.Kr = 2; tp.dil = 1; }
+    else { h->err = "fac_debug_conv_tc: unsupported stride/kernel"; return FAC_ERR_UNSUPPORTED; }
+    if (!tc_conv_plan(tp)) { h->err = "fac_debug_conv_tc: layer not eligible for the tensor-core path"; return FAC_ERR_UNSUPPORTED; }
+    int ldw = (Cout + 3) / 4 * 4;
+    std::vector<float> gen((size_t)K * Cin * ldw, 0.f);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int k = 0; k < K; ++k) gen[((size_t)k * Cin + ci) * ldw + co] = w_host[((size_t)co * Cin + ci) * K + k];
+    size_t nb = tc_blob_floats(tp);
+    auto al4 = [](size_t v) { return (v + 3) / 4 * 4; };
+    size_t o_b = al4(nb), o_ia = al4(o_b + Cout), o_iia = al4(o_ia + Cin), o_oa = al4(o_iia + Cin), o_oia = al4(o_oa + Cout);
+    std::vector<float> pk(o_oia + Cout + 16, 0.f);
+    tc_pack_blob(tp, gen.data(), ldw, pk.data());
+    for (int i = 0; i < Cout; ++i) pk[o_b + i] = bias_host ? bias_host[i] : 0.f;
+    for (int i = 0; i < Cin; ++i) { pk[o_ia + i] = in_alpha_host ? in_alpha_host[i] : 1.f; pk[o_iia + i] = 1.0f / (pk[o_ia + i] + 1e-9f); }
+    for (int i = 0; i < Cout; ++i) { pk[o_oa + i] = out_alpha_host ? out_alpha_host[i] : 1.f; pk[o_oia + i] = 1.0f / (pk[o_oa + i] + 1e-9f); }
+    float* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, pk.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
+    tp.x = x; tp.y = y; tp.wblob = d; tp.bias = d + o_b;
+    if (in_alpha_host) { tp.in_alpha = d + o_ia; tp.in_inv_alpha = d + o_iia; }
+    tp.out_act = act;
+    if (out_alpha_host) { tp.out_act = ACT_SNAKE; tp.out_alpha = d + o_oa; tp.out_inv_alpha = d + o_oia; }
+    tp.res = res;
+    tp.B = B; tp.Tin = Tin; tp.ldx = Cin;
+    tp.PLr = pad_left / tp.vf;
+    tp.pad_left_s = pad_left; tp.pad_right_s = pad_right; tp.reflect = reflect;
+    tp.Tout = Tout; tp.ldy = Cout;
+    tp.x_bstride = (size_t)Tin * Cin; tp.y_bstride = (size_t)Tout * Cout;
+    e = launch_conv_tc(tp, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) { h->err = std::string("fac_debug_conv_tc: ") + cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
+}
+
 int fac_debug_tap(fac_handle* h, const char* name, float* dst, size_t capacity_floats) {
     if (!h || !name) return FAC_ERR_INVALID;
     if (!dst) h->taps.erase(name);
@@ -1128,13 +1249,37 @@ int fac_profile_reset(fac_handle* h) {
 int fac_profile_get(fac_handle* h, const char* family, double* ms, double* flops, double* bytes, long long* launches) {
     if (!h || !family) return FAC_ERR_INVALID;
     profile_collect(h);
-    auto it = h->prof_agg.find(family);
-    if (it == h->prof_agg.end()) { if (ms) *ms = 0; if (flops) *flops = 0; if (bytes) *bytes = 0; if (launches) *launches = 0; return FAC_OK; }
-    if (ms) *ms = it->second.ms;
-    if (flops) *flops = it->second.flops;
-    if (bytes) *bytes = it->second.bytes;
-    if (launches) *launches = it->second.launches;
+    std::string fam(family);
+    fac_handle::ProfAgg t;
+    for (auto& kv : h->prof_agg) {
+        if (kv.first == fam || (kv.first.size() > fam.size() && kv.first.compare(0, fam.size(), fam) == 0 && kv.first[fam.size()] == ':')) {
+            t.ms += kv.second.ms; t.flops += kv.second.flops; t.bytes += kv.second.bytes; t.launches += kv.second.launches;
+        }
+    }
+    if (ms) *ms = t.ms;
+    if (flops) *flops = t.flops;
+    if (bytes) *bytes = t.bytes;
+    if (launches) *launches = t.launches;
     return FAC_OK;
+}
+
+// Text dump "key\tms\tgflop\tgbytes\tlaunches\n" of every profiled call site; returns bytes needed.
+size_t fac_profile_dump(fac_handle* h, char* buf, size_t cap) {
+    if (!h) return 0;
+    profile_collect(h);
+    std::string out;
+    char line[256];
+    for (auto& kv : h->prof_agg) {
+        snprintf(line, sizeof line, "%s\t%.4f\t%.3f\t%.4f\t%ld\n", kv.first.c_str(), kv.second.ms, kv.second.flops / 1e9,
+                 kv.second.bytes / 1e9, kv.second.launches);
+        out += line;
+    }
+    if (buf && cap > 0) {
+        size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size() + 1;
 }
 
 size_t fac_workspace_bytes(const fac_handle* h) { return h ? h->ws_bytes : 0; }

@@ -25,6 +25,35 @@ struct ConvParams {
 };
 cudaError_t launch_conv(const ConvParams& p, cudaStream_t st);
 
+// ---- tcgen05 tensor-core conv (conv_tc.cu) ---------------------------------------------------
+struct TcConvParams {
+    const float* x = nullptr;          // [B][Tin][ldx] channels-last samples
+    const float* wblob = nullptr;      // [ntile][chunk][tap][hi|lo][4][N][4] (tc_pack_blob)
+    const float* bias = nullptr;
+    const float* in_alpha = nullptr;   // [Cin] Snake on the input or null
+    const float* in_inv_alpha = nullptr;
+    const float* out_alpha = nullptr;  // [Cout] when out_act == ACT_SNAKE
+    const float* out_inv_alpha = nullptr;
+    const float* res = nullptr;        // [B][Tout][ldy] or null
+    float* y = nullptr;                // [B][Tout][ldy]
+    int B = 0, Tin = 0, Cin = 0, ldx = 0;
+    int vf = 1;                        // samples per A row (down-conv stride; 1 otherwise)
+    int Kr = 1, dil = 1, PLr = 0;      // taps / dilation / left pad, in rows
+    int pad_left_s = 0, pad_right_s = 0, reflect = 0;   // sample-level padding (PadMap)
+    int Tout = 0, Cout = 0, ldy = 0;
+    int out_act = 0;
+    int promoted = 0;                  // 1 = conv_tcp_kernel (register-promoted accumulation)
+    // plan (tc_conv_plan)
+    int promote_every = 1;
+    int N = 0, MT = 0, nchunk = 0, Rpad = 0, stagesB = 0, tmem_cols = 0;
+    size_t smem_bytes = 0;
+    size_t x_bstride = 0, y_bstride = 0;
+};
+bool tc_conv_plan(TcConvParams& p);
+size_t tc_blob_floats(const TcConvParams& p);
+void tc_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob);
+cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st);
+
 // ---- LSTM recurrence (lstm.cu) -----------------------------------------------------------
 // One nn.LSTM layer over all T steps for up to 32 sequences (dac/model/encodec.py:272-288).
 struct LstmParams {

@@ -55,6 +55,11 @@ class Engine:
         elif idx != self.device_index:
             raise _lib.FacError("engine is bound to cuda:%d, got cuda:%d" % (self.device_index, idx))
 
+    def set_option(self, name, value, device=None):
+        """fac_set_option, e.g. ("tensor_cores", 0|1|2)."""
+        self._ensure(device or torch.device("cuda", torch.cuda.current_device()))
+        _lib.check(self.handle, self.L.fac_set_option(self.handle, name.encode(), int(value)), "fac_set_option")
+
     def register(self, module_id, module):
         self.modules[module_id] = module
 

@@ -105,6 +105,12 @@ int fac_rvq_forward(fac_handle* h, int rvq_id, const float* x, int B, int T, int
 int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int act,
                        const float* alpha, const float* beta, float* y, void* stream);
 
+/* Engine options.  "tensor_cores": 0 = fp32 FMA kernels everywhere; 1 = tcgen05 3xTF32
+ * kernel for every eligible layer downstream of the VQ (decoder, timbre branch), fp32 FMA upstream
+ * (encoder, prosody branch); 2 (default) = tcgen05 everywhere, with the register-promoted accumulation
+ * variant upstream of the VQ where the bit-exact argmin needs fp32-grade sums. */
+int fac_set_option(fac_handle* h, const char* name, int value);
+
 /* Kernel-level test hooks (used by tests/test_gpu_kernels.py; not part of the drop-in surface).
  * fac_debug_conv runs the generic channels-last conv kernel on one layer: x [B,Tin,Cin] and
  * y [B,Tout,Cout] are DEVICE channels-last buffers, w_host is a HOST nn.Conv1d weight
@@ -116,6 +122,14 @@ int fac_debug_conv(fac_handle* h, const float* x, const float* w_host, const flo
                    int Cin, int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,
                    const float* in_alpha_host, const float* out_alpha_host, int act, const float* res,
                    float* y, int Tout, void* stream);
+/* Same contract as fac_debug_conv, forced through the tcgen05 (3xTF32) kernels: promoted = 0 ->
+ * conv_tc_kernel (accumulates in TMEM only), 1 -> conv_tcp_kernel (TMEM accumulators promoted to fp32
+ * registers every ~48 MMAs; the variant used upstream of the VQ).  Returns FAC_ERR_UNSUPPORTED when
+ * the layer geometry is not eligible (Cin % 16, Cout % 16, stride). */
+int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const float* bias_host, int B, int Tin,
+                      int Cin, int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,
+                      const float* in_alpha_host, const float* out_alpha_host, int act, const float* res,
+                      float* y, int Tout, int promoted, void* stream);
 int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, int B, int T, int H, float* y,
                     void* stream);
 /* Registers (dst != NULL) or clears a named tap: the next forward copies that channels-last
@@ -125,13 +139,16 @@ int fac_debug_tap(fac_handle* h, const char* name, float* dst, size_t capacity_f
 
 /* Per-kernel-family device timing for bench.py's roofline object: when enabled, every launch of
  * the forward paths is bracketed by CUDA events on the launching stream.  Families: "conv"
- * (conv_cl_kernel, all conv / linear layers), "lstm_rec", "fa_quantize".  fac_profile_get returns
+ * (conv_cl_kernel, fp32 FMA), "conv_tc" (conv_tc_kernel, tcgen05 3xTF32), "lstm_rec", "fa_quantize".  fac_profile_get returns
  * the accumulated device milliseconds, ALGORITHMIC flops (2*MACs) and bytes (in + out + weights
  * once) and launch count since the last fac_profile_reset (it synchronises the device). */
 int fac_profile_enable(fac_handle* h, int on);
 int fac_profile_reset(fac_handle* h);
 int fac_profile_get(fac_handle* h, const char* family, double* ms, double* flops, double* bytes,
                     long long* launches);
+/* Per-call-site breakdown as text lines "key<TAB>ms<TAB>GFLOP<TAB>GB<TAB>launches"; returns the
+ * buffer size needed (call with buf = NULL first). */
+size_t fac_profile_dump(fac_handle* h, char* buf, size_t cap);
 
 size_t fac_workspace_bytes(const fac_handle* h);
 /* number of kernel launches issued by the last forward call (bench.py "gpu_launches") */

@@ -108,3 +108,58 @@ def test_slstm_vs_torch(B, T, H, built_lib):
     assert rc == 0, e.L.fac_last_error(e.handle)
     y = yd.cpu().transpose(1, 2)
     assert (y - ref).abs().max().item() <= 2e-5
+
+
+TC_CASES = [
+    # B, T, Cin, Cout, K, dil, stride, pl, pr, reflect, in_snake, out_snake, act, res
+    (1, 128, 16, 64, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0),       # one chunk, one tap, one N tile
+    (1, 512, 64, 64, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0),       # MT=4 full, 4 chunks
+    (2, 300, 64, 64, 7, 1, 1, 6, 0, 1, 0, 0, 0, 0),       # taps as descriptor row offsets
+    (2, 333, 64, 64, 7, 1, 1, 6, 0, 1, 1, 1, 0, 0),       # + snake prologue/epilogue
+    (1, 700, 64, 64, 7, 9, 1, 54, 0, 1, 1, 1, 0, 0),      # d=9
+    (2, 40, 96, 96, 7, 9, 1, 54, 0, 1, 1, 1, 0, 0),       # short-input reflect branch, N=96
+    (2, 150, 128, 128, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1),     # residual add
+    (2, 200, 64, 128, 4, 1, 2, 2, 0, 1, 1, 0, 0, 0),      # down conv s=2 (vf=2)
+    (1, 203, 128, 256, 10, 1, 5, 5, 2, 1, 1, 0, 0, 0),    # down conv s=5 ragged, N=256 MT=2
+    (1, 37, 512, 1024, 12, 1, 6, 6, 5, 1, 1, 0, 0, 0),    # s=6 ragged, 4 N tiles
+    (2, 260, 192, 192, 7, 3, 1, 18, 0, 1, 1, 1, 0, 0),    # N=192
+    (2, 31, 512, 1024, 5, 1, 1, 2, 2, 0, 0, 0, 0, 0),     # zero pad both sides
+    (3, 20, 1536, 768, 2, 1, 1, 1, 0, 0, 1, 0, 0, 0),     # transposed-conv form, N=256 x3
+    (1, 300, 384, 1920, 2, 1, 1, 1, 0, 0, 1, 0, 0, 0),    # up-conv 384 -> 5*384, N=240
+    (2, 64, 1024, 1024, 3, 1, 1, 2, 0, 1, 1, 0, 0, 0),    # encoder conv_out geometry
+    (1, 640, 1024, 4096, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0),   # LSTM input projection geometry
+]
+
+
+@pytest.mark.parametrize("promoted", [0, 1])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_kernel_vs_torch(case, promoted, built_lib):
+    """tcgen05 3xTF32 conv vs fp32 torch.  Operands are split exactly (hi + lo), but the tensor core adds
+    into its fp32 TMEM accumulator with truncation, so the error grows ~0.5 ulp per chained MMA
+    (measured ~1e-5 relative after 168 MMAs); tolerance 6e-5 * scale.  promoted=1 is the variant that
+    drains TMEM into fp32 registers every ~48 MMAs: held to 4e-6 * scale like the fp32 FMA kernel."""
+    B, T, Cin, Cout, K, dil, stride, pl, pr, reflect, ins, outs, act, res = case
+    e = _engine()
+    g = torch.Generator().manual_seed(hash(case) % 1000 + 7)
+    x = torch.randn(B, Cin, T, generator=g) * 0.5
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ia = (torch.rand(Cin, generator=g) + 0.5) if ins else None
+    oa = (torch.rand(Cout, generator=g) + 0.5) if outs else None
+    Tout = (T + pl + pr - ((K - 1) * dil + 1)) // stride + 1
+    r = torch.randn(B, Cout, Tout, generator=g) if res else None
+    ref = ref_conv(x, w, b, dil, stride, pl, pr, reflect, ia, oa, act, r)
+    xd = x.transpose(1, 2).contiguous().cuda()
+    rd = r.transpose(1, 2).contiguous().cuda() if res else None
+    yd = torch.full((B, Tout, Cout), float("nan"), device="cuda")
+    rc = e.L.fac_debug_conv_tc(e.handle, _p(xd), _p(w.contiguous()), _p(b), B, T, Cin, Cout, K, dil, stride, pl, pr, reflect,
+                               _p(ia), _p(oa), act, _p(rd), _p(yd), Tout, promoted, None)
+    assert rc == 0, e.L.fac_last_error(e.handle)
+    y = yd.cpu().transpose(1, 2)
+    assert torch.isfinite(y).all()
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    rel_rms = ((y - ref).double().pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt()).item()
+    print(f"TCERR promoted={promoted} case={case} maxerr={err:.3e} scale={scale:.3f} rel_rms={rel_rms:.3e}")
+    tol = 4e-6 if promoted else 6e-5        # promoted: fp32-grade; plain: truncating TMEM accumulation
+    assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
