@@ -137,6 +137,91 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
+
+// ---- activation producer shared by both kernels ------------------------------------------------
+// Thread `ptid` of NT producer threads owns 16-byte piece pc = ptid & 3 (4 input channels) of
+// rows ptid/4, ptid/4 + NT/4, ...: channel offset, Snake parameters and the smem column are
+// per-thread constants for the whole chunk; only the row varies.
+template <int NT>
+__device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMap& pm, const float* __restrict__ xb,
+                                              int c, int t0, int R, int Rpad, uint8_t* ahi, uint8_t* alo, int ptid) {
+    const int pc = ptid & 3;
+    const int j = c * kChunk + pc * 4;
+    const int soff = j / p.Cin, ci = j - soff * p.Cin;
+    const bool has_alpha = p.in_alpha != nullptr;
+    float4 al = make_float4(0.f, 0.f, 0.f, 0.f), ia = al;
+    if (has_alpha) {
+        al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + ci));
+        ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + ci));
+    }
+    constexpr int RSTEP = NT / 4;
+    const int row_limit = p.Tout + (p.Kr - 1) * p.dil;
+    const int vrow0 = t0 - p.PLr;
+    const float* __restrict__ xcol = xb + ci;
+    uint8_t* hcol = ahi + (size_t)pc * Rpad * 16;
+    uint8_t* lcol = alo + (size_t)pc * Rpad * 16;
+#pragma unroll 1
+    for (int r = ptid >> 2; r < R; r += RSTEP * 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int rr = r + u * RSTEP;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int vrow = vrow0 + rr;
+            if (rr < R && vrow < row_limit) {
+                const int src = pm.src(vrow * p.vf + soff);
+                if (src >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)src * p.ldx));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int rr = r + u * RSTEP;
+            if (rr < R) {
+                float4 x4 = v[u];
+                if (has_alpha) {            // snake(0) == 0, so padded zeros stay zero
+                    x4.x = snake_fast(x4.x, al.x, ia.x);
+                    x4.y = snake_fast(x4.y, al.y, ia.y);
+                    x4.z = snake_fast(x4.z, al.z, ia.z);
+                    x4.w = snake_fast(x4.w, al.w, ia.w);
+                }
+                float4 hi, lo;
+                hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
+                hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
+                hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
+                hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
+                *reinterpret_cast<float4*>(hcol + (size_t)rr * 16) = hi;
+                *reinterpret_cast<float4*>(lcol + (size_t)rr * 16) = lo;
+            }
+        }
+    }
+}
+
+// ---- epilogue for 4 consecutive output channels of one row --------------------------------------
+__device__ __forceinline__ void epilogue_store4(const TcConvParams& p, float o0, float o1, float o2, float o3, int co,
+                                                float* __restrict__ yrow, const float* __restrict__ rrow) {
+    if (p.bias) {
+        float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+        o0 += bi.x; o1 += bi.y; o2 += bi.z; o3 += bi.w;
+    }
+    if (p.out_act == ACT_SNAKE) {
+        float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
+        float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
+        o0 = snake_fast(o0, al.x, ia.x);
+        o1 = snake_fast(o1, al.y, ia.y);
+        o2 = snake_fast(o2, al.z, ia.z);
+        o3 = snake_fast(o3, al.w, ia.w);
+    } else if (p.out_act == ACT_TANH) {
+        o0 = tanhf(o0); o1 = tanhf(o1); o2 = tanhf(o2); o3 = tanhf(o3);
+    } else if (p.out_act == ACT_MISH) {
+        o0 = mish_f(o0); o1 = mish_f(o1); o2 = mish_f(o2); o3 = mish_f(o3);
+    }
+    if (rrow) {
+        float4 rr = *reinterpret_cast<const float4*>(rrow + co);
+        o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w;
+    }
+    *reinterpret_cast<float4*>(yrow + co) = make_float4(o0, o1, o2, o3);
+}
+
 struct Smem {
     uint64_t b_full[kMaxStagesB];
     uint64_t b_empty[kMaxStagesB];
@@ -239,58 +324,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         const int ptid = tid - 64;                                  // 0..127
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
         const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
-        const int npieces = R * 4;
         for (int c = 0; c < nchunk; ++c) {
             const int buf = c & 1;
             mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
             uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-            uint8_t* alo = ahi + a_half;
-            for (int base = 0; base < npieces; base += 128 * 8) {
-                float4 v[8];
-                int ci_[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    int idx = base + u * 128 + ptid;
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    ci_[u] = -1;
-                    if (idx < npieces) {
-                        int r = idx >> 2, pc = idx & 3;
-                        int j = c * kChunk + pc * 4;
-                        int soff = j / p.Cin, ci = j - soff * p.Cin;
-                        int vrow = t0 - p.PLr + r;
-                        int src = -1;
-                        if (vrow < p.Tout + (Kr - 1) * p.dil) src = pm.src(vrow * p.vf + soff);
-                        if (src >= 0) {
-                            v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)src * p.ldx + ci));
-                            ci_[u] = ci;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    int idx = base + u * 128 + ptid;
-                    if (idx < npieces) {
-                        float4 x4 = v[u];
-                        if (p.in_alpha && ci_[u] >= 0) {
-                            float4 al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + ci_[u]));
-                            float4 ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + ci_[u]));
-                            x4.x = snake_f(x4.x, al.x, ia.x);
-                            x4.y = snake_f(x4.y, al.y, ia.y);
-                            x4.z = snake_f(x4.z, al.z, ia.z);
-                            x4.w = snake_f(x4.w, al.w, ia.w);
-                        }
-                        float4 hi, lo;
-                        hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
-                        hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
-                        hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
-                        hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
-                        int r = idx >> 2, pc = idx & 3;
-                        size_t off = ((size_t)pc * Rpad + r) * 16;
-                        *reinterpret_cast<float4*>(ahi + off) = hi;
-                        *reinterpret_cast<float4*>(alo + off) = lo;
-                    }
-                }
-            }
+            produce_chunk<128>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
             fence_proxy_async();        // make the generic-proxy stores visible to the tensor core
             mbar_arrive(&sm->a_full[buf]);
         }
@@ -301,45 +339,22 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         const int row = q * 32 + lane;
         float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
         const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
+#pragma unroll 1
         for (int mt = 0; mt < MT; ++mt) {
             const int t = t0 + mt * 128 + row;
             const bool row_ok = t < p.Tout;
-            for (int c0 = 0; c0 < N; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
+            float* yrow = yb + (size_t)t * p.ldy;
+            const float* rrow = rb ? rb + (size_t)t * p.ldy : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t acc[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
                 if (!row_ok) continue;
                 const int co0 = ntile * N + c0;
-                const int ncol = (N - c0) < 32 ? (N - c0) : 32;
-                const size_t off = (size_t)t * p.ldy + co0;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    if (j4 * 4 >= ncol) break;
-                    float o[4];
-                    float4 bi = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    o[0] = __uint_as_float(acc[j4 * 4 + 0]) + bi.x;
-                    o[1] = __uint_as_float(acc[j4 * 4 + 1]) + bi.y;
-                    o[2] = __uint_as_float(acc[j4 * 4 + 2]) + bi.z;
-                    o[3] = __uint_as_float(acc[j4 * 4 + 3]) + bi.w;
-                    if (p.out_act == ACT_SNAKE) {
-                        float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co0 + j4 * 4));
-                        float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co0 + j4 * 4));
-                        o[0] = snake_f(o[0], al.x, ia.x);
-                        o[1] = snake_f(o[1], al.y, ia.y);
-                        o[2] = snake_f(o[2], al.z, ia.z);
-                        o[3] = snake_f(o[3], al.w, ia.w);
-                    } else if (p.out_act == ACT_TANH) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = tanhf(o[e]);
-                    } else if (p.out_act == ACT_MISH) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = mish_f(o[e]);
-                    }
-                    if (rb) {
-                        float4 rr = *reinterpret_cast<const float4*>(rb + off + j4 * 4);
-                        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-                    }
-                    *reinterpret_cast<float4*>(yb + off + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                }
+                for (int j4 = 0; j4 < 4; ++j4)
+                    epilogue_store4(p, __uint_as_float(acc[j4 * 4 + 0]), __uint_as_float(acc[j4 * 4 + 1]),
+                                    __uint_as_float(acc[j4 * 4 + 2]), __uint_as_float(acc[j4 * 4 + 3]), co0 + j4 * 4, yrow, rrow);
             }
         }
     }
@@ -477,7 +492,6 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
         const int mycols = half ? ncols - split : split;
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
         const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
-        const int npieces = R * 4;
         float acc[128];
 #pragma unroll
         for (int i = 0; i < 128; ++i) acc[i] = 0.f;
@@ -487,53 +501,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                 const int buf = c & 1;
                 mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
                 uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-                uint8_t* alo = ahi + a_half;
-                for (int base = 0; base < npieces; base += 256 * 4) {
-                    float4 v[4];
-                    int ci_[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        int idx = base + u * 256 + wtid;
-                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        ci_[u] = -1;
-                        if (idx < npieces) {
-                            int r = idx >> 2, pc = idx & 3;
-                            int j = c * kChunk + pc * 4;
-                            int soff = j / p.Cin, ci = j - soff * p.Cin;
-                            int vrow = t0 - p.PLr + r;
-                            int src = -1;
-                            if (vrow < p.Tout + (Kr - 1) * p.dil) src = pm.src(vrow * p.vf + soff);
-                            if (src >= 0) {
-                                v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)src * p.ldx + ci));
-                                ci_[u] = ci;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        int idx = base + u * 256 + wtid;
-                        if (idx < npieces) {
-                            float4 x4 = v[u];
-                            if (p.in_alpha && ci_[u] >= 0) {
-                                float4 al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + ci_[u]));
-                                float4 ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + ci_[u]));
-                                x4.x = snake_f(x4.x, al.x, ia.x);
-                                x4.y = snake_f(x4.y, al.y, ia.y);
-                                x4.z = snake_f(x4.z, al.z, ia.z);
-                                x4.w = snake_f(x4.w, al.w, ia.w);
-                            }
-                            float4 hi, lo;
-                            hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
-                            hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
-                            hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
-                            hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
-                            int r = idx >> 2, pc = idx & 3;
-                            size_t off = ((size_t)pc * Rpad + r) * 16;
-                            *reinterpret_cast<float4*>(ahi + off) = hi;
-                            *reinterpret_cast<float4*>(alo + off) = lo;
-                        }
-                    }
-                }
+                produce_chunk<256>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
                 fence_proxy_async();
                 mbar_arrive(&sm->a_full[buf]);
             }
@@ -568,35 +536,12 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
             const int t = t0 + mt * 128 + q * 32 + lane;
             if (t >= p.Tout) continue;
             const int co0 = ntile * N + col;
-            const size_t off = (size_t)t * p.ldy + co0;
+            float* yrow = yb + (size_t)t * p.ldy;
+            const float* rrow = rb ? rb + (size_t)t * p.ldy : nullptr;
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                float o[4];
-                float4 bi = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                o[0] = acc[grp * 16 + j4 * 4 + 0] + bi.x;
-                o[1] = acc[grp * 16 + j4 * 4 + 1] + bi.y;
-                o[2] = acc[grp * 16 + j4 * 4 + 2] + bi.z;
-                o[3] = acc[grp * 16 + j4 * 4 + 3] + bi.w;
-                if (p.out_act == ACT_SNAKE) {
-                    float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co0 + j4 * 4));
-                    float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co0 + j4 * 4));
-                    o[0] = snake_f(o[0], al.x, ia.x);
-                    o[1] = snake_f(o[1], al.y, ia.y);
-                    o[2] = snake_f(o[2], al.z, ia.z);
-                    o[3] = snake_f(o[3], al.w, ia.w);
-                } else if (p.out_act == ACT_TANH) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = tanhf(o[e]);
-                } else if (p.out_act == ACT_MISH) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = mish_f(o[e]);
-                }
-                if (rb) {
-                    float4 rr = *reinterpret_cast<const float4*>(rb + off + j4 * 4);
-                    o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-                }
-                *reinterpret_cast<float4*>(yb + off + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            }
+            for (int j4 = 0; j4 < 4; ++j4)
+                epilogue_store4(p, acc[grp * 16 + j4 * 4 + 0], acc[grp * 16 + j4 * 4 + 1], acc[grp * 16 + j4 * 4 + 2],
+                                acc[grp * 16 + j4 * 4 + 3], co0 + j4 * 4, yrow, rrow);
         }
     }
     tc_fence_before();
