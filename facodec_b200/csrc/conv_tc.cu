@@ -11,14 +11,14 @@
 //   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi     (dropped term a_lo*b_lo ~ 2^-24 |ab|)
 // with fp32 accumulation in TMEM.  Weights are split offline; activations are split in-kernel.
 //
-// CTA = 6 warps, one 128*MT-row x N-channel output tile (MT accumulators in TMEM share every
+// CTA = 10 warps, one 128*MT-row x N-channel output tile (MT accumulators in TMEM share every
 // weight tile, which halves/quarters the L2->SMEM weight traffic per MMA):
 //   warp 0    : weight producer -- one elected lane streams pre-arranged [tap][16 ci] weight
 //               blobs (hi|lo, already in the UMMA K-major core-matrix layout) with 1-D bulk
 //               TMA copies (cp.async.bulk, UBLKCP) into a 4-deep mbarrier ring.
 //   warp 1    : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma.kind::tf32
 //               (M=128, N, K=8) and tcgen05.commit's to free ring slots.
-//   warps 2-5 : activation producers, then epilogue.  Per 16-channel chunk they load the UNION
+//   warps 2-9 : activation producers, then epilogue.  Per 16-channel chunk they load the UNION
 //               of the rows all taps need (128*MT + (K-1)*dil rows) once from HBM with 16-byte
 //               loads (reflect/zero padding = index map, no padded copy), apply Snake, split into
 //               hi/lo and store them in a no-swizzle K-major layout whose row pitch is a uniform
@@ -34,7 +34,7 @@ namespace fac {
 
 namespace tc {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;      // warp 0: weights, warp 1: MMA, warps 2..9: activation producers + epilogue
 constexpr int kChunk = 16;        // K elements (channels) per pipeline chunk
 constexpr int kMaxStagesB = 4;
 
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
 
     if (tid == 0) {
         for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->a_full[i], 256); mbar_init(&sm->a_empty[i], 1); }
         mbar_init(&sm->acc_full, 1);
         fence_mbar_init();
     }
@@ -320,15 +320,15 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
             umma_commit(&sm->acc_full);
         }
     } else {
-        // ================= activation producers (warps 2..5) =================
-        const int ptid = tid - 64;                                  // 0..127
+        // ================= activation producers (warps 2..9) =================
+        const int ptid = tid - 64;                                  // 0..255
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
         const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
         for (int c = 0; c < nchunk; ++c) {
             const int buf = c & 1;
             mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
             uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-            produce_chunk<128>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
+            produce_chunk<256>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
             fence_proxy_async();        // make the generic-proxy stores visible to the tensor core
             mbar_arrive(&sm->a_full[buf]);
         }
@@ -336,6 +336,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         mbar_wait(&sm->acc_full, 0);
         tc_fence_after();
         const int q = warp & 3;                                     // TMEM lane quarter of this warp
+        const int half = (warp - 2) >> 2;                           // two warps per quarter split the columns
+        const int csplit = ((N / 2 + 15) / 16) * 16;
+        const int cbeg = half ? csplit : 0, cend = half ? N : csplit;
         const int row = q * 32 + lane;
         float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
         const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
             float* yrow = yb + (size_t)t * p.ldy;
             const float* rrow = rb ? rb + (size_t)t * p.ldy : nullptr;
 #pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 16) {
+            for (int c0 = cbeg; c0 < cend; c0 += 16) {
                 uint32_t acc[16];
                 tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
                 if (!row_ok) continue;

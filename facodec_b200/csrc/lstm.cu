@@ -6,11 +6,14 @@
 // [c*U, c*U+U) (all four gates), keeps their cell state in shared memory, and exchanges h_t
 // through a [2][H][32] buffer in L2 with one device-wide barrier per step.
 //
-// Per step each CTA computes a [32 batch] x [4U gate rows] x [H] product on the FMA pipe:
-// the 8 warps split H eight ways and stream their slice of W_hh (pre-packed per CTA as
-// [H][4U], so the copy is linear) and of h_{t-1} through private cp.async double buffers;
-// partial sums meet in shared memory, then 32*U threads apply the gate math
-// (PyTorch gate order i, f, g, o).
+// Per step each CTA computes a [4U gate rows] x [32 batch] x [H] product: the 8 warps split H
+// eight ways and stream their slice of W_hh (pre-packed per CTA as [H][4U], so the copy is
+// linear) and of h_{t-1} through private cp.async double buffers, and feed them to the tensor
+// cores as mma.sync m16n8k8 TF32 tiles with the same fp32-faithful 3xTF32 split as the convs
+// (hi/lo formed in registers; 48-72 chained MMAs per accumulator, then an fp32 cross-warp sum).
+// A 32 x 4U x H product per step is far too small for a tcgen05/TMEM tile pipeline -- the step is
+// bounded by the L2 stream of W_hh and the grid barrier, not by the MMAs.  Partial sums meet in
+// shared memory, then 32*U threads apply the gate math (PyTorch gate order i, f, g, o).
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -20,6 +23,21 @@ namespace fac {
 constexpr int LSTM_BT = 32;     // batch tile (columns of hT)
 constexpr int LSTM_WARPS = 8;
 constexpr int LSTM_KS = 16;     // k rows per cp.async sub-chunk
+constexpr int LSTM_D = 3;       // cp.async pipeline depth (stages per warp)
+constexpr int LSTM_HP = LSTM_BT + 8;   // padded smem row of the h sub-chunk (conflict-free fragments)
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -33,10 +51,12 @@ template <int U>
 __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams p) {
     constexpr int R = 4 * U;
     constexpr int RP = R + 1;   // padded row of the reduction buffer (bank-conflict-free reads)
-    constexpr int STAGE_F = LSTM_KS * (LSTM_BT + R);  // floats per stage per warp
+    constexpr int WP = R + 8;                   // padded smem row of the W sub-chunk
+    constexpr int MT = R / 16, NTL = LSTM_BT / 8;
+    constexpr int STAGE_F = LSTM_KS * (LSTM_HP + WP);  // floats per stage per warp
     extern __shared__ __align__(16) float smem[];
-    float* stage_base = smem;                                   // [8 warps][2][STAGE_F]
-    float* red = smem + LSTM_WARPS * 2 * STAGE_F;               // [8][32][R]
+    float* stage_base = smem;                                   // [8 warps][LSTM_D][STAGE_F]
+    float* red = smem + LSTM_WARPS * LSTM_D * STAGE_F;          // [8][32][R]
     float* cstate = red + LSTM_WARPS * LSTM_BT * RP;            // [32][U]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -46,27 +66,44 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
     const int kslice = H / LSTM_WARPS;
     const int k_begin = warp * kslice;
     const int nsub = kslice / LSTM_KS;
-    const int bg = lane >> 2, rg = lane & 3;   // 8 batch groups x 4 gates
+    const int fg = lane >> 2, ft = lane & 3;   // mma fragment coordinates
 
     for (int i = tid; i < LSTM_BT * U; i += blockDim.x) cstate[i] = 0.f;
     __syncthreads();
 
     const float* wsrc = p.whh_p + (size_t)cta * H * R;
-    float* my_stage = stage_base + warp * 2 * STAGE_F;
+    float* my_stage = stage_base + warp * LSTM_D * STAGE_F;
 
     constexpr int PAIRS = (LSTM_BT * U + LSTM_WARPS * 32 - 1) / (LSTM_WARPS * 32);
     for (int t = 0; t < p.T; ++t) {
         // ---- prefetch this step's input-projection gates (independent of the barrier) ----
         float xgv[PAIRS][4];
+        float skv[PAIRS];
 #pragma unroll
         for (int pi = 0; pi < PAIRS; ++pi) {
             int idx = tid + pi * LSTM_WARPS * 32;
             int b = idx % LSTM_BT, u = idx / LSTM_BT;
+            skv[pi] = (p.skip && idx < LSTM_BT * U && b < p.B) ? __ldg(p.skip + ((size_t)b * p.T + t) * H + j0 + u) : 0.f;
 #pragma unroll
             for (int g = 0; g < 4; ++g)
                 xgv[pi][g] = (idx < LSTM_BT * U && b < p.B)
                                  ? __ldg(p.xg + ((size_t)b * p.T + t) * (4 * H) + (size_t)g * H + j0 + u)
                                  : 0.f;
+        }
+        // ---- W_hh tiles do not depend on the barrier: put the first LSTM_D-1 of them in flight now ----
+        auto issue_w = [&](int sub) {
+            float* wsm = my_stage + (sub % LSTM_D) * STAGE_F + LSTM_KS * LSTM_HP;
+            const float* wg = wsrc + (size_t)(k_begin + sub * LSTM_KS) * R;
+#pragma unroll
+            for (int i = lane; i < LSTM_KS * R / 4; i += 32) {
+                int kr = i / (R / 4), c4 = i % (R / 4);
+                cp_async16(wsm + kr * WP + c4 * 4, wg + kr * R + c4 * 4);
+            }
+        };
+#pragma unroll
+        for (int s0 = 0; s0 < LSTM_D - 1; ++s0) {
+            if (s0 < nsub) issue_w(s0);
+            cp_async_commit();
         }
         // ---- wait until every CTA has published h_{t-1} ----
         if (t > 0) {
@@ -81,59 +118,84 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
         }
         const float* hprev = p.hT + (size_t)((t + 1) & 1) * H * LSTM_BT;  // parity of t-1
 
-        float acc[4][U];
+        float acc[MT][NTL][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int j = 0; j < U; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < NTL; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-        auto issue = [&](int sub, int buf) {
-            float* hs = my_stage + buf * STAGE_F;
-            float* wsm = hs + LSTM_KS * LSTM_BT;
+        auto issue_h = [&](int sub) {
+            float* hs = my_stage + (sub % LSTM_D) * STAGE_F;
             const float* hg = hprev + (size_t)(k_begin + sub * LSTM_KS) * LSTM_BT;
-            const float* wg = wsrc + (size_t)(k_begin + sub * LSTM_KS) * R;
 #pragma unroll
-            for (int i = lane; i < LSTM_KS * LSTM_BT / 4; i += 32) cp_async16(hs + i * 4, hg + i * 4);
-#pragma unroll
-            for (int i = lane; i < LSTM_KS * R / 4; i += 32) cp_async16(wsm + i * 4, wg + i * 4);
-            cp_async_commit();
-        };
-
-        issue(0, 0);
-        for (int sub = 0; sub < nsub; ++sub) {
-            int buf = sub & 1;
-            if (sub + 1 < nsub) {
-                issue(sub + 1, buf ^ 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
+            for (int i = lane; i < LSTM_KS * LSTM_BT / 4; i += 32) {
+                int kr = i / (LSTM_BT / 4), c4 = i % (LSTM_BT / 4);
+                cp_async16(hs + kr * LSTM_HP + c4 * 4, hg + kr * LSTM_BT + c4 * 4);
             }
+        };
+#pragma unroll
+        for (int s0 = 0; s0 < LSTM_D - 1; ++s0) {
+            if (s0 < nsub) issue_h(s0);
+            cp_async_commit();
+        }
+        // group order: W0..W(D-2), h0..h(D-2), [W+h](D-1), ... ; tile `sub` is complete once at most
+        // D-1 younger groups are pending (an empty group is committed when nothing is left to issue)
+        for (int sub = 0; sub < nsub; ++sub) {
+            const int nxt = sub + LSTM_D - 1;
+            if (nxt < nsub) { issue_w(nxt); issue_h(nxt); }
+            cp_async_commit();
+            cp_async_wait<LSTM_D - 1>();
             __syncwarp();
-            const float* hs = my_stage + buf * STAGE_F;
-            const float* wsm = hs + LSTM_KS * LSTM_BT;
+            const float* hs = my_stage + (sub % LSTM_D) * STAGE_F;
+            const float* wsm = hs + LSTM_KS * LSTM_HP;
 #pragma unroll
-            for (int k = 0; k < LSTM_KS; ++k) {
-                float4 hv = *reinterpret_cast<const float4*>(hs + k * LSTM_BT + bg * 4);
-                float hb[4] = {hv.x, hv.y, hv.z, hv.w};
-                float wv[U];
+            for (int ks = 0; ks < LSTM_KS / 8; ++ks) {
+                const int k0 = ks * 8;
+                // B fragments: h[k][b], b0 = (k0+ft, n0+fg), b1 = (k0+ft+4, n0+fg); hi/lo split in registers
+                float bh[NTL][2], bl[NTL][2];
 #pragma unroll
-                for (int j = 0; j < U; j += 4) {
-                    float4 w4 = *reinterpret_cast<const float4*>(wsm + k * R + rg * U + j);
-                    wv[j] = w4.x; wv[j + 1] = w4.y; wv[j + 2] = w4.z; wv[j + 3] = w4.w;
+                for (int j = 0; j < NTL; ++j) {
+                    float v0 = hs[(k0 + ft) * LSTM_HP + j * 8 + fg];
+                    float v1 = hs[(k0 + ft + 4) * LSTM_HP + j * 8 + fg];
+                    bh[j][0] = tf32_rn(v0); bl[j][0] = tf32_rn(v0 - bh[j][0]);
+                    bh[j][1] = tf32_rn(v1); bl[j][1] = tf32_rn(v1 - bh[j][1]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < MT; ++i) {
+                    // A fragments: W[r][k] staged as wsm[k][r]; a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4)
+                    float ah[4], al[4];
+                    float w0 = wsm[(k0 + ft) * WP + i * 16 + fg];
+                    float w1 = wsm[(k0 + ft) * WP + i * 16 + fg + 8];
+                    float w2 = wsm[(k0 + ft + 4) * WP + i * 16 + fg];
+                    float w3 = wsm[(k0 + ft + 4) * WP + i * 16 + fg + 8];
+                    ah[0] = tf32_rn(w0); al[0] = tf32_rn(w0 - ah[0]);
+                    ah[1] = tf32_rn(w1); al[1] = tf32_rn(w1 - ah[1]);
+                    ah[2] = tf32_rn(w2); al[2] = tf32_rn(w2 - ah[2]);
+                    ah[3] = tf32_rn(w3); al[3] = tf32_rn(w3 - ah[3]);
 #pragma unroll
-                    for (int j = 0; j < U; ++j) acc[i][j] = fmaf(hb[i], wv[j], acc[i][j]);
+                    for (int j = 0; j < NTL; ++j) {
+                        mma_tf32_16x8x8(acc[i][j], al, bh[j]);     // small terms first
+                        mma_tf32_16x8x8(acc[i][j], ah, bl[j]);
+                        mma_tf32_16x8x8(acc[i][j], ah, bh[j]);
+                    }
+                }
             }
-            __syncwarp();   // everyone done with buf before it is refilled two iterations later
+            __syncwarp();   // everyone done with this stage before it is refilled
         }
-        // ---- cross-warp reduction through shared memory ----
+        // ---- cross-warp reduction through shared memory: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1) ----
         float* myred = red + warp * LSTM_BT * RP;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int j = 0; j < U; ++j) myred[(bg * 4 + i) * RP + rg * U + j] = acc[i][j];
+            for (int j = 0; j < NTL; ++j) {
+                const int r0 = i * 16 + fg, b0 = j * 8 + 2 * ft;
+                myred[b0 * RP + r0] = acc[i][j][0];
+                myred[(b0 + 1) * RP + r0] = acc[i][j][1];
+                myred[b0 * RP + r0 + 8] = acc[i][j][2];
+                myred[(b0 + 1) * RP + r0 + 8] = acc[i][j][3];
+            }
         __syncthreads();
 
         float* hcur = p.hT + (size_t)(t & 1) * H * LSTM_BT;
@@ -157,13 +219,16 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
             hcur[(size_t)(j0 + u) * LSTM_BT + b] = h;
             if (b < p.B) {
                 size_t o = ((size_t)b * p.T + t) * H + j0 + u;
-                p.y[o] = p.skip ? h + p.skip[o] : h;
+                p.y[o] = h + skv[pi];
             }
         }
-        // ---- publish ----
-        __threadfence();
+        // ---- publish: CTA barrier orders every thread's h stores before thread 0, whose gpu-scope
+        // fence is cumulative, then one release-arrive on the grid counter ----
         __syncthreads();
-        if (tid == 0) atomicAdd(p.bar, 1u);
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(p.bar, 1u);
+        }
     }
 }
 
@@ -176,7 +241,7 @@ int lstm_units_per_cta(int H) {
 template <int U>
 static cudaError_t launch_u(const LstmParams& p, cudaStream_t st) {
     constexpr int R = 4 * U;
-    size_t smem = sizeof(float) * (LSTM_WARPS * 2 * LSTM_KS * (LSTM_BT + R) + LSTM_WARPS * LSTM_BT * (R + 1) + LSTM_BT * U);
+    size_t smem = sizeof(float) * (LSTM_WARPS * LSTM_D * LSTM_KS * (LSTM_HP + R + 8) + LSTM_WARPS * LSTM_BT * (R + 1) + LSTM_BT * U);
     cudaError_t e = cudaFuncSetAttribute(lstm_rec_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(p.bar, 0, sizeof(unsigned int), st);
