@@ -196,9 +196,74 @@ __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMa
     }
 }
 
+// Software-pipelined variant for tiles with at most PIPE_P pieces per thread (MT <= 2): the loads
+// of chunk c+1 are issued into registers BEFORE chunk c is transformed, so two chunks of HBM
+// reads are in flight per thread and the load latency hides behind the transform + barrier wait.
+constexpr int PIPE_P = 5;
+struct ChunkRegs { float4 v[PIPE_P]; };
+
+template <int NT>
+__device__ __forceinline__ void load_chunk_regs(const TcConvParams& p, const PadMap& pm, const float* __restrict__ xb,
+                                                int c, int t0, int R, int ptid, ChunkRegs& cr) {
+    const int pc = ptid & 3;
+    const int j = c * kChunk + pc * 4;
+    const int soff = j / p.Cin, ci = j - soff * p.Cin;
+    constexpr int RSTEP = NT / 4;
+    const int row_limit = p.Tout + (p.Kr - 1) * p.dil;
+    const int vrow0 = t0 - p.PLr;
+    const float* __restrict__ xcol = xb + ci;
+#pragma unroll
+    for (int u = 0; u < PIPE_P; ++u) {
+        const int rr = (ptid >> 2) + u * RSTEP;
+        cr.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int vrow = vrow0 + rr;
+        if (rr < R && vrow < row_limit) {
+            const int src = pm.src(vrow * p.vf + soff);
+            if (src >= 0) cr.v[u] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)src * p.ldx));
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void store_chunk_regs(const TcConvParams& p, int c, int R, int Rpad, uint8_t* ahi, uint8_t* alo,
+                                                 int ptid, const ChunkRegs& cr) {
+    const int pc = ptid & 3;
+    const int j = c * kChunk + pc * 4;
+    const int soff = j / p.Cin, ci = j - soff * p.Cin;
+    const bool has_alpha = p.in_alpha != nullptr;
+    float4 al = make_float4(0.f, 0.f, 0.f, 0.f), ia = al;
+    if (has_alpha) {
+        al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + ci));
+        ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + ci));
+    }
+    constexpr int RSTEP = NT / 4;
+    uint8_t* hcol = ahi + (size_t)pc * Rpad * 16;
+    uint8_t* lcol = alo + (size_t)pc * Rpad * 16;
+#pragma unroll
+    for (int u = 0; u < PIPE_P; ++u) {
+        const int rr = (ptid >> 2) + u * RSTEP;
+        if (rr < R) {
+            float4 x4 = cr.v[u];
+            if (has_alpha) {
+                x4.x = snake_fast(x4.x, al.x, ia.x);
+                x4.y = snake_fast(x4.y, al.y, ia.y);
+                x4.z = snake_fast(x4.z, al.z, ia.z);
+                x4.w = snake_fast(x4.w, al.w, ia.w);
+            }
+            float4 hi, lo;
+            hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
+            hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
+            hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
+            hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
+            *reinterpret_cast<float4*>(hcol + (size_t)rr * 16) = hi;
+            *reinterpret_cast<float4*>(lcol + (size_t)rr * 16) = lo;
+        }
+    }
+}
+
 // ---- epilogue for 4 consecutive output channels of one row --------------------------------------
 __device__ __forceinline__ void epilogue_store4(const TcConvParams& p, float o0, float o1, float o2, float o3, int co,
-                                                float* __restrict__ yrow, const float* __restrict__ rrow) {
+                                                float* __restrict__ yrow, bool has_res, float4 rr) {
     if (p.bias) {
         float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
         o0 += bi.x; o1 += bi.y; o2 += bi.z; o3 += bi.w;
@@ -215,10 +280,7 @@ __device__ __forceinline__ void epilogue_store4(const TcConvParams& p, float o0,
     } else if (p.out_act == ACT_MISH) {
         o0 = mish_f(o0); o1 = mish_f(o1); o2 = mish_f(o2); o3 = mish_f(o3);
     }
-    if (rrow) {
-        float4 rr = *reinterpret_cast<const float4*>(rrow + co);
-        o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w;
-    }
+    if (has_res) { o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w; }
     *reinterpret_cast<float4*>(yrow + co) = make_float4(o0, o1, o2, o3);
 }
 
@@ -324,13 +386,29 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         const int ptid = tid - 64;                                  // 0..255
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
         const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
-        for (int c = 0; c < nchunk; ++c) {
-            const int buf = c & 1;
-            mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
-            uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-            produce_chunk<256>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
-            fence_proxy_async();        // make the generic-proxy stores visible to the tensor core
-            mbar_arrive(&sm->a_full[buf]);
+        if (R <= PIPE_P * 64) {
+            // <= 5 pieces per thread: keep the next chunk's loads in flight while transforming this one
+            ChunkRegs cur, nxt;
+            load_chunk_regs<256>(p, pm, xb, 0, t0, R, ptid, cur);
+            for (int c = 0; c < nchunk; ++c) {
+                const int buf = c & 1;
+                if (c + 1 < nchunk) load_chunk_regs<256>(p, pm, xb, c + 1, t0, R, ptid, nxt);
+                mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
+                store_chunk_regs<256>(p, c, R, Rpad, ahi, ahi + a_half, ptid, cur);
+                fence_proxy_async();    // make the generic-proxy stores visible to the tensor core
+                mbar_arrive(&sm->a_full[buf]);
+                cur = nxt;
+            }
+        } else {
+            for (int c = 0; c < nchunk; ++c) {
+                const int buf = c & 1;
+                mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
+                produce_chunk<256>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
+                fence_proxy_async();
+                mbar_arrive(&sm->a_full[buf]);
+            }
         }
         // ================= epilogue =================
         mbar_wait(&sm->acc_full, 0);
@@ -342,23 +420,42 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         const int row = q * 32 + lane;
         float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
         const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
-#pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
+        // flat loop over (mt, 16-column group); the residual of group g+1 is fetched while group g is
+        // drained from TMEM and stored, so its DRAM latency is off the critical path
+        const int ngrp = (cend - cbeg) / 16;
+        const int total = MT * ngrp;
+        const bool has_res = rb != nullptr;
+        float4 rcur[4], rnxt[4];
+        auto fetch_res = [&](int g, float4 (&dst)[4]) {
+            const int mt = g / ngrp, c0 = cbeg + (g - mt * ngrp) * 16;
             const int t = t0 + mt * 128 + row;
-            const bool row_ok = t < p.Tout;
-            float* yrow = yb + (size_t)t * p.ldy;
-            const float* rrow = rb ? rb + (size_t)t * p.ldy : nullptr;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res && t < p.Tout) {
+                const float* rrow = rb + (size_t)t * p.ldy + ntile * N + c0;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) dst[j4] = *reinterpret_cast<const float4*>(rrow + j4 * 4);
+            }
+        };
+        if (total > 0) fetch_res(0, rcur);
 #pragma unroll 1
-            for (int c0 = cbeg; c0 < cend; c0 += 16) {
-                uint32_t acc[16];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
-                if (!row_ok) continue;
+        for (int g = 0; g < total; ++g) {
+            const int mt = g / ngrp, c0 = cbeg + (g - mt * ngrp) * 16;
+            const int t = t0 + mt * 128 + row;
+            if (g + 1 < total) fetch_res(g + 1, rnxt);
+            uint32_t acc[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
+            if (t < p.Tout) {
+                float* yrow = yb + (size_t)t * p.ldy;
                 const int co0 = ntile * N + c0;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4)
                     epilogue_store4(p, __uint_as_float(acc[j4 * 4 + 0]), __uint_as_float(acc[j4 * 4 + 1]),
-                                    __uint_as_float(acc[j4 * 4 + 2]), __uint_as_float(acc[j4 * 4 + 3]), co0 + j4 * 4, yrow, rrow);
+                                    __uint_as_float(acc[j4 * 4 + 2]), __uint_as_float(acc[j4 * 4 + 3]), co0 + j4 * 4, yrow,
+                                    has_res, rcur[j4]);
             }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
         }
     }
     tc_fence_before();
@@ -499,12 +596,22 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
 #pragma unroll
         for (int i = 0; i < 128; ++i) acc[i] = 0.f;
 
+        const bool piped = false;   // register budget (168 with 10 warps) leaves no room for a second chunk in flight here
+        ChunkRegs cur, nxt;
+        if (piped) load_chunk_regs<256>(p, pm, xb, 0, t0, R, wtid, cur);
         for (int c = 0; c <= nchunk; ++c) {
             if (c < nchunk) {
                 const int buf = c & 1;
-                mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
                 uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-                produce_chunk<256>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
+                if (piped) {
+                    if (c + 1 < nchunk) load_chunk_regs<256>(p, pm, xb, c + 1, t0, R, wtid, nxt);
+                    mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                    store_chunk_regs<256>(p, c, R, Rpad, ahi, ahi + a_half, wtid, cur);
+                    cur = nxt;
+                } else {
+                    mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                    produce_chunk<256>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
+                }
                 fence_proxy_async();
                 mbar_arrive(&sm->a_full[buf]);
             }
@@ -540,11 +647,14 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
             if (t >= p.Tout) continue;
             const int co0 = ntile * N + col;
             float* yrow = yb + (size_t)t * p.ldy;
-            const float* rrow = rb ? rb + (size_t)t * p.ldy : nullptr;
+            float4 rr[4];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+                rr[j4] = rb ? *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co0 + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4)
                 epilogue_store4(p, acc[grp * 16 + j4 * 4 + 0], acc[grp * 16 + j4 * 4 + 1], acc[grp * 16 + j4 * 4 + 2],
-                                acc[grp * 16 + j4 * 4 + 3], co0 + j4 * 4, yrow, rrow);
+                                acc[grp * 16 + j4 * 4 + 3], co0 + j4 * 4, yrow, rb != nullptr, rr[j4]);
         }
     }
     tc_fence_before();
