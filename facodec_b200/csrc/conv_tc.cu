@@ -119,6 +119,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes stored as
 // 128 contiguous bytes; SBO = byte pitch between 8-row groups, LBO = byte pitch between the two
 // 16-byte K halves of one K=8 (tf32) MMA; version = 1 (sm_100).
@@ -262,22 +270,23 @@ __device__ __forceinline__ void store_chunk_regs(const TcConvParams& p, int c, i
 }
 
 // ---- epilogue for 4 consecutive output channels of one row --------------------------------------
-__device__ __forceinline__ void epilogue_store4(const TcConvParams& p, float o0, float o1, float o2, float o3, int co,
-                                                float* __restrict__ yrow, bool has_res, float4 rr) {
-    if (p.bias) {
-        float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+__device__ __forceinline__ void epilogue_store4(const TcConvParams& p, const float* __restrict__ bias, int act, float o0,
+                                                float o1, float o2, float o3, int co, float* __restrict__ yrow,
+                                                bool has_res, float4 rr) {
+    if (bias) {
+        float4 bi = __ldg(reinterpret_cast<const float4*>(bias + co));
         o0 += bi.x; o1 += bi.y; o2 += bi.z; o3 += bi.w;
     }
-    if (p.out_act == ACT_SNAKE) {
+    if (act == ACT_SNAKE) {
         float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
         float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
         o0 = snake_fast(o0, al.x, ia.x);
         o1 = snake_fast(o1, al.y, ia.y);
         o2 = snake_fast(o2, al.z, ia.z);
         o3 = snake_fast(o3, al.w, ia.w);
-    } else if (p.out_act == ACT_TANH) {
+    } else if (act == ACT_TANH) {
         o0 = tanhf(o0); o1 = tanhf(o1); o2 = tanhf(o2); o3 = tanhf(o3);
-    } else if (p.out_act == ACT_MISH) {
+    } else if (act == ACT_MISH) {
         o0 = mish_f(o0); o1 = mish_f(o1); o2 = mish_f(o2); o3 = mish_f(o3);
     }
     if (has_res) { o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w; }
@@ -290,12 +299,20 @@ struct Smem {
     uint64_t a_full[2];
     uint64_t a_empty[2];
     uint64_t acc_full;
+    uint64_t acc2_full;
     uint32_t tmem_base;
     uint32_t pad;
 };
 
 }  // namespace tc
 
+// FUSED = true runs a whole ResidualUnit (dac.py:25-42) in one launch when all its channels fit one CTA:
+//   y = x + W1 . snake2(conv7_d(snake1(x)) + b7) + b1
+// GEMM 1 (the dilated conv) accumulates D1 in TMEM columns [0, MT*N); the worker warps then read D1 back
+// 16 columns at a time (tcgen05.ld), add b7, apply Snake, split hi/lo and write it as the K-major A operand
+// of GEMM 2 (the 1x1 conv) into the same double-buffered activation ring; D2 accumulates in TMEM columns
+// [MT*N, 2*MT*N).  The 96/192-channel intermediate never goes to HBM and the K=1 launch disappears.
+template <bool FUSED>
 __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -320,6 +337,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&sm->a_full[i], 256); mbar_init(&sm->a_empty[i], 1); }
         mbar_init(&sm->acc_full, 1);
+        mbar_init(&sm->acc2_full, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&sm->tmem_base, ncols);
@@ -340,6 +358,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                     mbar_arrive_expect_tx(&sm->b_full[s], 2 * b_half);
                     bulk_g2s(b_base + (size_t)s * 2 * b_half, wsrc + (size_t)it * (2 * b_half / 4), 2 * b_half, &sm->b_full[s]);
                 }
+            if (FUSED) {
+                for (int c2 = 0; c2 < p.nchunk2; ++c2, ++it) {
+                    int s = it % S;
+                    mbar_wait(&sm->b_empty[s], ((it / S) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&sm->b_full[s], 2 * b_half);
+                    bulk_g2s(b_base + (size_t)s * 2 * b_half, p.wblob2 + (size_t)c2 * (2 * b_half / 4), 2 * b_half, &sm->b_full[s]);
+                }
+            }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -380,6 +406,38 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                 umma_commit(&sm->a_empty[buf]);         // activation buffer free
             }
             umma_commit(&sm->acc_full);
+            if (FUSED) {
+                for (int c2 = 0; c2 < p.nchunk2; ++c2, ++it) {
+                    const int cc = nchunk + c2, buf = cc & 1;
+                    mbar_wait(&sm->a_full[buf], (cc >> 1) & 1);
+                    const int s = it % S;
+                    mbar_wait(&sm->b_full[s], (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(a_base + (size_t)buf * 2 * a_half);
+                    const uint32_t a_lo = a_hi + a_half;
+                    const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
+                    const uint32_t b_lo = b_hi + b_half;
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t row_off = (uint32_t)(mt * 128) * 16;
+                        const uint32_t d_tmem = tmem + (uint32_t)(MT * N + mt * N);
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
+                            const uint32_t bb = (pass == 1 ? b_lo : b_hi);
+#pragma unroll
+                            for (int ks = 0; ks < kChunk / 8; ++ks) {
+                                uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
+                                uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
+                                uint32_t accum = (c2 | pass | ks) != 0;
+                                umma_tf32(d_tmem, ad, bd, idesc, accum);
+                            }
+                        }
+                    }
+                    umma_commit(&sm->b_empty[s]);
+                    umma_commit(&sm->a_empty[buf]);
+                }
+                umma_commit(&sm->acc2_full);
+            }
         }
     } else {
         // ================= activation producers (warps 2..9) =================
@@ -415,6 +473,76 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         tc_fence_after();
         const int q = warp & 3;                                     // TMEM lane quarter of this warp
         const int half = (warp - 2) >> 2;                           // two warps per quarter split the columns
+        uint32_t d_base = tmem;                                     // accumulator the final epilogue reads
+        const float* ep_bias = p.bias;
+        int ep_act = p.out_act;
+        if (FUSED) {
+            // ---- GEMM-2 operand: snake2(D1 + b7), 16 channels per chunk, straight from TMEM ----
+            for (int c2 = 0; c2 < p.nchunk2; ++c2) {
+                const int cc = nchunk + c2, buf = cc & 1;
+                mbar_wait(&sm->a_empty[buf], ((cc >> 1) & 1) ^ 1);
+                uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
+                uint8_t* alo = ahi + a_half;
+                if (MT == 2) {
+                    const int arow = half * 128 + q * 32 + lane;
+                    uint32_t v[16];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * N + c2 * 16), v);
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc) {
+                        const int co = c2 * 16 + pc * 4;
+                        float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+                        float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
+                        float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
+                        float4 x4;
+                        x4.x = snake_fast(__uint_as_float(v[pc * 4 + 0]) + bi.x, al.x, ia.x);
+                        x4.y = snake_fast(__uint_as_float(v[pc * 4 + 1]) + bi.y, al.y, ia.y);
+                        x4.z = snake_fast(__uint_as_float(v[pc * 4 + 2]) + bi.z, al.z, ia.z);
+                        x4.w = snake_fast(__uint_as_float(v[pc * 4 + 3]) + bi.w, al.w, ia.w);
+                        float4 hi, lo;
+                        hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
+                        hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
+                        hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
+                        hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
+                        const size_t off = ((size_t)pc * Rpad + arow) * 16;
+                        *reinterpret_cast<float4*>(ahi + off) = hi;
+                        *reinterpret_cast<float4*>(alo + off) = lo;
+                    }
+                } else {   // MT == 1: the two warps of a lane quarter take 8 columns each
+                    const int arow = q * 32 + lane;
+                    uint32_t v[8];
+                    tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c2 * 16 + half * 8), v);
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int pc = half * 2 + pp;
+                        const int co = c2 * 16 + pc * 4;
+                        float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+                        float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
+                        float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
+                        float4 x4;
+                        x4.x = snake_fast(__uint_as_float(v[pp * 4 + 0]) + bi.x, al.x, ia.x);
+                        x4.y = snake_fast(__uint_as_float(v[pp * 4 + 1]) + bi.y, al.y, ia.y);
+                        x4.z = snake_fast(__uint_as_float(v[pp * 4 + 2]) + bi.z, al.z, ia.z);
+                        x4.w = snake_fast(__uint_as_float(v[pp * 4 + 3]) + bi.w, al.w, ia.w);
+                        float4 hi, lo;
+                        hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
+                        hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
+                        hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
+                        hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
+                        const size_t off = ((size_t)pc * Rpad + arow) * 16;
+                        *reinterpret_cast<float4*>(ahi + off) = hi;
+                        *reinterpret_cast<float4*>(alo + off) = lo;
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(&sm->a_full[buf]);
+            }
+            mbar_wait(&sm->acc2_full, 0);
+            tc_fence_after();
+            d_base = tmem + (uint32_t)(MT * N);
+            ep_bias = p.bias2;
+            ep_act = ACT_NONE;
+        }
         const int csplit = ((N / 2 + 15) / 16) * 16;
         const int cbeg = half ? csplit : 0, cend = half ? N : csplit;
         const int row = q * 32 + lane;
@@ -444,13 +572,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
             const int t = t0 + mt * 128 + row;
             if (g + 1 < total) fetch_res(g + 1, rnxt);
             uint32_t acc[16];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
+            tmem_ld16(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
             if (t < p.Tout) {
                 float* yrow = yb + (size_t)t * p.ldy;
                 const int co0 = ntile * N + c0;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4)
-                    epilogue_store4(p, __uint_as_float(acc[j4 * 4 + 0]), __uint_as_float(acc[j4 * 4 + 1]),
+                    epilogue_store4(p, ep_bias, ep_act, __uint_as_float(acc[j4 * 4 + 0]), __uint_as_float(acc[j4 * 4 + 1]),
                                     __uint_as_float(acc[j4 * 4 + 2]), __uint_as_float(acc[j4 * 4 + 3]), co0 + j4 * 4, yrow,
                                     has_res, rcur[j4]);
             }
@@ -653,8 +781,8 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                 rr[j4] = rb ? *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co0 + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4)
-                epilogue_store4(p, acc[grp * 16 + j4 * 4 + 0], acc[grp * 16 + j4 * 4 + 1], acc[grp * 16 + j4 * 4 + 2],
-                                acc[grp * 16 + j4 * 4 + 3], co0 + j4 * 4, yrow, rb != nullptr, rr[j4]);
+                epilogue_store4(p, p.bias, p.out_act, acc[grp * 16 + j4 * 4 + 0], acc[grp * 16 + j4 * 4 + 1],
+                                acc[grp * 16 + j4 * 4 + 2], acc[grp * 16 + j4 * 4 + 3], co0 + j4 * 4, yrow, rb != nullptr, rr[j4]);
         }
     }
     tc_fence_before();
@@ -674,6 +802,11 @@ bool tc_conv_plan(TcConvParams& p) {
     if (p.promoted) {
         p.MT = (N <= 64) ? 4 : 2;              // MT * N <= 256 columns per TMEM buffer
         p.promote_every = 8 / p.Kr < 1 ? 1 : 8 / p.Kr;
+    } else if (p.fused) {
+        // whole ResidualUnit in one CTA: every channel in one tile, D1 and D2 both resident in TMEM
+        if (N != p.Cout || p.Cin != p.Cout || p.vf != 1 || N > 256) return false;
+        p.MT = (2 * 2 * N <= 512) ? 2 : 1;
+        p.nchunk2 = p.Cout / tc::kChunk;
     } else {
         p.MT = (N <= 128) ? 4 : 2;
     }
@@ -682,7 +815,7 @@ bool tc_conv_plan(TcConvParams& p) {
     int Rpad = R;
     while (Rpad % 8 != 2) ++Rpad;
     p.Rpad = Rpad;
-    int cols = p.MT * N, pow2 = 32;
+    int cols = p.MT * N * (p.fused ? 2 : 1), pow2 = 32;
     while (pow2 < cols) pow2 <<= 1;
     if (pow2 > 512 || (p.promoted && cols > 256)) return false;
     p.tmem_cols = p.promoted ? 512 : pow2;
@@ -733,7 +866,8 @@ cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
     if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
     static size_t configured = 0;
     if (p.smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
         if (e != cudaSuccess) return e;
         configured = 225 * 1024;
     }
@@ -747,7 +881,8 @@ cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
         }
         conv_tcp_kernel<<<grid, tc::kThreadsP, p.smem_bytes, st>>>(p);
     } else {
-        conv_tc_kernel<<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        if (p.fused) conv_tc_kernel<true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        else conv_tc_kernel<false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
     }
     return cudaGetLastError();
 }

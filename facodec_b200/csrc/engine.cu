@@ -76,6 +76,7 @@ struct fac_handle {
     // tcgen05 3xTF32 path (fac_set_option "tensor_cores"): 0 = never, 1 = layers downstream of the VQ only
     // (decoder, timbre branch), 2 = every eligible layer (default; promoted accumulation upstream of the VQ)
     int use_tc = 2;
+    bool fuse_res = true;           // fused ResidualUnit launches (fac_set_option "fuse_resunit")
     float* aa_filter = nullptr;
     // optional per-kernel-family timing (fac_profile_*): CUDA events around every launch
     bool profiling = false;
@@ -526,8 +527,38 @@ int sconv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int T, int di
     return Tout;
 }
 
+// Whole ResidualUnit in one tcgen05 launch (conv_tc_kernel<true>) when every channel fits one CTA tile.
+bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B, int T) {
+    if (c.h->use_tc < 1 || !c.h->fuse_res || c.vq_critical || !r.c7.tc || !r.c1.tc || r.c7.promoted || r.c1.promoted ||
+        r.c7.Cin != r.c7.Cout || r.c1.K != 1 || r.c7.vf != 1)
+        return false;
+    TcConvParams tp;
+    tp.Cin = r.c7.Cin; tp.Cout = r.c7.Cout; tp.vf = 1; tp.Kr = r.c7.K; tp.dil = r.dil; tp.fused = 1;
+    if (!tc_conv_plan(tp)) return false;
+    if (c.dry) return true;
+    const int k_eff = (r.c7.K - 1) * r.dil + 1;
+    tp.x = x; tp.y = y; tp.res = x;
+    tp.wblob = c.W(r.c7.tcw); tp.bias = c.W(r.c7.b);
+    tp.wblob2 = c.W(r.c1.tcw); tp.bias2 = c.W(r.c1.b);
+    tp.in_alpha = c.W(r.s1.a); tp.in_inv_alpha = c.W(r.s1.ia);
+    tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(r.s2.a); tp.out_inv_alpha = c.W(r.s2.ia);
+    tp.B = B; tp.Tin = T; tp.ldx = r.c7.Cin;
+    tp.PLr = k_eff - 1; tp.pad_left_s = k_eff - 1; tp.pad_right_s = 0; tp.reflect = 1;
+    tp.Tout = T; tp.ldy = r.c7.Cout;
+    tp.x_bstride = (size_t)T * r.c7.Cin; tp.y_bstride = (size_t)T * r.c7.Cout;
+    double flops = 2.0 * B * T * (double)r.c7.Cout * r.c7.Cin * (r.c7.K + 1);
+    double bytes = 4.0 * ((double)B * T * r.c7.Cin * 2 + (double)B * T * r.c7.Cout + (double)(r.c7.K + 1) * r.c7.Cin * r.c7.Cout);
+    char det[96];
+    snprintf(det, sizeof det, "res.fused C%d K%d d%d T%d", r.c7.Cin, r.c7.K, r.dil, T);
+    c.begin("conv_tc", flops, bytes, det);
+    c.check(launch_conv_tc(tp, c.st), "res.fused");
+    c.end();
+    return true;
+}
+
 // ResidualUnit (dac.py:25-42): y = x + conv1(snake2(conv7_d(snake1(x))))
 void residual_unit(Ctx& c, const ResW& r, const float* x, float* tmp, float* y, int B, int T) {
+    if (residual_unit_fused(c, r, x, y, B, T)) return;
     ConvOpts o1;
     o1.in_snake = &r.s1;
     o1.out_snake = &r.s2;
@@ -1159,6 +1190,7 @@ int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, i
 
 int fac_set_option(fac_handle* h, const char* name, int value) {
     if (!h || !name) return FAC_ERR_INVALID;
+    if (std::string(name) == "fuse_resunit") { h->fuse_res = value != 0; return FAC_OK; }
     if (std::string(name) == "tensor_cores") { h->use_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     h->err = std::string("unknown option ") + name;
     return FAC_ERR_INVALID;
@@ -1209,6 +1241,51 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
     cudaFree(d);
     if (e != cudaSuccess) { h->err = std::string("fac_debug_conv_tc: ") + cudaGetErrorString(e); return FAC_ERR_CUDA; }
     return FAC_OK;
+}
+
+int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const float* b7_host, const float* w1_host,
+                      const float* b1_host, const float* alpha1_host, const float* alpha2_host, int B, int T, int C,
+                      int dil, int mode, float* y, void* stream) {
+    if (!h || !x || !y || !w7_host || !w1_host) return FAC_ERR_INVALID;
+    fac_handle tmp;
+    tmp.device = h->device;
+    tmp.use_tc = mode == 0 ? 0 : 1;          // 0: fp32 FMA, 1: two tcgen05 launches, 2: fused launch
+    tmp.fuse_res = mode == 2;
+    auto put = [&](const char* key, const float* d, std::vector<int64_t> shp) {
+        HostTensor t;
+        t.shape = shp;
+        t.data.assign(d, d + t.numel());
+        tmp.host[0][key] = std::move(t);
+    };
+    put("u.block.0.alpha", alpha1_host, {1, C, 1});
+    put("u.block.1.conv.conv.weight", w7_host, {C, C, 7});
+    put("u.block.1.conv.conv.bias", b7_host, {C});
+    put("u.block.2.alpha", alpha2_host, {1, C, 1});
+    put("u.block.3.conv.conv.weight", w1_host, {C, C, 1});
+    put("u.block.3.conv.conv.bias", b1_host, {C});
+    ResW r;
+    try { r = pack_res(&tmp, 0, "u", dil, false); } catch (const PackError& e) { h->err = e.msg; return FAC_ERR_STATE; }
+    cudaSetDevice(h->device);
+    cudaError_t e = cudaMalloc(&tmp.warena, (tmp.pack.size() + 64) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(tmp.warena, tmp.pack.data(), tmp.pack.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* scratch = nullptr;
+    e = cudaMalloc(&scratch, sizeof(float) * (size_t)B * T * C);
+    int rc = FAC_OK;
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = FAC_ERR_CUDA; }
+    if (rc == FAC_OK) {
+        Ctx c{&tmp, st, false};
+        residual_unit(c, r, x, scratch, y, B, T);
+        rc = finish(&tmp, c);
+        cudaError_t e2 = cudaStreamSynchronize(st);
+        if (rc == FAC_OK && e2 != cudaSuccess) { tmp.err = cudaGetErrorString(e2); rc = FAC_ERR_CUDA; }
+        if (rc == FAC_OK && mode == 2 && tmp.launches != 1) { tmp.err = "fused path not taken for this geometry"; rc = FAC_ERR_UNSUPPORTED; }
+    }
+    if (rc != FAC_OK) h->err = tmp.err;
+    if (scratch) cudaFree(scratch);
+    cudaFree(tmp.warena);
+    return rc;
 }
 
 int fac_debug_tap(fac_handle* h, const char* name, float* dst, size_t capacity_floats) {

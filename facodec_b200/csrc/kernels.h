@@ -43,6 +43,10 @@ struct TcConvParams {
     int Tout = 0, Cout = 0, ldy = 0;
     int out_act = 0;
     int promoted = 0;                  // 1 = conv_tcp_kernel (register-promoted accumulation)
+    int fused = 0;                     // 1 = whole ResidualUnit: conv7 -> +b7 -> Snake -> 1x1 conv -> +b1 -> +x
+    const float* wblob2 = nullptr;     // 1x1 conv weight blob (same tile N), when fused
+    const float* bias2 = nullptr;
+    int nchunk2 = 0;
     // plan (tc_conv_plan)
     int promote_every = 1;
     int N = 0, MT = 0, nchunk = 0, Rpad = 0, stagesB = 0, tmem_cols = 0;

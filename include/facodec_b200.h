@@ -108,7 +108,9 @@ int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int a
 /* Engine options.  "tensor_cores": 0 = fp32 FMA kernels everywhere; 1 = tcgen05 3xTF32
  * kernel for every eligible layer downstream of the VQ (decoder, timbre branch), fp32 FMA upstream
  * (encoder, prosody branch); 2 (default) = tcgen05 everywhere, with the register-promoted accumulation
- * variant upstream of the VQ where the bit-exact argmin needs fp32-grade sums. */
+ * variant upstream of the VQ where the bit-exact argmin needs fp32-grade sums.
+ * "fuse_resunit": 1 (default) runs each decoder ResidualUnit whose channels fit one CTA tile as a single
+ * fused launch (conv7 -> Snake -> 1x1 conv -> +x with the intermediate kept in TMEM/SMEM); 0 = two launches. */
 int fac_set_option(fac_handle* h, const char* name, int value);
 
 /* Kernel-level test hooks (used by tests/test_gpu_kernels.py; not part of the drop-in surface).
@@ -130,6 +132,12 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
                       int Cin, int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,
                       const float* in_alpha_host, const float* out_alpha_host, int act, const float* res,
                       float* y, int Tout, int promoted, void* stream);
+/* One ResidualUnit (dac/model/dac.py:25-42) y = x + conv1(snake(conv7_d(snake(x)))) on DEVICE channels-last
+ * x, y [B,T,C] with HOST folded weights w7 [C,C,7], w1 [C,C,1].  mode 0: fp32 FMA kernels, 1: two tcgen05
+ * launches, 2: the single fused tcgen05 launch (FAC_ERR_UNSUPPORTED if the geometry cannot be fused). */
+int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const float* b7_host, const float* w1_host,
+                      const float* b1_host, const float* alpha1_host, const float* alpha2_host, int B, int T, int C,
+                      int dil, int mode, float* y, void* stream);
 int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, int B, int T, int H, float* y,
                     void* stream);
 /* Registers (dst != NULL) or clears a named tap: the next forward copies that channels-last

@@ -163,3 +163,34 @@ def test_conv_tc_kernel_vs_torch(case, promoted, built_lib):
     print(f"TCERR promoted={promoted} case={case} maxerr={err:.3e} scale={scale:.3f} rel_rms={rel_rms:.3e}")
     tol = 4e-6 if promoted else 6e-5        # promoted: fp32-grade; plain: truncating TMEM accumulation
     assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("B,T,C,dil", [(2, 300, 96, 1), (1, 520, 96, 9), (2, 200, 192, 3), (1, 130, 256, 1), (2, 40, 96, 9)])
+def test_residual_unit_modes(B, T, C, dil, mode, built_lib):
+    """ResidualUnit (dac.py:25-42) through the fp32 FMA path, two tcgen05 launches, and the fused launch."""
+    from oracle import facodec_oracle as O
+    e = _engine()
+    g = torch.Generator().manual_seed(C + dil + T)
+    x = torch.randn(B, C, T, generator=g) * 0.5
+    w7 = torch.randn(C, C, 7, generator=g) / math.sqrt(C * 7)
+    w1 = torch.randn(C, C, 1, generator=g) / math.sqrt(C)
+    b7 = torch.randn(C, generator=g) * 0.1
+    b1 = torch.randn(C, generator=g) * 0.1
+    a1 = torch.rand(C, generator=g) + 0.5
+    a2 = torch.rand(C, generator=g) + 0.5
+    sd = {"u.block.0.alpha": a1.view(1, C, 1), "u.block.1.conv.conv.weight": w7, "u.block.1.conv.conv.bias": b7,
+          "u.block.2.alpha": a2.view(1, C, 1), "u.block.3.conv.conv.weight": w1, "u.block.3.conv.conv.bias": b1}
+    ref = O.residual_unit(x, sd, "u", dil)
+    xd = x.transpose(1, 2).contiguous().cuda()
+    yd = torch.full((B, T, C), float("nan"), device="cuda")
+    rc = e.L.fac_debug_resunit(e.handle, _p(xd), _p(w7.contiguous()), _p(b7), _p(w1.contiguous()), _p(b1), _p(a1), _p(a2),
+                               B, T, C, dil, mode, _p(yd), None)
+    assert rc == 0, e.L.fac_last_error(e.handle)
+    y = yd.cpu().transpose(1, 2)
+    assert torch.isfinite(y).all()
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    tol = 2e-5 if mode == 0 else 8e-5
+    print(f"RESUNIT mode={mode} C={C} d={dil} T={T} maxerr={err:.3e} scale={scale:.3f}")
+    assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
