@@ -3,6 +3,7 @@
 // (modules/quantize.py:375-454) and Decoder.forward (dac/model/dac.py:131-165).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>

@@ -207,3 +207,23 @@ def test_error_paths(built_lib):
         m.encoder(torch.zeros(1, 1, 3000))                       # CPU tensor: no fallback
     with pytest.raises(fb.FacError):
         m.quantizer(torch.zeros(1, 1024, 2).cuda(), torch.zeros(1, 1, 600).cuda())   # shorter than STFT padding
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_other_precision_modes_keep_parity(mode, built_lib):
+    """fac_set_option("tensor_cores", 0 | 1): the fp32 FMA path and the decoder-only tensor-core path
+    stay correct (default mode 2 is what every other test runs)."""
+    c = GOLDEN_CASES["b2_t7200"]
+    g = load_golden("b2_t7200")
+    m = model_for(c["wseed"])
+    eng = m.encoder._engine
+    x, kw = case_inputs(c)
+    try:
+        eng.set_option("tensor_cores", mode, torch.device("cuda:0"))
+        z, q, y = run_model(m, x, c["n_c"], kw)
+    finally:
+        eng.set_option("tensor_cores", 2, torch.device("cuda:0"))
+    for k, t in zip(("codes_p", "codes_c", "codes_r"), q[5]):
+        assert np.array_equal(t.cpu().numpy(), g[k]), k
+    assert np.abs(z.cpu().numpy() - g["z"]).max() <= Z_RTOL * np.abs(g["z"]).max()
+    assert rms(y, g["y"]) <= (2e-7 if mode == 0 else RMS_TOL)
