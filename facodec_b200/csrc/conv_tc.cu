@@ -32,6 +32,9 @@
 
 namespace fac {
 
+// phase timestamps (clock64) of one probe CTA of the last conv_tc_kernel launch: kernel-tuning aid
+__device__ long long g_tc_phase_clock[8];
+
 namespace tc {
 
 constexpr int kThreads = 320;      // warp 0: weights, warp 1: MMA, warps 2..9: activation producers + epilogue
@@ -293,6 +296,57 @@ __device__ __forceinline__ void epilogue_store4(const TcConvParams& p, const flo
     *reinterpret_cast<float4*>(yrow + co) = make_float4(o0, o1, o2, o3);
 }
 
+// ---- coalesced epilogue of one warp tile -------------------------------------------------------
+// tcgen05.ld hands every lane one ROW (32 consecutive channels of its time step).  Storing that
+// directly touches 32 different 128-byte lines per instruction (measured: ~3000 cycles per
+// 16-column group, the epilogue was 30-50 % of a CTA).  Instead the warp parks its 32x32 tile in
+// shared memory (row pitch 36 floats: conflict-free 16-byte accesses both ways) and reads it back
+// so that 8 lanes cover 128 contiguous bytes of one row: every global load/store instruction
+// (residual in, result out) then touches 4 full lines instead of 32 partial ones.
+__device__ __forceinline__ void epilogue_tile32(const TcConvParams& p, const float* __restrict__ bias, int act,
+                                                const float (&v)[32], float* stage /* [32][36] per warp */, int lane,
+                                                int t_first /* time step of tile row 0 */, int co0 /* channel of col 0 */,
+                                                float* __restrict__ yb, const float* __restrict__ rb) {
+    const int c4 = lane & 7, rsub = lane >> 3;
+    const int co = co0 + c4 * 4;
+    // residual rows for this lane's 8 (row, 16-byte column chunk) slots: issued first, consumed last
+    float4 rr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int t = t_first + 4 * i + rsub;
+        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rb && t < p.Tout) rr[i] = *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+    __syncwarp();
+    float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), al = bi, ia = bi;
+    if (bias) bi = __ldg(reinterpret_cast<const float4*>(bias + co));
+    if (act == ACT_SNAKE) {
+        al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
+        ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + rsub;
+        const int t = t_first + row;
+        float4 o = *reinterpret_cast<const float4*>(stage + row * 36 + c4 * 4);
+        o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
+        if (act == ACT_SNAKE) {
+            o.x = snake_fast(o.x, al.x, ia.x); o.y = snake_fast(o.y, al.y, ia.y);
+            o.z = snake_fast(o.z, al.z, ia.z); o.w = snake_fast(o.w, al.w, ia.w);
+        } else if (act == ACT_TANH) {
+            o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
+        } else if (act == ACT_MISH) {
+            o.x = mish_f(o.x); o.y = mish_f(o.y); o.z = mish_f(o.z); o.w = mish_f(o.w);
+        }
+        o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w;
+        if (t < p.Tout) *reinterpret_cast<float4*>(yb + (size_t)t * p.ldy + co) = o;
+    }
+    __syncwarp();
+}
+
 struct Smem {
     uint64_t b_full[kMaxStagesB];
     uint64_t b_empty[kMaxStagesB];
@@ -442,6 +496,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
     } else {
         // ================= activation producers (warps 2..9) =================
         const int ptid = tid - 64;                                  // 0..255
+        const bool probe = (ptid == 0 && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0);
+        if (probe) g_tc_phase_clock[0] = clock64();
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
         const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
         if (R <= PIPE_P * 64) {
@@ -469,8 +525,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
             }
         }
         // ================= epilogue =================
+        if (probe) g_tc_phase_clock[1] = clock64();                 // all activation chunks produced
         mbar_wait(&sm->acc_full, 0);
         tc_fence_after();
+        if (probe) g_tc_phase_clock[2] = clock64();                 // GEMM 1 retired
         const int q = warp & 3;                                     // TMEM lane quarter of this warp
         const int half = (warp - 2) >> 2;                           // two warps per quarter split the columns
         uint32_t d_base = tmem;                                     // accumulator the final epilogue reads
@@ -537,8 +595,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                 fence_proxy_async();
                 mbar_arrive(&sm->a_full[buf]);
             }
+            if (probe) g_tc_phase_clock[3] = clock64();             // GEMM-2 operand produced
             mbar_wait(&sm->acc2_full, 0);
             tc_fence_after();
+            if (probe) g_tc_phase_clock[4] = clock64();             // GEMM 2 retired
             d_base = tmem + (uint32_t)(MT * N);
             ep_bias = p.bias2;
             ep_act = ACT_NONE;
@@ -548,6 +608,25 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         const int row = q * 32 + lane;
         float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
         const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
+        if ((N & 31) == 0) {
+            // coalesced path: 32-column groups through the (now idle) activation buffers as transpose stage
+            float* stage = reinterpret_cast<float*>(a_base) + (size_t)(warp - 2) * (32 * 36);
+            const int ng = N / 32, gsplit = (ng + 1) / 2;
+            const int gbeg = half ? gsplit : 0, gend = half ? ng : gsplit;
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll 1
+                for (int g = gbeg; g < gend; ++g) {
+                    uint32_t acc[32];
+                    tmem_ld32(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + g * 32), acc);
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+                    epilogue_tile32(p, ep_bias, ep_act, v, stage, lane, t0 + mt * 128 + q * 32, ntile * N + g * 32, yb, rb);
+                }
+            }
+            if (probe) g_tc_phase_clock[5] = clock64();
+        } else {
         // flat loop over (mt, 16-column group); the residual of group g+1 is fetched while group g is
         // drained from TMEM and stored, so its DRAM latency is off the critical path
         const int ngrp = (cend - cbeg) / 16;
@@ -584,6 +663,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
             }
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
+        }
+        if (probe) g_tc_phase_clock[5] = clock64();                 // epilogue done
         }
     }
     tc_fence_before();
@@ -766,6 +847,22 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
         // ================= epilogue from registers =================
         float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
         const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
+        if ((N & 31) == 0 && (mycols & 31) == 0 && (mycol0 & 31) == 0) {
+            // all MMAs have retired (last promotion waited on them): the activation buffers are free to
+            // serve as the per-warp transpose stage of the coalesced epilogue
+            float* stage = reinterpret_cast<float*>(a_base) + (size_t)(warp - 2) * (32 * 36);
+#pragma unroll
+            for (int gp = 0; gp < 4; ++gp) {
+                if (gp * 32 < mycols) {
+                    const int j0 = mycol0 + gp * 32;
+                    const int mt = j0 / N, col = j0 - mt * N;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = acc[gp * 32 + i];
+                    epilogue_tile32(p, p.bias, p.out_act, v, stage, lane, t0 + mt * 128 + q * 32, ntile * N + col, yb, rb);
+                }
+            }
+        } else
 #pragma unroll
         for (int grp = 0; grp < 8; ++grp) {
             if (grp * 16 >= mycols) continue;
@@ -860,6 +957,10 @@ void tc_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob) 
                                 memcpy(&lo_r, &lu, 4);
                                 blob[o++] = hl == 0 ? hi : lo_r;
                             }
+}
+
+cudaError_t tc_read_phase_clocks(long long* out8) {
+    return cudaMemcpyFromSymbol(out8, g_tc_phase_clock, sizeof(long long) * 8);
 }
 
 cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {

@@ -1289,6 +1289,15 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
     return rc;
 }
 
+int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8) {
+    if (!h || !out8) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaError_t e = tc_read_phase_clocks(out8);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
+}
+
 int fac_debug_tap(fac_handle* h, const char* name, float* dst, size_t capacity_floats) {
     if (!h || !name) return FAC_ERR_INVALID;
     if (!dst) h->taps.erase(name);

@@ -57,6 +57,7 @@ bool tc_conv_plan(TcConvParams& p);
 size_t tc_blob_floats(const TcConvParams& p);
 void tc_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob);
 cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st);
+cudaError_t tc_read_phase_clocks(long long* out8);   // probe-CTA phase timestamps of the last conv_tc_kernel
 
 // ---- LSTM recurrence (lstm.cu) -----------------------------------------------------------
 // One nn.LSTM layer over all T steps for up to 32 sequences (dac/model/encodec.py:272-288).

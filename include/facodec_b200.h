@@ -138,6 +138,10 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
 int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const float* b7_host, const float* w1_host,
                       const float* b1_host, const float* alpha1_host, const float* alpha2_host, int B, int T, int C,
                       int dil, int mode, float* y, void* stream);
+/* clock64() phase timestamps written by one probe CTA of the most recent conv_tc_kernel launch:
+ * [0] start, [1] all activation chunks produced, [2] GEMM 1 retired, [3] GEMM-2 operand produced (fused),
+ * [4] GEMM 2 retired (fused), [5] epilogue done.  Kernel-tuning aid. */
+int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8);
 int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, int B, int T, int H, float* y,
                     void* stream);
 /* Registers (dst != NULL) or clears a named tap: the next forward copies that channels-last
