@@ -25,6 +25,8 @@
 //               16 bytes, so each tap is just a descriptor start-address offset of tap*dil rows
 //               (taps are never re-loaded or im2col'ed).  Epilogue: tcgen05.ld -> bias ->
 //               Snake/tanh/Mish -> residual -> 128-byte row stores.
+#include <cuda_bf16.h>
+
 #include <cstring>
 
 #include "common.cuh"
@@ -96,6 +98,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if constexpr (BF16) umma_bf16(tmem_d, adesc, bdesc, idesc, accum);
+    else umma_tf32(tmem_d, adesc, bdesc, idesc, accum);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -149,11 +164,40 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 
+// hi/lo split of 4 consecutive channels of one row + store into the K-major operand buffers.
+//   TF32 (BF16 = false): hi = rna_tf32(x), lo = rna_tf32(x - hi); 16-byte piece pc of 4 per 16-channel chunk.
+//   BF16 (BF16 = true) : hi = rn_bf16(x), lo = rn_bf16(x - hi) (16 mantissa bits in total: used downstream of the
+//   VQ only); 8 bytes = half of 16-byte k-group pc/2 (a k-group is 8 bf16 channels).
+template <bool BF16>
+__device__ __forceinline__ void split_store(float4 x4, int pc, int row, int Rpad, uint8_t* ahi, uint8_t* alo) {
+    if constexpr (!BF16) {
+        float4 hi, lo;
+        hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
+        hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
+        hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
+        hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
+        const size_t off = ((size_t)pc * Rpad + row) * 16;
+        *reinterpret_cast<float4*>(ahi + off) = hi;
+        *reinterpret_cast<float4*>(alo + off) = lo;
+    } else {
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(x4.x, x4.y), h23 = __floats2bfloat162_rn(x4.z, x4.w);
+        float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        __nv_bfloat162 l01 = __floats2bfloat162_rn(x4.x - f01.x, x4.y - f01.y);
+        __nv_bfloat162 l23 = __floats2bfloat162_rn(x4.z - f23.x, x4.w - f23.y);
+        const size_t off = ((size_t)(pc >> 1) * Rpad + row) * 16 + (size_t)(pc & 1) * 8;
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(ahi + off) = hv;
+        *reinterpret_cast<uint2*>(alo + off) = lv;
+    }
+}
+
 // ---- activation producer shared by both kernels ------------------------------------------------
 // Thread `ptid` of NT producer threads owns 16-byte piece pc = ptid & 3 (4 input channels) of
 // rows ptid/4, ptid/4 + NT/4, ...: channel offset, Snake parameters and the smem column are
 // per-thread constants for the whole chunk; only the row varies.
-template <int NT>
+template <int NT, bool BF16>
 __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMap& pm, const float* __restrict__ xb,
                                               int c, int t0, int R, int Rpad, uint8_t* ahi, uint8_t* alo, int ptid) {
     const int pc = ptid & 3;
@@ -169,8 +213,6 @@ __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMa
     const int row_limit = p.Tout + (p.Kr - 1) * p.dil;
     const int vrow0 = t0 - p.PLr;
     const float* __restrict__ xcol = xb + ci;
-    uint8_t* hcol = ahi + (size_t)pc * Rpad * 16;
-    uint8_t* lcol = alo + (size_t)pc * Rpad * 16;
 #pragma unroll 1
     for (int r = ptid >> 2; r < R; r += RSTEP * 4) {
         float4 v[4];
@@ -195,13 +237,7 @@ __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMa
                     x4.z = snake_fast(x4.z, al.z, ia.z);
                     x4.w = snake_fast(x4.w, al.w, ia.w);
                 }
-                float4 hi, lo;
-                hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
-                hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
-                hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
-                hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
-                *reinterpret_cast<float4*>(hcol + (size_t)rr * 16) = hi;
-                *reinterpret_cast<float4*>(lcol + (size_t)rr * 16) = lo;
+                split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
             }
         }
     }
@@ -235,7 +271,7 @@ __device__ __forceinline__ void load_chunk_regs(const TcConvParams& p, const Pad
     }
 }
 
-template <int NT>
+template <int NT, bool BF16>
 __device__ __forceinline__ void store_chunk_regs(const TcConvParams& p, int c, int R, int Rpad, uint8_t* ahi, uint8_t* alo,
                                                  int ptid, const ChunkRegs& cr) {
     const int pc = ptid & 3;
@@ -248,8 +284,6 @@ __device__ __forceinline__ void store_chunk_regs(const TcConvParams& p, int c, i
         ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + ci));
     }
     constexpr int RSTEP = NT / 4;
-    uint8_t* hcol = ahi + (size_t)pc * Rpad * 16;
-    uint8_t* lcol = alo + (size_t)pc * Rpad * 16;
 #pragma unroll
     for (int u = 0; u < PIPE_P; ++u) {
         const int rr = (ptid >> 2) + u * RSTEP;
@@ -261,13 +295,7 @@ __device__ __forceinline__ void store_chunk_regs(const TcConvParams& p, int c, i
                 x4.z = snake_fast(x4.z, al.z, ia.z);
                 x4.w = snake_fast(x4.w, al.w, ia.w);
             }
-            float4 hi, lo;
-            hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
-            hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
-            hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
-            hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
-            *reinterpret_cast<float4*>(hcol + (size_t)rr * 16) = hi;
-            *reinterpret_cast<float4*>(lcol + (size_t)rr * 16) = lo;
+            split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
         }
     }
 }
@@ -366,16 +394,22 @@ struct Smem {
 // 16 columns at a time (tcgen05.ld), add b7, apply Snake, split hi/lo and write it as the K-major A operand
 // of GEMM 2 (the 1x1 conv) into the same double-buffered activation ring; D2 accumulates in TMEM columns
 // [MT*N, 2*MT*N).  The 96/192-channel intermediate never goes to HBM and the K=1 launch disappears.
-template <bool FUSED>
+// BF16 = true (decoder only): operands split into bf16 hi + bf16 lo instead of tf32 hi + tf32 lo, issued as
+// tcgen05.mma.kind::f16 with K = 16.  Half the MMA instructions and half the shared-memory operand bytes
+// per channel (the SS-mode TF32 MMAs are shared-memory-bandwidth bound for N <= 192); 16 mantissa bits
+// keep the waveform error at ~1e-5 RMS, well inside the 1e-4 bar, but not VQ-exact -- never used upstream.
+template <bool FUSED, bool BF16>
 __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem* sm = reinterpret_cast<Smem*>(smem_raw);
+    constexpr int KG = BF16 ? 2 : 4;                        // 16-byte k-groups per 16-channel chunk
+    constexpr int KSTEPS = BF16 ? 1 : 2;                    // MMAs per chunk and pass (K = 16 / K = 8)
     const int N = p.N, MT = p.MT;
     const int R = 128 * MT + (p.Kr - 1) * p.dil;            // union of rows all taps touch
     const int Rpad = p.Rpad;                                // R rounded so that Rpad % 8 == 2
-    const uint32_t a_half = (uint32_t)Rpad * 16 * 4;        // bytes of one hi (or lo) A buffer
-    const uint32_t b_half = (uint32_t)N * 16 * 4;           // bytes of one hi (or lo) weight tile
+    const uint32_t a_half = (uint32_t)Rpad * 16 * KG;       // bytes of one hi (or lo) A buffer
+    const uint32_t b_half = (uint32_t)N * 16 * KG;          // bytes of one hi (or lo) weight tile
     uint8_t* a_base = smem_raw + 128;                       // [2 bufs][hi|lo][4 k4][Rpad][16B]
     uint8_t* b_base = a_base + 4 * a_half;                  // [S][hi|lo][4 k4][N][16B]
     const int S = p.stagesB;
@@ -425,7 +459,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         // ================= MMA issuer =================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=tf32, K-major both, N>>3, M=128>>4
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t fmt = BF16 ? 1u : 2u;   // F16F32Format: BF16 = 1, TF32 = 2
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t a_lbo = (uint32_t)Rpad * 16, b_lbo = (uint32_t)N * 16;
             int it = 0;
             for (int c = 0; c < nchunk; ++c) {
@@ -447,11 +482,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                             const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
                             const uint32_t bb = (pass == 1 ? b_lo : b_hi);
 #pragma unroll
-                            for (int ks = 0; ks < kChunk / 8; ++ks) {
+                            for (int ks = 0; ks < KSTEPS; ++ks) {
                                 uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
                                 uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
                                 uint32_t accum = (c | tap | pass | ks) != 0;
-                                umma_tf32(d_tmem, ad, bd, idesc, accum);
+                                umma<BF16>(d_tmem, ad, bd, idesc, accum);
                             }
                         }
                     }
@@ -479,11 +514,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                             const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
                             const uint32_t bb = (pass == 1 ? b_lo : b_hi);
 #pragma unroll
-                            for (int ks = 0; ks < kChunk / 8; ++ks) {
+                            for (int ks = 0; ks < KSTEPS; ++ks) {
                                 uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
                                 uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
                                 uint32_t accum = (c2 | pass | ks) != 0;
-                                umma_tf32(d_tmem, ad, bd, idesc, accum);
+                                umma<BF16>(d_tmem, ad, bd, idesc, accum);
                             }
                         }
                     }
@@ -509,7 +544,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                 if (c + 1 < nchunk) load_chunk_regs<256>(p, pm, xb, c + 1, t0, R, ptid, nxt);
                 mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
                 uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-                store_chunk_regs<256>(p, c, R, Rpad, ahi, ahi + a_half, ptid, cur);
+                store_chunk_regs<256, BF16>(p, c, R, Rpad, ahi, ahi + a_half, ptid, cur);
                 fence_proxy_async();    // make the generic-proxy stores visible to the tensor core
                 mbar_arrive(&sm->a_full[buf]);
                 cur = nxt;
@@ -519,7 +554,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                 const int buf = c & 1;
                 mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
                 uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-                produce_chunk<256>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
+                produce_chunk<256, BF16>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
                 fence_proxy_async();
                 mbar_arrive(&sm->a_full[buf]);
             }
@@ -556,14 +591,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                         x4.y = snake_fast(__uint_as_float(v[pc * 4 + 1]) + bi.y, al.y, ia.y);
                         x4.z = snake_fast(__uint_as_float(v[pc * 4 + 2]) + bi.z, al.z, ia.z);
                         x4.w = snake_fast(__uint_as_float(v[pc * 4 + 3]) + bi.w, al.w, ia.w);
-                        float4 hi, lo;
-                        hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
-                        hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
-                        hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
-                        hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
-                        const size_t off = ((size_t)pc * Rpad + arow) * 16;
-                        *reinterpret_cast<float4*>(ahi + off) = hi;
-                        *reinterpret_cast<float4*>(alo + off) = lo;
+                        split_store<BF16>(x4, pc, arow, Rpad, ahi, alo);
                     }
                 } else {   // MT == 1: the two warps of a lane quarter take 8 columns each
                     const int arow = q * 32 + lane;
@@ -581,14 +609,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                         x4.y = snake_fast(__uint_as_float(v[pp * 4 + 1]) + bi.y, al.y, ia.y);
                         x4.z = snake_fast(__uint_as_float(v[pp * 4 + 2]) + bi.z, al.z, ia.z);
                         x4.w = snake_fast(__uint_as_float(v[pp * 4 + 3]) + bi.w, al.w, ia.w);
-                        float4 hi, lo;
-                        hi.x = to_tf32(x4.x); lo.x = to_tf32(x4.x - hi.x);
-                        hi.y = to_tf32(x4.y); lo.y = to_tf32(x4.y - hi.y);
-                        hi.z = to_tf32(x4.z); lo.z = to_tf32(x4.z - hi.z);
-                        hi.w = to_tf32(x4.w); lo.w = to_tf32(x4.w - hi.w);
-                        const size_t off = ((size_t)pc * Rpad + arow) * 16;
-                        *reinterpret_cast<float4*>(ahi + off) = hi;
-                        *reinterpret_cast<float4*>(alo + off) = lo;
+                        split_store<BF16>(x4, pc, arow, Rpad, ahi, alo);
                     }
                 }
                 tc_fence_before();
@@ -815,11 +836,11 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                 if (piped) {
                     if (c + 1 < nchunk) load_chunk_regs<256>(p, pm, xb, c + 1, t0, R, wtid, nxt);
                     mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
-                    store_chunk_regs<256>(p, c, R, Rpad, ahi, ahi + a_half, wtid, cur);
+                    store_chunk_regs<256, false>(p, c, R, Rpad, ahi, ahi + a_half, wtid, cur);
                     cur = nxt;
                 } else {
                     mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
-                    produce_chunk<256>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
+                    produce_chunk<256, false>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
                 }
                 fence_proxy_async();
                 mbar_arrive(&sm->a_full[buf]);
@@ -916,8 +937,10 @@ bool tc_conv_plan(TcConvParams& p) {
     while (pow2 < cols) pow2 <<= 1;
     if (pow2 > 512 || (p.promoted && cols > 256)) return false;
     p.tmem_cols = p.promoted ? 512 : pow2;
-    size_t a_bytes = (size_t)4 * Rpad * 16 * 4;         // 2 bufs x (hi,lo)
-    size_t b_stage = (size_t)2 * N * 16 * 4;
+    const int KG = p.bf16 ? 2 : 4;
+    if (p.bf16 && p.promoted) return false;
+    size_t a_bytes = (size_t)4 * Rpad * 16 * KG;        // 2 bufs x (hi,lo)
+    size_t b_stage = (size_t)2 * N * 16 * KG;
     int S = tc::kMaxStagesB;
     while (S > 2 && 128 + a_bytes + S * b_stage > 225 * 1024) --S;
     if (128 + a_bytes + S * b_stage > 225 * 1024) return false;
@@ -927,12 +950,40 @@ bool tc_conv_plan(TcConvParams& p) {
 }
 
 size_t tc_blob_floats(const TcConvParams& p) {
-    return (size_t)(p.Cout / p.N) * p.nchunk * p.Kr * 2 * 4 * p.N * 4;
+    return (size_t)(p.Cout / p.N) * p.nchunk * p.Kr * 2 * (p.bf16 ? 2 : 4) * p.N * 4;
+}
+
+static inline uint16_t bf16_rn_host(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
 }
 
 // wp: packed generic weights [Kr * vf*Cin][ldw] (conv_simt layout).  blob: see file header.
 void tc_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob) {
     const int Cw = p.Cin * p.vf;   // columns per row-tap
+    if (p.bf16) {
+        // [ntile][chunk][tap][hi|lo][k8 (2)][N][8 bf16]
+        uint16_t* ob = reinterpret_cast<uint16_t*>(blob);
+        size_t o16 = 0;
+        for (int nt = 0; nt < p.Cout / p.N; ++nt)
+            for (int c = 0; c < p.nchunk; ++c)
+                for (int tap = 0; tap < p.Kr; ++tap)
+                    for (int hl = 0; hl < 2; ++hl)
+                        for (int k8 = 0; k8 < 2; ++k8)
+                            for (int n = 0; n < p.N; ++n)
+                                for (int e = 0; e < 8; ++e) {
+                                    int kk = tap * Cw + c * tc::kChunk + k8 * 8 + e;
+                                    float w = wp[(size_t)kk * ldw + nt * p.N + n];
+                                    uint16_t hi = bf16_rn_host(w);
+                                    uint32_t hu = (uint32_t)hi << 16;
+                                    float hf;
+                                    memcpy(&hf, &hu, 4);
+                                    ob[o16++] = hl == 0 ? hi : bf16_rn_host(w - hf);
+                                }
+        return;
+    }
     size_t o = 0;
     for (int nt = 0; nt < p.Cout / p.N; ++nt)
         for (int c = 0; c < p.nchunk; ++c)
@@ -967,8 +1018,10 @@ cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
     if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
     static size_t configured = 0;
     if (p.smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
         if (e != cudaSuccess) return e;
         configured = 225 * 1024;
     }
@@ -982,8 +1035,10 @@ cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
         }
         conv_tcp_kernel<<<grid, tc::kThreadsP, p.smem_bytes, st>>>(p);
     } else {
-        if (p.fused) conv_tc_kernel<true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
-        else conv_tc_kernel<false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        if (p.fused && p.bf16) conv_tc_kernel<true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        else if (p.fused) conv_tc_kernel<true, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        else if (p.bf16) conv_tc_kernel<false, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        else conv_tc_kernel<false, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
     }
     return cudaGetLastError();
 }

@@ -36,6 +36,7 @@ struct ConvW {
     // tensor-core blob (conv_tc.cu): present when the layer is eligible
     bool tc = false; size_t tcw = 0; int vf = 1, Kr = 0;
     bool promoted = false;   // blob built for conv_tcp_kernel (layers upstream of the VQ)
+    bool has16 = false; size_t tcw16 = 0;   // bf16 hi/lo blob (non-promoted layers only)
 };
 struct SnakeW { size_t a = 0, ia = 0; int C = 0; };
 struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; int H = 0, U = 0, G = 0; };
@@ -78,6 +79,7 @@ struct fac_handle {
     // (decoder, timbre branch), 2 = every eligible layer (default; promoted accumulation upstream of the VQ)
     int use_tc = 2;
     bool fuse_res = true;           // fused ResidualUnit launches (fac_set_option "fuse_resunit")
+    bool dec_bf16 = true;           // decoder-side layers use the bf16x3 split (fac_set_option "decoder_bf16")
     float* aa_filter = nullptr;
     // optional per-kernel-family timing (fac_profile_*): CUDA events around every launch
     bool profiling = false;
@@ -147,6 +149,15 @@ void attach_tc(fac_handle* h, ConvW& c, int stride, bool promoted) {
     c.tcw = pack_alloc(h, n);
     tc_pack_blob(tp, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw);
     c.tc = true;
+    if (!promoted) {
+        TcConvParams t16 = tp;
+        t16.bf16 = 1;
+        if (tc_conv_plan(t16) && t16.N == tp.N) {
+            c.tcw16 = pack_alloc(h, tc_blob_floats(t16));
+            tc_pack_blob(t16, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw16);
+            c.has16 = true;
+        }
+    }
 }
 
 // nn.Conv1d [Cout][Cin][K] -> packed [K*Cin][ldw]
@@ -469,8 +480,9 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
         TcConvParams tp;
         tp.Cin = w.Cin; tp.Cout = w.Cout; tp.vf = w.vf; tp.Kr = w.Kr; tp.promoted = w.promoted ? 1 : 0;
         tp.dil = w.vf == 1 ? o.dil : 1;
+        tp.bf16 = (c.h->dec_bf16 && w.has16 && !c.vq_critical) ? 1 : 0;
         if (tc_conv_plan(tp)) {
-            tp.x = x; tp.y = y; tp.wblob = c.W(w.tcw); tp.bias = c.W(w.b);
+            tp.x = x; tp.y = y; tp.wblob = c.W(tp.bf16 ? w.tcw16 : w.tcw); tp.bias = c.W(w.b);
             if (o.in_snake) { tp.in_alpha = c.W(o.in_snake->a); tp.in_inv_alpha = c.W(o.in_snake->ia); }
             tp.out_act = o.act;
             if (o.out_snake) { tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(o.out_snake->a); tp.out_inv_alpha = c.W(o.out_snake->ia); }
@@ -535,12 +547,13 @@ bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B,
         return false;
     TcConvParams tp;
     tp.Cin = r.c7.Cin; tp.Cout = r.c7.Cout; tp.vf = 1; tp.Kr = r.c7.K; tp.dil = r.dil; tp.fused = 1;
+    tp.bf16 = (c.h->dec_bf16 && r.c7.has16 && r.c1.has16) ? 1 : 0;
     if (!tc_conv_plan(tp)) return false;
     if (c.dry) return true;
     const int k_eff = (r.c7.K - 1) * r.dil + 1;
     tp.x = x; tp.y = y; tp.res = x;
-    tp.wblob = c.W(r.c7.tcw); tp.bias = c.W(r.c7.b);
-    tp.wblob2 = c.W(r.c1.tcw); tp.bias2 = c.W(r.c1.b);
+    tp.wblob = c.W(tp.bf16 ? r.c7.tcw16 : r.c7.tcw); tp.bias = c.W(r.c7.b);
+    tp.wblob2 = c.W(tp.bf16 ? r.c1.tcw16 : r.c1.tcw); tp.bias2 = c.W(r.c1.b);
     tp.in_alpha = c.W(r.s1.a); tp.in_inv_alpha = c.W(r.s1.ia);
     tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(r.s2.a); tp.out_inv_alpha = c.W(r.s2.ia);
     tp.B = B; tp.Tin = T; tp.ldx = r.c7.Cin;
@@ -1192,6 +1205,7 @@ int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, i
 int fac_set_option(fac_handle* h, const char* name, int value) {
     if (!h || !name) return FAC_ERR_INVALID;
     if (std::string(name) == "fuse_resunit") { h->fuse_res = value != 0; return FAC_OK; }
+    if (std::string(name) == "decoder_bf16") { h->dec_bf16 = value != 0; return FAC_OK; }
     if (std::string(name) == "tensor_cores") { h->use_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     h->err = std::string("unknown option ") + name;
     return FAC_ERR_INVALID;
@@ -1205,7 +1219,7 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     TcConvParams tp;
-    tp.Cin = Cin; tp.Cout = Cout; tp.promoted = promoted ? 1 : 0;
+    tp.Cin = Cin; tp.Cout = Cout; tp.promoted = promoted == 1 ? 1 : 0; tp.bf16 = promoted == 2 ? 1 : 0;
     if (stride == 1) { tp.vf = 1; tp.Kr = K; tp.dil = dil; }
     else if (K == 2 * stride && dil == 1) { tp.vf = stride; tp.Kr = 2; tp.dil = 1; }
     else { h->err = "fac_debug_conv_tc: unsupported stride/kernel"; return FAC_ERR_UNSUPPORTED; }
@@ -1250,8 +1264,9 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
     if (!h || !x || !y || !w7_host || !w1_host) return FAC_ERR_INVALID;
     fac_handle tmp;
     tmp.device = h->device;
-    tmp.use_tc = mode == 0 ? 0 : 1;          // 0: fp32 FMA, 1: two tcgen05 launches, 2: fused launch
-    tmp.fuse_res = mode == 2;
+    tmp.use_tc = mode == 0 ? 0 : 1;          // 0: fp32 FMA, 1: two tcgen05 launches, 2: fused launch; 3/4 = 1/2 with bf16 split
+    tmp.fuse_res = mode == 2 || mode == 4;
+    tmp.dec_bf16 = mode >= 3;
     auto put = [&](const char* key, const float* d, std::vector<int64_t> shp) {
         HostTensor t;
         t.shape = shp;
@@ -1281,7 +1296,7 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
         rc = finish(&tmp, c);
         cudaError_t e2 = cudaStreamSynchronize(st);
         if (rc == FAC_OK && e2 != cudaSuccess) { tmp.err = cudaGetErrorString(e2); rc = FAC_ERR_CUDA; }
-        if (rc == FAC_OK && mode == 2 && tmp.launches != 1) { tmp.err = "fused path not taken for this geometry"; rc = FAC_ERR_UNSUPPORTED; }
+        if (rc == FAC_OK && (mode == 2 || mode == 4) && tmp.launches != 1) { tmp.err = "fused path not taken for this geometry"; rc = FAC_ERR_UNSUPPORTED; }
     }
     if (rc != FAC_OK) h->err = tmp.err;
     if (scratch) cudaFree(scratch);

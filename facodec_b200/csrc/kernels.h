@@ -43,6 +43,7 @@ struct TcConvParams {
     int Tout = 0, Cout = 0, ldy = 0;
     int out_act = 0;
     int promoted = 0;                  // 1 = conv_tcp_kernel (register-promoted accumulation)
+    int bf16 = 0;                      // 1 = bf16 hi/lo split (kind::f16, K = 16) instead of tf32 hi/lo; decoder only
     int fused = 0;                     // 1 = whole ResidualUnit: conv7 -> +b7 -> Snake -> 1x1 conv -> +b1 -> +x
     const float* wblob2 = nullptr;     // 1x1 conv weight blob (same tile N), when fused
     const float* bias2 = nullptr;

@@ -110,7 +110,10 @@ int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int a
  * (encoder, prosody branch); 2 (default) = tcgen05 everywhere, with the register-promoted accumulation
  * variant upstream of the VQ where the bit-exact argmin needs fp32-grade sums.
  * "fuse_resunit": 1 (default) runs each decoder ResidualUnit whose channels fit one CTA tile as a single
- * fused launch (conv7 -> Snake -> 1x1 conv -> +x with the intermediate kept in TMEM/SMEM); 0 = two launches. */
+ * fused launch (conv7 -> Snake -> 1x1 conv -> +x with the intermediate kept in TMEM/SMEM); 0 = two launches.
+ * "decoder_bf16": 1 (default) = layers downstream of the VQ split operands into bf16 hi + bf16 lo
+ * (tcgen05.mma.kind::f16, K = 16: half the MMAs and half the operand bytes of the TF32 split; waveform error
+ * ~1e-5 RMS against the 1e-4 bar); 0 = TF32 hi/lo everywhere.  Never applied upstream of the VQ. */
 int fac_set_option(fac_handle* h, const char* name, int value);
 
 /* Kernel-level test hooks (used by tests/test_gpu_kernels.py; not part of the drop-in surface).
@@ -124,9 +127,10 @@ int fac_debug_conv(fac_handle* h, const float* x, const float* w_host, const flo
                    int Cin, int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,
                    const float* in_alpha_host, const float* out_alpha_host, int act, const float* res,
                    float* y, int Tout, void* stream);
-/* Same contract as fac_debug_conv, forced through the tcgen05 (3xTF32) kernels: promoted = 0 ->
- * conv_tc_kernel (accumulates in TMEM only), 1 -> conv_tcp_kernel (TMEM accumulators promoted to fp32
- * registers every ~48 MMAs; the variant used upstream of the VQ).  Returns FAC_ERR_UNSUPPORTED when
+/* Same contract as fac_debug_conv, forced through the tcgen05 kernels: promoted = 0 -> conv_tc_kernel
+ * (3xTF32, accumulates in TMEM only), 1 -> conv_tcp_kernel (3xTF32, TMEM accumulators promoted to fp32
+ * registers every ~48 MMAs; the variant used upstream of the VQ), 2 -> conv_tc_kernel with the bf16 hi/lo
+ * split (decoder-only precision class).  Returns FAC_ERR_UNSUPPORTED when
  * the layer geometry is not eligible (Cin % 16, Cout % 16, stride). */
 int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const float* bias_host, int B, int Tin,
                       int Cin, int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,
@@ -134,7 +138,8 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
                       float* y, int Tout, int promoted, void* stream);
 /* One ResidualUnit (dac/model/dac.py:25-42) y = x + conv1(snake(conv7_d(snake(x)))) on DEVICE channels-last
  * x, y [B,T,C] with HOST folded weights w7 [C,C,7], w1 [C,C,1].  mode 0: fp32 FMA kernels, 1: two tcgen05
- * launches, 2: the single fused tcgen05 launch (FAC_ERR_UNSUPPORTED if the geometry cannot be fused). */
+ * launches, 2: the single fused tcgen05 launch (FAC_ERR_UNSUPPORTED if the geometry cannot be fused);
+ * 3 / 4: as 1 / 2 with the bf16 hi/lo split. */
 int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const float* b7_host, const float* w1_host,
                       const float* b1_host, const float* alpha1_host, const float* alpha2_host, int B, int T, int C,
                       int dil, int mode, float* y, void* stream);

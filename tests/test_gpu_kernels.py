@@ -131,7 +131,7 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("promoted", [0, 1])
+@pytest.mark.parametrize("promoted", [0, 1, 2])
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc_kernel_vs_torch(case, promoted, built_lib):
     """tcgen05 3xTF32 conv vs fp32 torch.  Operands are split exactly (hi + lo), but the tensor core adds
@@ -161,11 +161,11 @@ def test_conv_tc_kernel_vs_torch(case, promoted, built_lib):
     scale = ref.abs().max().item()
     rel_rms = ((y - ref).double().pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt()).item()
     print(f"TCERR promoted={promoted} case={case} maxerr={err:.3e} scale={scale:.3f} rel_rms={rel_rms:.3e}")
-    tol = 4e-6 if promoted else 6e-5        # promoted: fp32-grade; plain: truncating TMEM accumulation
+    tol = {0: 6e-5, 1: 4e-6, 2: 2e-4}[promoted]   # TMEM-truncating 3xTF32 / promoted (fp32-grade) / bf16 hi+lo
     assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("B,T,C,dil", [(2, 300, 96, 1), (1, 520, 96, 9), (2, 200, 192, 3), (1, 130, 256, 1), (2, 40, 96, 9)])
 def test_residual_unit_modes(B, T, C, dil, mode, built_lib):
     """ResidualUnit (dac.py:25-42) through the fp32 FMA path, two tcgen05 launches, and the fused launch."""
@@ -191,6 +191,6 @@ def test_residual_unit_modes(B, T, C, dil, mode, built_lib):
     assert torch.isfinite(y).all()
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item()
-    tol = 2e-5 if mode == 0 else 8e-5
+    tol = 2e-5 if mode == 0 else (8e-5 if mode <= 2 else 3e-4)
     print(f"RESUNIT mode={mode} C={C} d={dil} T={T} maxerr={err:.3e} scale={scale:.3f}")
     assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
