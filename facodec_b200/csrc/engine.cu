@@ -1309,6 +1309,16 @@ int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     cudaError_t e = tc_read_phase_clocks(out8);
+
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
+}
+
+int fac_debug_lstm_phase_clocks(fac_handle* h, long long* out4) {
+    if (!h || !out4) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaError_t e = lstm_read_phase_clocks(out4);
     if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
     return FAC_OK;
 }

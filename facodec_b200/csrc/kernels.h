@@ -72,7 +72,8 @@ struct LstmParams {
     int B = 0, T = 0, H = 0, U = 0, G = 0;
 };
 cudaError_t launch_lstm_layer(const LstmParams& p, cudaStream_t st);
-int lstm_units_per_cta(int H);  // U such that H % U == 0 and H / U <= resident CTAs
+int lstm_units_per_cta(int H);
+cudaError_t lstm_read_phase_clocks(long long* out4);   // CTA-0 accumulated phase clocks of the last launch  // U such that H % U == 0 and H / U <= resident CTAs
 
 // ---- mel front-end (frontend.cu) -----------------------------------------------------------
 // spec [B][F][ldspec] (re at 2*bin, im at 2*bin+1) -> mel [B][Tm][80] = (log(1e-5 + |.|^2 fb)+4)/4

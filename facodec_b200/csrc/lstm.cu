@@ -20,6 +20,9 @@
 
 namespace fac {
 
+// accumulated clock64 per phase of CTA 0 (kernel-tuning aid): [0] barrier wait, [1] K loop, [2] reduce+gates, [3] publish
+__device__ long long g_lstm_phase_clock[4];
+
 constexpr int LSTM_BT = 32;     // batch tile (columns of hT)
 constexpr int LSTM_WARPS = 8;
 constexpr int LSTM_KS = 16;     // k rows per cp.async sub-chunk
@@ -75,7 +78,10 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
     float* my_stage = stage_base + warp * LSTM_D * STAGE_F;
 
     constexpr int PAIRS = (LSTM_BT * U + LSTM_WARPS * 32 - 1) / (LSTM_WARPS * 32);
+    const bool probe = (cta == 0 && tid == 0);
+    long long ph[4] = {0, 0, 0, 0}, tc0 = 0;
     for (int t = 0; t < p.T; ++t) {
+        if (probe) tc0 = clock64();
         // ---- prefetch this step's input-projection gates (independent of the barrier) ----
         float xgv[PAIRS][4];
         float skv[PAIRS];
@@ -117,6 +123,7 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
             __syncthreads();
         }
         const float* hprev = p.hT + (size_t)((t + 1) & 1) * H * LSTM_BT;  // parity of t-1
+        if (probe) { long long n = clock64(); ph[0] += n - tc0; tc0 = n; }
 
         float acc[MT][NTL][4];
 #pragma unroll
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
             }
             __syncwarp();   // everyone done with this stage before it is refilled
         }
+        if (probe) { long long n = clock64(); ph[1] += n - tc0; tc0 = n; }
         // ---- cross-warp reduction through shared memory: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1) ----
         float* myred = red + warp * LSTM_BT * RP;
 #pragma unroll
@@ -222,6 +230,7 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
                 p.y[o] = h + skv[pi];
             }
         }
+        if (probe) { long long n = clock64(); ph[2] += n - tc0; tc0 = n; }
         // ---- publish: CTA barrier orders every thread's h stores before thread 0, whose gpu-scope
         // fence is cumulative, then one release-arrive on the grid counter ----
         __syncthreads();
@@ -229,8 +238,12 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
             __threadfence();
             atomicAdd(p.bar, 1u);
         }
+        if (probe) { long long n = clock64(); ph[3] += n - tc0; }
     }
+    if (probe) { for (int i = 0; i < 4; ++i) g_lstm_phase_clock[i] = ph[i]; }
 }
+
+cudaError_t lstm_read_phase_clocks(long long* out4) { return cudaMemcpyFromSymbol(out4, g_lstm_phase_clock, sizeof(long long) * 4); }
 
 int lstm_units_per_cta(int H) {
     if (H % 12 == 0 && H / 12 <= 132 && (H / LSTM_WARPS) % LSTM_KS == 0) return 12;

@@ -147,6 +147,9 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
  * [0] start, [1] all activation chunks produced, [2] GEMM 1 retired, [3] GEMM-2 operand produced (fused),
  * [4] GEMM 2 retired (fused), [5] epilogue done.  Kernel-tuning aid. */
 int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8);
+/* clock64() totals of CTA 0 of the most recent lstm_rec_kernel launch, summed over all steps:
+ * [0] grid-barrier wait, [1] W_hh/h streaming + MMAs, [2] cross-warp reduce + gate math, [3] publish. */
+int fac_debug_lstm_phase_clocks(fac_handle* h, long long* out4);
 int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, int B, int T, int H, float* y,
                     void* stream);
 /* Registers (dst != NULL) or clears a named tap: the next forward copies that channels-last
