@@ -46,8 +46,14 @@ static __device__ __noinline__ float sin2_slow(float x) {
     float s = sinf(x);
     return s * s;
 }
+// INLINE_SLOW: kernels that re-allocate registers with setmaxnreg must not contain ABI calls (ptxas 12.9
+// crashes on the combination), so they inline the rarely-taken sinf() path instead of calling it.
+template <bool INLINE_SLOW = false>
 __device__ __forceinline__ float sin2_f(float x) {
-    if (fabsf(x) > 4096.0f) return sin2_slow(x);
+    if (fabsf(x) > 4096.0f) {
+        if constexpr (INLINE_SLOW) { float s = sinf(x); return s * s; }
+        else return sin2_slow(x);
+    }
     float k = rintf(x * 0.318309886183790672f);
     float r = fmaf(k, -3.14159274101257324f, x);      // pi_hi (fp32)
     r = fmaf(k, 8.74227765734758578e-8f, r);          // -pi_lo: pi = pi_hi + pi_lo, pi_lo = -8.742e-8
@@ -60,8 +66,9 @@ __device__ __forceinline__ float sin2_f(float x) {
     p = fmaf(p * r2, r, r);                           // r + r^3 * (...)
     return p * p;
 }
+template <bool INLINE_SLOW = false>
 __device__ __forceinline__ float snake_fast(float x, float alpha, float inv_alpha) {
-    return fmaf(inv_alpha, sin2_f(alpha * x), x);
+    return fmaf(inv_alpha, sin2_f<INLINE_SLOW>(alpha * x), x);
 }
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -90,19 +90,24 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
 }
+// The MMA warp runs its loop CONVERGED (all 32 lanes); each tcgen05 instruction is issued by the lane
+// elect.sync picks, inside the same asm block.  (Issuing from an `if (lane == 0)` region made the compiler
+// wrap every UTCHMMA in an ELECT / BRA.U.ANY serialisation loop: ~75 extra cycles per MMA, measured.)
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
@@ -111,8 +116,12 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
     if constexpr (BF16) umma_bf16(tmem_d, adesc, bdesc, idesc, accum);
     else umma_tf32(tmem_d, adesc, bdesc, idesc, accum);
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {   // converged warp; one elected lane commits
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -197,7 +206,7 @@ __device__ __forceinline__ void split_store(float4 x4, int pc, int row, int Rpad
 // Thread `ptid` of NT producer threads owns 16-byte piece pc = ptid & 3 (4 input channels) of
 // rows ptid/4, ptid/4 + NT/4, ...: channel offset, Snake parameters and the smem column are
 // per-thread constants for the whole chunk; only the row varies.
-template <int NT, bool BF16>
+template <int NT, bool BF16, int BATCH = 4, bool INL = false>
 __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMap& pm, const float* __restrict__ xb,
                                               int c, int t0, int R, int Rpad, uint8_t* ahi, uint8_t* alo, int ptid) {
     const int pc = ptid & 3;
@@ -214,10 +223,10 @@ __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMa
     const int vrow0 = t0 - p.PLr;
     const float* __restrict__ xcol = xb + ci;
 #pragma unroll 1
-    for (int r = ptid >> 2; r < R; r += RSTEP * 4) {
-        float4 v[4];
+    for (int r = ptid >> 2; r < R; r += RSTEP * BATCH) {
+        float4 v[BATCH];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BATCH; ++u) {
             const int rr = r + u * RSTEP;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             const int vrow = vrow0 + rr;
@@ -227,15 +236,15 @@ __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMa
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BATCH; ++u) {
             const int rr = r + u * RSTEP;
             if (rr < R) {
                 float4 x4 = v[u];
                 if (has_alpha) {            // snake(0) == 0, so padded zeros stay zero
-                    x4.x = snake_fast(x4.x, al.x, ia.x);
-                    x4.y = snake_fast(x4.y, al.y, ia.y);
-                    x4.z = snake_fast(x4.z, al.z, ia.z);
-                    x4.w = snake_fast(x4.w, al.w, ia.w);
+                    x4.x = snake_fast<INL>(x4.x, al.x, ia.x);
+                    x4.y = snake_fast<INL>(x4.y, al.y, ia.y);
+                    x4.z = snake_fast<INL>(x4.z, al.z, ia.z);
+                    x4.w = snake_fast<INL>(x4.w, al.w, ia.w);
                 }
                 split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
             }
@@ -331,6 +340,7 @@ __device__ __forceinline__ void epilogue_store4(const TcConvParams& p, const flo
 // shared memory (row pitch 36 floats: conflict-free 16-byte accesses both ways) and reads it back
 // so that 8 lanes cover 128 contiguous bytes of one row: every global load/store instruction
 // (residual in, result out) then touches 4 full lines instead of 32 partial ones.
+template <bool PREFETCH_RES = true>
 __device__ __forceinline__ void epilogue_tile32(const TcConvParams& p, const float* __restrict__ bias, int act,
                                                 const float (&v)[32], float* stage /* [32][36] per warp */, int lane,
                                                 int t_first /* time step of tile row 0 */, int co0 /* channel of col 0 */,
@@ -338,12 +348,14 @@ __device__ __forceinline__ void epilogue_tile32(const TcConvParams& p, const flo
     const int c4 = lane & 7, rsub = lane >> 3;
     const int co = co0 + c4 * 4;
     // residual rows for this lane's 8 (row, 16-byte column chunk) slots: issued first, consumed last
-    float4 rr[8];
+    float4 rr[PREFETCH_RES ? 8 : 1];
+    if constexpr (PREFETCH_RES) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int t = t_first + 4 * i + rsub;
-        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rb && t < p.Tout) rr[i] = *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co);
+        for (int i = 0; i < 8; ++i) {
+            const int t = t_first + 4 * i + rsub;
+            rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rb && t < p.Tout) rr[i] = *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -369,7 +381,12 @@ __device__ __forceinline__ void epilogue_tile32(const TcConvParams& p, const flo
         } else if (act == ACT_MISH) {
             o.x = mish_f(o.x); o.y = mish_f(o.y); o.z = mish_f(o.z); o.w = mish_f(o.w);
         }
-        o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w;
+        if constexpr (PREFETCH_RES) {
+            o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w;
+        } else if (rb && t < p.Tout) {      // low-register variant (promoted kernel): residual fetched in place
+            float4 r1 = *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co);
+            o.x += r1.x; o.y += r1.y; o.z += r1.z; o.w += r1.w;
+        }
         if (t < p.Tout) *reinterpret_cast<float4*>(yb + (size_t)t * p.ldy + co) = o;
     }
     __syncwarp();
@@ -456,8 +473,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (whole warp converged, see umma_tf32) =================
+        {
             // instruction descriptor: D=f32, A=B=tf32, K-major both, N>>3, M=128>>4
             const uint32_t fmt = BF16 ? 1u : 2u;   // F16F32Format: BF16 = 1, TF32 = 2
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
@@ -702,11 +719,19 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
 // to flip near-tied VQ decisions.  Here each TMEM accumulator only lives for `promote_every`
 // chunks (~48 MMAs); 8 worker warps then pull it out with tcgen05.ld and add it into fp32
 // REGISTER accumulators with round-to-nearest (128 registers per thread hold the 128 x 256 tile),
-// while the MMA warp already fills the other TMEM buffer.  The same 8 warps are the activation
-// producers: produce(chunk c) ; promote(group of chunk c-1) ; ...
+// while the MMA warp already fills the other TMEM buffer.
+// Warp-specialised with register re-allocation (setmaxnreg): 20 warps launch with 96 registers each;
+// the 4 control warps drop to 32, the 8 activation-producer warps to 64, and the 8 accumulator warps
+// grow to 160, so producing, MMA issue and promotion/epilogue all overlap instead of taking turns on
+// the same warps (measured before the split: produce 39 %, wait 19 %, promote 5 %, epilogue 36 % of
+// a CTA, serially).
 // ================================================================================================
 namespace tc {
-constexpr int kThreadsP = 320;     // warp 0: weights, warp 1: MMA, warps 2..9: workers
+constexpr int kThreadsP = 640;     // warps 0-3: control (weights, MMA, 2 idle); 4-11: producers; 12-19: accumulators
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 struct SmemP {
     uint64_t b_full[kMaxStagesB];
     uint64_t b_empty[kMaxStagesB];
@@ -754,6 +779,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
 
+    if (warp < 4) reg_dec<32>();      // whole control warpgroup at one program point (4*32*32 + 8*32*64 + 8*32*160 == 640*96)
     if (warp == 0) {
         if (lane == 0) {
             const float* wsrc = p.wblob + (size_t)ntile * nchunk * Kr * (size_t)(2 * b_half / 4);
@@ -767,7 +793,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp converged; tcgen05 instructions are elect-predicated inside their asm blocks
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t a_lbo = (uint32_t)Rpad * 16, b_lbo = (uint32_t)N * 16;
             int it = 0;
@@ -811,97 +837,108 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                 umma_commit(&sm->acc_ready[abuf]);
             }
         }
-    } else {
-        // ================= workers: activation producers + promoters + epilogue =================
-        const int wtid = tid - 64;                                  // 0..255
+    } else if (warp >= 4 && warp < 12) {
+        // ================= activation producers (warps 4..11, 64 registers each) =================
+        reg_dec<64>();
+        const int wtid = tid - 128;                                 // 0..255
+        const bool probe = (wtid == 0 && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0);
+        if (probe) g_tc_phase_clock[0] = clock64();
+        const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
+        const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
+        for (int c = 0; c < nchunk; ++c) {
+            const int buf = c & 1;
+            uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
+            mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+            produce_chunk<256, false, 4, true>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
+            fence_proxy_async();
+            mbar_arrive(&sm->a_full[buf]);
+        }
+        if (probe) g_tc_phase_clock[1] = clock64();                 // all chunks produced
+    } else if (warp >= 12) {
+        // ================= accumulators (warps 12..19, 160 registers each): promote + epilogue =================
+        reg_inc<160>();
         const int q = warp & 3;                                     // TMEM lane quarter
-        const int half = (warp - 2) >> 2;                           // column half of the tile set
+        const int half = (warp - 12) >> 2;                          // column half of the tile set
         int split = ((ncols / 2 + 15) / 16) * 16;
         if (split > ncols) split = ncols;
         const int mycol0 = half ? split : 0;
         const int mycols = half ? ncols - split : split;
-        const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
-        const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
         float acc[128];
 #pragma unroll
         for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-
-        const bool piped = false;   // register budget (168 with 10 warps) leaves no room for a second chunk in flight here
-        ChunkRegs cur, nxt;
-        if (piped) load_chunk_regs<256>(p, pm, xb, 0, t0, R, wtid, cur);
-        for (int c = 0; c <= nchunk; ++c) {
-            if (c < nchunk) {
-                const int buf = c & 1;
-                uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-                if (piped) {
-                    if (c + 1 < nchunk) load_chunk_regs<256>(p, pm, xb, c + 1, t0, R, wtid, nxt);
-                    mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
-                    store_chunk_regs<256, false>(p, c, R, Rpad, ahi, ahi + a_half, wtid, cur);
-                    cur = nxt;
-                } else {
-                    mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
-                    produce_chunk<256, false>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
-                }
-                fence_proxy_async();
-                mbar_arrive(&sm->a_full[buf]);
-            }
-            if (c >= 1 && ((c % P) == 0 || c == nchunk)) {
-                // ---- promote the group that ended with chunk c-1 ----
-                const int g = (c - 1) / P;
-                const int abuf = g & 1;
-                mbar_wait(&sm->acc_ready[abuf], (g >> 1) & 1);
-                tc_fence_after();
-                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + mycol0);
+        const int G = (nchunk + P - 1) / P;
+        for (int g = 0; g < G; ++g) {
+            const int abuf = g & 1;
+            mbar_wait(&sm->acc_ready[abuf], (g >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + mycol0);
 #pragma unroll
-                for (int grp = 0; grp < 8; ++grp) {
-                    if (grp * 16 < mycols) {
-                        uint32_t v[16];
-                        tmem_ld16(tbase + grp * 16, v);
+            for (int grp = 0; grp < 8; ++grp) {
+                if (grp * 16 < mycols) {
+                    uint32_t v[16];
+                    tmem_ld16(tbase + grp * 16, v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[grp * 16 + i] += __uint_as_float(v[i]);
-                    }
+                    for (int i = 0; i < 16; ++i) acc[grp * 16 + i] += __uint_as_float(v[i]);
                 }
-                tc_fence_before();
-                mbar_arrive(&sm->acc_free[abuf]);
             }
+            tc_fence_before();
+            mbar_arrive(&sm->acc_free[abuf]);
         }
-        // ================= epilogue from registers =================
+        // ---- epilogue: every MMA has retired and the producers are done, so the operand buffers are free.
+        // Park the whole register tile in shared memory ([32 rows][132] per warp, conflict-free both ways), then a
+        // ROLLED loop streams it out coalesced (8 lanes = 128 contiguous bytes of one row).  Rolled on purpose: the
+        // unrolled register epilogue was 20k SASS instructions and ran out of the instruction cache.
         float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
         const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
-        if ((N & 31) == 0 && (mycols & 31) == 0 && (mycol0 & 31) == 0) {
-            // all MMAs have retired (last promotion waited on them): the activation buffers are free to
-            // serve as the per-warp transpose stage of the coalesced epilogue
-            float* stage = reinterpret_cast<float*>(a_base) + (size_t)(warp - 2) * (32 * 36);
+        const bool aprobe = (tid == 12 * 32 && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0);
+        if (aprobe) g_tc_phase_clock[2] = clock64();                // last promotion done
+        float* stage = reinterpret_cast<float*>(a_base) + (size_t)(warp - 12) * (32 * 132);
 #pragma unroll
-            for (int gp = 0; gp < 4; ++gp) {
-                if (gp * 32 < mycols) {
-                    const int j0 = mycol0 + gp * 32;
-                    const int mt = j0 / N, col = j0 - mt * N;
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = acc[gp * 32 + i];
-                    epilogue_tile32(p, p.bias, p.out_act, v, stage, lane, t0 + mt * 128 + q * 32, ntile * N + col, yb, rb);
-                }
+        for (int j = 0; j < 32; ++j)
+            if (j * 4 < mycols)
+                *reinterpret_cast<float4*>(stage + lane * 132 + j * 4) =
+                    make_float4(acc[j * 4], acc[j * 4 + 1], acc[j * 4 + 2], acc[j * 4 + 3]);
+        __syncwarp();
+        if (aprobe) g_tc_phase_clock[3] = clock64();                // register tile staged
+        const int c4 = lane & 7, rsub = lane >> 3;
+        const int act = p.out_act;
+#pragma unroll 1
+        for (int cb = 0; cb < mycols; cb += 32) {                   // 32-column block of this thread's range
+            const int jc = cb + c4 * 4;                             // column inside my range handled by this lane
+            if (jc >= mycols) continue;
+            const int jflat = mycol0 + jc;
+            const int mt = jflat / N, col = jflat - mt * N;
+            const int co = ntile * N + col;
+            float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), al = bi, ia = bi;
+            if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+            if (act == ACT_SNAKE) {
+                al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
+                ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
             }
-        } else
-#pragma unroll
-        for (int grp = 0; grp < 8; ++grp) {
-            if (grp * 16 >= mycols) continue;
-            const int j0 = mycol0 + grp * 16;
-            const int mt = j0 / N, col = j0 - mt * N;
-            const int t = t0 + mt * 128 + q * 32 + lane;
-            if (t >= p.Tout) continue;
-            const int co0 = ntile * N + col;
-            float* yrow = yb + (size_t)t * p.ldy;
-            float4 rr[4];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-                rr[j4] = rb ? *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co0 + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-                epilogue_store4(p, p.bias, p.out_act, acc[grp * 16 + j4 * 4 + 0], acc[grp * 16 + j4 * 4 + 1],
-                                acc[grp * 16 + j4 * 4 + 2], acc[grp * 16 + j4 * 4 + 3], co0 + j4 * 4, yrow, rb != nullptr, rr[j4]);
+            const int tbase_row = t0 + mt * 128 + q * 32;
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+                const int row = 4 * i + rsub;
+                const int t = tbase_row + row;
+                if (t >= p.Tout) continue;
+                float4 o = *reinterpret_cast<const float4*>(stage + row * 132 + jc);
+                o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
+                if (act == ACT_SNAKE) {
+                    o.x = snake_fast<true>(o.x, al.x, ia.x); o.y = snake_fast<true>(o.y, al.y, ia.y);
+                    o.z = snake_fast<true>(o.z, al.z, ia.z); o.w = snake_fast<true>(o.w, al.w, ia.w);
+                } else if (act == ACT_TANH) {
+                    o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
+                } else if (act == ACT_MISH) {
+                    o.x = mish_f(o.x); o.y = mish_f(o.y); o.z = mish_f(o.z); o.w = mish_f(o.w);
+                }
+                if (rb) {
+                    float4 r1 = *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co);
+                    o.x += r1.x; o.y += r1.y; o.z += r1.z; o.w += r1.w;
+                }
+                *reinterpret_cast<float4*>(yb + (size_t)t * p.ldy + co) = o;
+            }
         }
+        if (aprobe) g_tc_phase_clock[5] = clock64();                // epilogue done
     }
     tc_fence_before();
     __syncthreads();
@@ -946,6 +983,11 @@ bool tc_conv_plan(TcConvParams& p) {
     if (128 + a_bytes + S * b_stage > 225 * 1024) return false;
     p.stagesB = S;
     p.smem_bytes = 128 + a_bytes + S * b_stage;
+    if (p.promoted) {
+        // the accumulator warps reuse the operand buffers as an [8 warps][32][132] transpose stage
+        size_t stage = (size_t)8 * 32 * 132 * 4 + 128;
+        if (p.smem_bytes < stage) p.smem_bytes = stage;
+    }
     return true;
 }
 
