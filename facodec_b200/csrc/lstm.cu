@@ -8,11 +8,14 @@
 //
 // Per step each CTA computes a [4U gate rows] x [32 batch] x [H] product: the 8 warps split H
 // eight ways and stream their slice of W_hh (pre-packed per CTA as [H][4U], so the copy is
-// linear) and of h_{t-1} through private cp.async double buffers, and feed them to the tensor
+// linear) and of h_{t-1} through private multi-stage cp.async rings, and feed them to the tensor
 // cores as mma.sync m16n8k8 TF32 tiles with the same fp32-faithful 3xTF32 split as the convs
 // (hi/lo formed in registers; 48-72 chained MMAs per accumulator, then an fp32 cross-warp sum).
-// A 32 x 4U x H product per step is far too small for a tcgen05/TMEM tile pipeline -- the step is
-// bounded by the L2 stream of W_hh and the grid barrier, not by the MMAs.  Partial sums meet in
+// A 32 x 4U x H product per step is far too small for a tcgen05/TMEM tile pipeline.  Measured per
+// step (clock64 probe, fac_debug_lstm_phase_clocks): barrier wait ~2.0k cycles, K loop 12k (H=1024) /
+// 23.5k (H=1536), reduce+gates 1.4-2.6k, publish 1.4k.  The K loop is bound by the legacy HMMA.1688
+// TF32 rate of this chip (~1 per 32 cycles per SM sub-partition == the fp32 FMA rate: the earlier FMA
+// version of this loop ran at the same speed), not by the cp.async ring (deepening it changed nothing).  Partial sums meet in
 // shared memory, then 32*U threads apply the gate math (PyTorch gate order i, f, g, o).
 #include <cooperative_groups.h>
 #include "common.cuh"
@@ -26,7 +29,9 @@ __device__ long long g_lstm_phase_clock[4];
 constexpr int LSTM_BT = 32;     // batch tile (columns of hT)
 constexpr int LSTM_WARPS = 8;
 constexpr int LSTM_KS = 16;     // k rows per cp.async sub-chunk
-constexpr int LSTM_D = 3;       // cp.async pipeline depth (stages per warp)
+// cp.async pipeline depth (stages per warp): as deep as shared memory allows -- the K loop is bound by
+// bytes in flight x L2 latency, not by the MMAs.  The cross-warp reduction buffer aliases the stage memory.
+template <int U> struct LstmDepth { static constexpr int D = (U == 8) ? 5 : 4; };
 constexpr int LSTM_HP = LSTM_BT + 8;   // padded smem row of the h sub-chunk (conflict-free fragments)
 
 __device__ __forceinline__ float tf32_rn(float x) {
@@ -57,10 +62,11 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
     constexpr int WP = R + 8;                   // padded smem row of the W sub-chunk
     constexpr int MT = R / 16, NTL = LSTM_BT / 8;
     constexpr int STAGE_F = LSTM_KS * (LSTM_HP + WP);  // floats per stage per warp
+    constexpr int LSTM_D = LstmDepth<U>::D;
+    static_assert(LSTM_D * STAGE_F >= LSTM_BT * RP, "reduction buffer must fit in a warp's own stage memory");
     extern __shared__ __align__(16) float smem[];
     float* stage_base = smem;                                   // [8 warps][LSTM_D][STAGE_F]
-    float* red = smem + LSTM_WARPS * LSTM_D * STAGE_F;          // [8][32][R]
-    float* cstate = red + LSTM_WARPS * LSTM_BT * RP;            // [32][U]
+    float* cstate = smem + LSTM_WARPS * LSTM_D * STAGE_F;       // [32][U]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x;
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
         }
         if (probe) { long long n = clock64(); ph[1] += n - tc0; tc0 = n; }
         // ---- cross-warp reduction through shared memory: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1) ----
-        float* myred = red + warp * LSTM_BT * RP;
+        float* myred = my_stage;   // aliases this warp's own (fully consumed) stage buffers
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
             for (int g = 0; g < 4; ++g) {
                 float s = 0.f;
 #pragma unroll
-                for (int w = 0; w < LSTM_WARPS; ++w) s += red[w * LSTM_BT * RP + b * RP + g * U + u];
+                for (int w = 0; w < LSTM_WARPS; ++w) s += stage_base[w * LSTM_D * STAGE_F + b * RP + g * U + u];
                 g4[g] = s + xgv[pi][g];
             }
             float ig = sigmoid_f(g4[0]), fg = sigmoid_f(g4[1]), gg = tanhf(g4[2]), og = sigmoid_f(g4[3]);
@@ -254,7 +260,7 @@ int lstm_units_per_cta(int H) {
 template <int U>
 static cudaError_t launch_u(const LstmParams& p, cudaStream_t st) {
     constexpr int R = 4 * U;
-    size_t smem = sizeof(float) * (LSTM_WARPS * LSTM_D * LSTM_KS * (LSTM_HP + R + 8) + LSTM_WARPS * LSTM_BT * (R + 1) + LSTM_BT * U);
+    size_t smem = sizeof(float) * (LSTM_WARPS * LstmDepth<U>::D * LSTM_KS * (LSTM_HP + R + 8) + LSTM_BT * U);
     cudaError_t e = cudaFuncSetAttribute(lstm_rec_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(p.bar, 0, sizeof(unsigned int), st);
