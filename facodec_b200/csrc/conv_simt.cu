@@ -224,53 +224,78 @@ __global__ void __launch_bounds__(2 * BN) conv_cl_kernel(ConvParams p) {
 // ---- Cout == 1 (decoder's last conv, dac.py:158-160: Snake -> SConv1d(96 -> 1, k=7) -> tanh) -------
 // A dot product of K*Cin per output sample: HBM-bound (reads the widest activation of the model once).
 // CTA = 128 output samples: stage the (128 + halo) x Cin input tile in shared memory with Snake applied
-// (coalesced 16-byte loads), then one warp per 16 outputs, lanes split the channels, shuffle-reduce.
+// (coalesced 16-byte loads, 4 in flight per thread).  Then thread (t, h) accumulates output sample t over
+// the 16-byte channel pieces c4 = h, h+2, ... of every tap with 128-bit shared loads: the row pitch Cp is
+// 4*odd floats, so the 8 threads of a quarter-warp (consecutive t, same piece) hit 8 distinct bank groups;
+// weights are warp-uniform broadcasts.  The two halves meet in shared memory; stores are coalesced.
 constexpr int C1_TILE = 128;
+__host__ __device__ inline int c1_pitch(int Cin) { return ((Cin / 4) & 1) ? Cin : Cin + 4; }
 __global__ void __launch_bounds__(256) conv_cout1_kernel(ConvParams p) {
     extern __shared__ __align__(16) float c1_smem[];
-    const int Cin = p.Cin;
+    const int Cin = p.Cin, Cp = c1_pitch(Cin);
     const int halo = (p.K - 1) * p.dil;
     const int rows = C1_TILE + halo;
-    float* xs = c1_smem;                       // [rows][Cin]
-    float* wsm = c1_smem + (size_t)rows * Cin; // [K][Cin]
+    float* xs = c1_smem;                        // [rows][Cp]
+    float* wsm = c1_smem + (size_t)rows * Cp;   // [K][Cin]
+    float* part = wsm + (size_t)p.K * Cin;      // [C1_TILE] partial sums of the odd pieces
     const int b = blockIdx.y, t0 = blockIdx.x * C1_TILE;
     const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
     const PadMap pm = PadMap::make(p.Tin, p.pad_left, p.pad_right, p.pad_reflect);
     const int c4n = Cin / 4;
-    for (int i = threadIdx.x; i < rows * c4n; i += blockDim.x) {
-        int r = i / c4n, c4 = i - r * c4n;
-        int row = pm.src(t0 + r - p.pad_left);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row >= 0 && t0 + r - halo < p.Tout + 0) {
-            v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.ldx + c4 * 4));
-            if (p.in_alpha) {
-                float4 al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + c4 * 4));
-                float4 ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + c4 * 4));
-                v.x = snake_f(v.x, al.x, ia.x); v.y = snake_f(v.y, al.y, ia.y);
-                v.z = snake_f(v.z, al.z, ia.z); v.w = snake_f(v.w, al.w, ia.w);
+    const bool has_alpha = p.in_alpha != nullptr;
+    const int total = rows * c4n;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 256) {
+        float4 v[4];
+        int rr[4], cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 256;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[u] = -1; cc[u] = 0;
+            if (i < total) {
+                const int r = i / c4n, c4 = i - r * c4n;
+                rr[u] = r; cc[u] = c4;
+                const int row = pm.src(t0 + r - p.pad_left);
+                if (row >= 0 && t0 + r - halo < p.Tout) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.ldx + c4 * 4));
             }
         }
-        *reinterpret_cast<float4*>(xs + (size_t)r * Cin + c4 * 4) = v;
-    }
-    for (int i = threadIdx.x; i < p.K * Cin; i += blockDim.x) wsm[i] = p.w[(size_t)i * p.ldw];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float bias = p.bias ? p.bias[0] : 0.f;
-    float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
-    for (int o = 0; o < C1_TILE / 8; ++o) {
-        int tl = warp * (C1_TILE / 8) + o;
-        float acc = 0.f;
-        for (int tap = 0; tap < p.K; ++tap) {
-            const float* xr = xs + (size_t)(tl + tap * p.dil) * Cin;
-            const float* wr = wsm + tap * Cin;
-            for (int ci = lane; ci < Cin; ci += 32) acc = fmaf(xr[ci], wr[ci], acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (rr[u] < 0) continue;
+            float4 x4 = v[u];
+            if (has_alpha) {
+                const float4 al = __ldg(reinterpret_cast<const float4*>(p.in_alpha + cc[u] * 4));
+                const float4 ia = __ldg(reinterpret_cast<const float4*>(p.in_inv_alpha + cc[u] * 4));
+                x4.x = snake_fast(x4.x, al.x, ia.x); x4.y = snake_fast(x4.y, al.y, ia.y);
+                x4.z = snake_fast(x4.z, al.z, ia.z); x4.w = snake_fast(x4.w, al.w, ia.w);
+            }
+            *reinterpret_cast<float4*>(xs + (size_t)rr[u] * Cp + cc[u] * 4) = x4;
         }
-        acc = warp_sum(acc);
-        int t = t0 + tl;
-        if (lane == 0 && t < p.Tout) {
-            float v = acc + bias;
+    }
+    for (int i = threadIdx.x; i < p.K * Cin; i += 256) wsm[i] = p.w[(size_t)i * p.ldw];
+    __syncthreads();
+    const int tl = threadIdx.x & (C1_TILE - 1), h = threadIdx.x >> 7;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int tap = 0; tap < p.K; ++tap) {
+        const float* xr = xs + (size_t)(tl + tap * p.dil) * Cp;
+        const float* wr = wsm + tap * Cin;
+#pragma unroll 4
+        for (int c4 = h; c4 < c4n; c4 += 2) {
+            const float4 xv = *reinterpret_cast<const float4*>(xr + c4 * 4);
+            const float4 wv = *reinterpret_cast<const float4*>(wr + c4 * 4);
+            a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1);
+            a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
+        }
+    }
+    const float acc = (a0 + a1) + (a2 + a3);
+    if (h == 1) part[tl] = acc;
+    __syncthreads();
+    if (h == 0) {
+        const int t = t0 + tl;
+        if (t < p.Tout) {
+            float v = acc + part[tl] + (p.bias ? p.bias[0] : 0.f);
             if (p.out_act == ACT_TANH) v = tanhf(v);
-            yb[(size_t)t * p.ldy] = v;
+            p.y[(size_t)b * p.y_bstride + (size_t)t * p.ldy] = v;
         }
     }
 }
@@ -279,7 +304,7 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t st) {
     if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
     if (p.Cout == 1 && p.stride == 1 && (p.Cin % 4) == 0 && !p.res && !p.valid_len && !p.y_transposed &&
         (p.out_act == ACT_NONE || p.out_act == ACT_TANH)) {
-        size_t smem = sizeof(float) * ((size_t)(C1_TILE + (p.K - 1) * p.dil) * p.Cin + (size_t)p.K * p.Cin);
+        size_t smem = sizeof(float) * ((size_t)(C1_TILE + (p.K - 1) * p.dil) * c1_pitch(p.Cin) + (size_t)p.K * p.Cin + C1_TILE);
         if (smem <= 200 * 1024) {
             static bool configured = false;
             if (!configured) {

@@ -42,6 +42,7 @@ namespace tc {
 constexpr int kThreads = 320;      // warp 0: weights, warp 1: MMA, warps 2..9: activation producers + epilogue
 constexpr int kChunk = 16;        // K elements (channels) per pipeline chunk
 constexpr int kMaxStagesB = 4;
+constexpr int kSmemHdr = 256;     // barriers + TMEM base at the start of dynamic shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,6 +153,34 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Split issue / wait so that a TMEM load can stay in flight behind arithmetic on the previous one.  The wait names the
+// destination registers as in/out operands: the compiler then cannot move a read of them above the wait.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&v)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+                 :: "memory");
 }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes stored as
@@ -399,9 +428,11 @@ struct Smem {
     uint64_t a_empty[2];
     uint64_t acc_full;
     uint64_t acc2_full;
+    uint64_t a2_full[16];          // fused: GEMM-2 operand chunk c2 written (256 worker arrivals)
     uint32_t tmem_base;
     uint32_t pad;
 };
+static_assert(sizeof(Smem) <= 256, "Smem header");
 
 }  // namespace tc
 
@@ -416,7 +447,7 @@ struct Smem {
 // per channel (the SS-mode TF32 MMAs are shared-memory-bandwidth bound for N <= 192); 16 mantissa bits
 // keep the waveform error at ~1e-5 RMS, well inside the 1e-4 bar, but not VQ-exact -- never used upstream.
 template <bool FUSED, bool BF16>
-__global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p) {
+__global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem* sm = reinterpret_cast<Smem*>(smem_raw);
@@ -427,9 +458,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
     const int Rpad = p.Rpad;                                // R rounded so that Rpad % 8 == 2
     const uint32_t a_half = (uint32_t)Rpad * 16 * KG;       // bytes of one hi (or lo) A buffer
     const uint32_t b_half = (uint32_t)N * 16 * KG;          // bytes of one hi (or lo) weight tile
-    uint8_t* a_base = smem_raw + 128;                       // [2 bufs][hi|lo][4 k4][Rpad][16B]
+    uint8_t* a_base = smem_raw + kSmemHdr;                  // [2 bufs][hi|lo][4 k4][Rpad][16B]
     uint8_t* b_base = a_base + 4 * a_half;                  // [S][hi|lo][4 k4][N][16B]
     const int S = p.stagesB;
+    // fused: resident GEMM-2 operand, [nchunk2][hi|lo][KG][R2pad][16B]
+    const uint32_t a2_half = (uint32_t)p.R2pad * 16 * KG;
+    uint8_t* a2_base = b_base + (size_t)S * 2 * b_half;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t0 = blockIdx.x * 128 * MT;
@@ -443,6 +477,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         for (int i = 0; i < 2; ++i) { mbar_init(&sm->a_full[i], 256); mbar_init(&sm->a_empty[i], 1); }
         mbar_init(&sm->acc_full, 1);
         mbar_init(&sm->acc2_full, 1);
+        if (FUSED) for (int i = 0; i < 16; ++i) mbar_init(&sm->a2_full[i], 256);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&sm->tmem_base, ncols);
@@ -513,14 +548,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
             }
             umma_commit(&sm->acc_full);
             if (FUSED) {
+                const uint32_t a2_lbo = (uint32_t)p.R2pad * 16;
                 for (int c2 = 0; c2 < p.nchunk2; ++c2, ++it) {
-                    const int cc = nchunk + c2, buf = cc & 1;
-                    mbar_wait(&sm->a_full[buf], (cc >> 1) & 1);
+                    mbar_wait(&sm->a2_full[c2], 0);
                     const int s = it % S;
                     mbar_wait(&sm->b_full[s], (it / S) & 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(a_base + (size_t)buf * 2 * a_half);
-                    const uint32_t a_lo = a_hi + a_half;
+                    const uint32_t a_hi = smem_u32(a2_base + (size_t)c2 * 2 * a2_half);
+                    const uint32_t a_lo = a_hi + a2_half;
                     const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
                     const uint32_t b_lo = b_hi + b_half;
                     for (int mt = 0; mt < MT; ++mt) {
@@ -532,7 +567,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                             const uint32_t bb = (pass == 1 ? b_lo : b_hi);
 #pragma unroll
                             for (int ks = 0; ks < KSTEPS; ++ks) {
-                                uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
+                                uint64_t ad = smem_desc(aa + ks * 2 * a2_lbo, a2_lbo, 128);
                                 uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
                                 uint32_t accum = (c2 | pass | ks) != 0;
                                 umma<BF16>(d_tmem, ad, bd, idesc, accum);
@@ -540,7 +575,6 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                         }
                     }
                     umma_commit(&sm->b_empty[s]);
-                    umma_commit(&sm->a_empty[buf]);
                 }
                 umma_commit(&sm->acc2_full);
             }
@@ -588,15 +622,22 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
         int ep_act = p.out_act;
         if (FUSED) {
             // ---- GEMM-2 operand: snake2(D1 + b7), 16 channels per chunk, straight from TMEM ----
-            for (int c2 = 0; c2 < p.nchunk2; ++c2) {
-                const int cc = nchunk + c2, buf = cc & 1;
-                mbar_wait(&sm->a_empty[buf], ((cc >> 1) & 1) ^ 1);
-                uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-                uint8_t* alo = ahi + a_half;
-                if (MT == 2) {
-                    const int arow = half * 128 + q * 32 + lane;
-                    uint32_t v[16];
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * N + c2 * 16), v);
+            // The whole operand stays resident (no ring, no waits): the MMA warp starts chunk c2 as soon as it is
+            // complete while the workers already transform the next ones.
+            const int Rpad2 = p.R2pad;
+            const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+            if (MT == 2) {
+                // warp (q, half) owns rows q*32.. of accumulator `half`, all 16 columns of a chunk
+                const int arow = half * 128 + q * 32 + lane;
+                uint32_t v[16], vn[16];
+                tmem_ld16_issue(lane_addr + (uint32_t)(half * N), v);
+                tmem_ld_wait16(v);
+#pragma unroll 1
+                for (int c2 = 0; c2 < p.nchunk2; ++c2) {
+                    uint8_t* ahi = a2_base + (size_t)c2 * 2 * a2_half;
+                    uint8_t* alo = ahi + a2_half;
+                    const bool more = c2 + 1 < p.nchunk2;
+                    if (more) tmem_ld16_issue(lane_addr + (uint32_t)(half * N + (c2 + 1) * 16), vn);
 #pragma unroll
                     for (int pc = 0; pc < 4; ++pc) {
                         const int co = c2 * 16 + pc * 4;
@@ -608,12 +649,28 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                         x4.y = snake_fast(__uint_as_float(v[pc * 4 + 1]) + bi.y, al.y, ia.y);
                         x4.z = snake_fast(__uint_as_float(v[pc * 4 + 2]) + bi.z, al.z, ia.z);
                         x4.w = snake_fast(__uint_as_float(v[pc * 4 + 3]) + bi.w, al.w, ia.w);
-                        split_store<BF16>(x4, pc, arow, Rpad, ahi, alo);
+                        split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
                     }
-                } else {   // MT == 1: the two warps of a lane quarter take 8 columns each
-                    const int arow = q * 32 + lane;
-                    uint32_t v[8];
-                    tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c2 * 16 + half * 8), v);
+                    fence_proxy_async();
+                    mbar_arrive(&sm->a2_full[c2]);
+                    if (more) {
+                        tmem_ld_wait16(vn);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = vn[i];
+                    }
+                }
+            } else {
+                // MT == 1: the two warps of a lane quarter take 8 columns of every chunk each
+                const int arow = q * 32 + lane;
+                uint32_t v[8], vn[8];
+                tmem_ld8_issue(lane_addr + (uint32_t)(half * 8), v);
+                tmem_ld_wait8(v);
+#pragma unroll 1
+                for (int c2 = 0; c2 < p.nchunk2; ++c2) {
+                    uint8_t* ahi = a2_base + (size_t)c2 * 2 * a2_half;
+                    uint8_t* alo = ahi + a2_half;
+                    const bool more = c2 + 1 < p.nchunk2;
+                    if (more) tmem_ld8_issue(lane_addr + (uint32_t)((c2 + 1) * 16 + half * 8), vn);
 #pragma unroll
                     for (int pp = 0; pp < 2; ++pp) {
                         const int pc = half * 2 + pp;
@@ -626,13 +683,18 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(TcConvParams p
                         x4.y = snake_fast(__uint_as_float(v[pp * 4 + 1]) + bi.y, al.y, ia.y);
                         x4.z = snake_fast(__uint_as_float(v[pp * 4 + 2]) + bi.z, al.z, ia.z);
                         x4.w = snake_fast(__uint_as_float(v[pp * 4 + 3]) + bi.w, al.w, ia.w);
-                        split_store<BF16>(x4, pc, arow, Rpad, ahi, alo);
+                        split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&sm->a2_full[c2]);
+                    if (more) {
+                        tmem_ld_wait8(vn);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = vn[i];
                     }
                 }
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(&sm->a_full[buf]);
             }
+            tc_fence_before();
             if (probe) g_tc_phase_clock[3] = clock64();             // GEMM-2 operand produced
             mbar_wait(&sm->acc2_full, 0);
             tc_fence_after();
@@ -954,41 +1016,60 @@ bool tc_conv_plan(TcConvParams& p) {
         if (p.Cout % cand == 0) { N = cand; break; }
     if (N < 32) return false;
     p.N = N;
+    const int KG = p.bf16 ? 2 : 4;
+    if (p.bf16 && p.promoted) return false;
+    if (p.fused && (N != p.Cout || p.Cin != p.Cout || p.vf != 1 || N > 256)) return false;
+    p.nchunk = p.Cin * p.vf / tc::kChunk;
+    p.nchunk2 = p.fused ? p.Cout / tc::kChunk : 0;
     if (p.promoted) {
         p.MT = (N <= 64) ? 4 : 2;              // MT * N <= 256 columns per TMEM buffer
         p.promote_every = 8 / p.Kr < 1 ? 1 : 8 / p.Kr;
-    } else if (p.fused) {
-        // whole ResidualUnit in one CTA: every channel in one tile, D1 and D2 both resident in TMEM
-        if (N != p.Cout || p.Cin != p.Cout || p.vf != 1 || N > 256) return false;
-        p.MT = (2 * 2 * N <= 512) ? 2 : 1;
-        p.nchunk2 = p.Cout / tc::kChunk;
-    } else {
-        p.MT = (N <= 128) ? 4 : 2;
-    }
-    p.nchunk = p.Cin * p.vf / tc::kChunk;
-    int R = 128 * p.MT + (p.Kr - 1) * p.dil;
-    int Rpad = R;
-    while (Rpad % 8 != 2) ++Rpad;
-    p.Rpad = Rpad;
-    int cols = p.MT * N * (p.fused ? 2 : 1), pow2 = 32;
-    while (pow2 < cols) pow2 <<= 1;
-    if (pow2 > 512 || (p.promoted && cols > 256)) return false;
-    p.tmem_cols = p.promoted ? 512 : pow2;
-    const int KG = p.bf16 ? 2 : 4;
-    if (p.bf16 && p.promoted) return false;
-    size_t a_bytes = (size_t)4 * Rpad * 16 * KG;        // 2 bufs x (hi,lo)
-    size_t b_stage = (size_t)2 * N * 16 * KG;
-    int S = tc::kMaxStagesB;
-    while (S > 2 && 128 + a_bytes + S * b_stage > 225 * 1024) --S;
-    if (128 + a_bytes + S * b_stage > 225 * 1024) return false;
-    p.stagesB = S;
-    p.smem_bytes = 128 + a_bytes + S * b_stage;
-    if (p.promoted) {
+        int R = 128 * p.MT + (p.Kr - 1) * p.dil, Rpad = R;
+        while (Rpad % 8 != 2) ++Rpad;
+        p.Rpad = Rpad;
+        p.tmem_cols = 512;
+        size_t a_bytes = (size_t)4 * Rpad * 16 * KG, b_stage = (size_t)2 * N * 16 * KG;
+        int S = tc::kMaxStagesB;
+        while (S > 2 && 128 + a_bytes + S * b_stage > 225 * 1024) --S;
+        if (128 + a_bytes + S * b_stage > 225 * 1024) return false;
+        p.stagesB = S;
+        p.smem_bytes = 128 + a_bytes + S * b_stage;
         // the accumulator warps reuse the operand buffers as an [8 warps][32][132] transpose stage
         size_t stage = (size_t)8 * 32 * 132 * 4 + 128;
         if (p.smem_bytes < stage) p.smem_bytes = stage;
+        return true;
     }
-    return true;
+    // conv_tc_kernel.  A tile is MT accumulators of 128 rows x N columns (x2 when fused: D1 and D2) sharing every weight
+    // tile.  Two candidate residencies: two CTAs per SM (<= 256 TMEM columns, <= 112 KB smem each; one CTA's produce and
+    // epilogue phases hide behind the other's MMAs) when the caller allows it for this N, else one CTA per SM.
+    const int per = (p.fused ? 2 : 1) * N;
+    for (int pass = (p.occ2_maxn > 0 && N <= p.occ2_maxn) ? 0 : 1; pass < 2; ++pass) {
+        const int colcap = pass == 0 ? 256 : 512;
+        const size_t smemcap = pass == 0 ? 112 * 1024 : 225 * 1024;
+        int MT = colcap / per;
+        MT = MT >= 4 ? 4 : (MT >= 2 ? 2 : MT);
+        if (p.fused && MT > 2) MT = 2;
+        for (; MT >= 1; MT >>= 1) {
+            int R = 128 * MT + (p.Kr - 1) * p.dil, Rpad = R;
+            while (Rpad % 8 != 2) ++Rpad;
+            int cols = MT * per, pow2 = 32;
+            while (pow2 < cols) pow2 <<= 1;
+            size_t a_bytes = (size_t)4 * Rpad * 16 * KG;        // 2 bufs x (hi,lo)
+            size_t b_stage = (size_t)2 * N * 16 * KG;
+            // fused: the whole GEMM-2 operand snake2(D1 + b7) stays resident: nchunk2 chunks of (hi,lo) x KG x R2pad x 16 B
+            const int R2pad = 128 * MT + 2;
+            size_t a2_bytes = p.fused ? (size_t)p.nchunk2 * 2 * KG * R2pad * 16 : 0;
+            int S = tc::kMaxStagesB;
+            while (S > 2 && tc::kSmemHdr + a_bytes + S * b_stage + a2_bytes > smemcap) --S;
+            size_t total = tc::kSmemHdr + a_bytes + S * b_stage + a2_bytes;
+            if (total > smemcap) continue;
+            const size_t stage = (size_t)8 * 32 * 36 * 4 + tc::kSmemHdr;   // epilogue transpose stage (8 warps x [32][36] floats)
+            if (total < stage) total = stage;
+            p.MT = MT; p.Rpad = Rpad; p.R2pad = R2pad; p.tmem_cols = pow2; p.stagesB = S; p.smem_bytes = total;
+            return true;
+        }
+    }
+    return false;
 }
 
 size_t tc_blob_floats(const TcConvParams& p) {

@@ -39,7 +39,7 @@ struct ConvW {
     bool has16 = false; size_t tcw16 = 0;   // bf16 hi/lo blob (non-promoted layers only)
 };
 struct SnakeW { size_t a = 0, ia = 0; int C = 0; };
-struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; int H = 0, U = 0, G = 0; };
+struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; size_t whh16[2] = {0, 0}; bool has16 = false; int H = 0, U = 0, G = 0; };
 struct ResW { SnakeW s1; ConvW c7; SnakeW s2; ConvW c1; int dil = 1; };
 struct VqW { size_t w_in, b_in, cb, cbn, cbn2, w_out, b_out; };
 
@@ -78,7 +78,9 @@ struct fac_handle {
     // tcgen05 3xTF32 path (fac_set_option "tensor_cores"): 0 = never, 1 = layers downstream of the VQ only
     // (decoder, timbre branch), 2 = every eligible layer (default; promoted accumulation upstream of the VQ)
     int use_tc = 2;
-    bool fuse_res = true;           // fused ResidualUnit launches (fac_set_option "fuse_resunit")
+    int fuse_res = 1;               // fused ResidualUnit launches (fac_set_option "fuse_resunit"); 2 = only where the
+                                    // fused tile still allows two CTAs per SM (C <= 128)
+    int tc_occ2 = 256;              // fac_set_option "tc_occ2_maxn": conv_tc tiles with N <= this are planned for two CTAs per SM (0 = off)
     bool dec_bf16 = true;           // decoder-side layers use the bf16x3 split (fac_set_option "decoder_bf16")
     float* aa_filter = nullptr;
     // optional per-kernel-family timing (fac_profile_*): CUDA events around every launch
@@ -258,6 +260,26 @@ LstmW pack_lstm(fac_handle* h, int m, const std::string& prefix, bool promoted =
                     for (int u = 0; u < U; ++u)
                         h->pack[L.whh[l] + ((size_t)cta * H + k) * R + g * U + u] =
                             whh.data[((size_t)g * H + cta * U + u) * H + k];
+        if (!promoted) {
+            // bf16 hi/lo words for the recurrence downstream of the VQ: [cta][H/16][hi|lo][8 k-pairs][R]
+            auto bf16_rn = [](float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7FFFu + ((u >> 16) & 1u); return (uint32_t)(u >> 16); };
+            auto bf16_f = [](uint32_t b) { uint32_t u = b << 16; float f; memcpy(&f, &u, 4); return f; };
+            L.whh16[l] = pack_alloc(h, (size_t)L.G * H * R);
+            for (int cta = 0; cta < L.G; ++cta)
+                for (int sub = 0; sub < H / 16; ++sub)
+                    for (int k2 = 0; k2 < 8; ++k2)
+                        for (int r = 0; r < R; ++r) {
+                            const int g = r / U, u = r % U;
+                            const float* wrow = &whh.data[((size_t)g * H + cta * U + u) * H + sub * 16 + 2 * k2];
+                            uint32_t h0 = bf16_rn(wrow[0]), h1 = bf16_rn(wrow[1]);
+                            uint32_t l0 = bf16_rn(wrow[0] - bf16_f(h0)), l1 = bf16_rn(wrow[1] - bf16_f(h1));
+                            uint32_t hw = h0 | (h1 << 16), lw = l0 | (l1 << 16);
+                            size_t base = L.whh16[l] + ((size_t)cta * (H / 16) + sub) * 16 * R;
+                            memcpy(&h->pack[base + (size_t)k2 * R + r], &hw, 4);
+                            memcpy(&h->pack[base + (size_t)(8 + k2) * R + r], &lw, 4);
+                        }
+            L.has16 = true;
+        }
     }
     return L;
 }
@@ -481,6 +503,7 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
         tp.Cin = w.Cin; tp.Cout = w.Cout; tp.vf = w.vf; tp.Kr = w.Kr; tp.promoted = w.promoted ? 1 : 0;
         tp.dil = w.vf == 1 ? o.dil : 1;
         tp.bf16 = (c.h->dec_bf16 && w.has16 && !c.vq_critical) ? 1 : 0;
+        tp.occ2_maxn = c.h->tc_occ2;
         if (tc_conv_plan(tp)) {
             tp.x = x; tp.y = y; tp.wblob = c.W(tp.bf16 ? w.tcw16 : w.tcw); tp.bias = c.W(w.b);
             if (o.in_snake) { tp.in_alpha = c.W(o.in_snake->a); tp.in_inv_alpha = c.W(o.in_snake->ia); }
@@ -548,6 +571,8 @@ bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B,
     TcConvParams tp;
     tp.Cin = r.c7.Cin; tp.Cout = r.c7.Cout; tp.vf = 1; tp.Kr = r.c7.K; tp.dil = r.dil; tp.fused = 1;
     tp.bf16 = (c.h->dec_bf16 && r.c7.has16 && r.c1.has16) ? 1 : 0;
+    tp.occ2_maxn = c.h->tc_occ2;
+    if (c.h->fuse_res == 2 && r.c7.Cout > 128) return false;
     if (!tc_conv_plan(tp)) return false;
     if (c.dry) return true;
     const int k_eff = (r.c7.K - 1) * r.dil + 1;
@@ -599,6 +624,7 @@ void slstm(Ctx& c, const LstmW& L, const float* x, float* y, int B, int T) {
             LstmParams p;
             p.xg = xg + (size_t)b0 * T * 4 * H;
             p.whh_p = c.W(L.whh[l]);
+            if (c.h->dec_bf16 && L.has16 && !c.vq_critical) { p.bf16 = 1; p.whh_p16 = c.W(L.whh16[l]); }
             p.skip = l == 1 ? x + (size_t)b0 * T * H : nullptr;
             p.y = (l == 0 ? h1 : y) + (size_t)b0 * T * H;
             p.hT = hT; p.bar = bar;
@@ -1180,6 +1206,7 @@ int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, i
         t.data.assign(w_host[i], w_host[i] + t.numel());
         tmp.host[0][std::string("l.") + names[i]] = std::move(t);
     }
+    tmp.dec_bf16 = h->dec_bf16;     // decoder-class precision (bf16 hi/lo) unless the caller switched it off
     LstmW L;
     try { L = pack_lstm(&tmp, 0, "l"); } catch (const PackError& e) { h->err = e.msg; return FAC_ERR_UNSUPPORTED; }
     cudaSetDevice(h->device);
@@ -1204,7 +1231,8 @@ int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, i
 
 int fac_set_option(fac_handle* h, const char* name, int value) {
     if (!h || !name) return FAC_ERR_INVALID;
-    if (std::string(name) == "fuse_resunit") { h->fuse_res = value != 0; return FAC_OK; }
+    if (std::string(name) == "fuse_resunit") { h->fuse_res = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
+    if (std::string(name) == "tc_occ2_maxn") { h->tc_occ2 = value < 0 ? 0 : value; return FAC_OK; }
     if (std::string(name) == "decoder_bf16") { h->dec_bf16 = value != 0; return FAC_OK; }
     if (std::string(name) == "tensor_cores") { h->use_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     h->err = std::string("unknown option ") + name;
@@ -1220,6 +1248,7 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
     cudaStream_t st = (cudaStream_t)stream;
     TcConvParams tp;
     tp.Cin = Cin; tp.Cout = Cout; tp.promoted = promoted == 1 ? 1 : 0; tp.bf16 = promoted == 2 ? 1 : 0;
+    tp.occ2_maxn = h->tc_occ2;
     if (stride == 1) { tp.vf = 1; tp.Kr = K; tp.dil = dil; }
     else if (K == 2 * stride && dil == 1) { tp.vf = stride; tp.Kr = 2; tp.dil = 1; }
     else { h->err = "fac_debug_conv_tc: unsupported stride/kernel"; return FAC_ERR_UNSUPPORTED; }
@@ -1265,8 +1294,9 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
     fac_handle tmp;
     tmp.device = h->device;
     tmp.use_tc = mode == 0 ? 0 : 1;          // 0: fp32 FMA, 1: two tcgen05 launches, 2: fused launch; 3/4 = 1/2 with bf16 split
-    tmp.fuse_res = mode == 2 || mode == 4;
+    tmp.fuse_res = (mode == 2 || mode == 4) ? 1 : 0;
     tmp.dec_bf16 = mode >= 3;
+    tmp.tc_occ2 = h->tc_occ2;
     auto put = [&](const char* key, const float* d, std::vector<int64_t> shp) {
         HostTensor t;
         t.shape = shp;

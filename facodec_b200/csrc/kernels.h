@@ -48,9 +48,13 @@ struct TcConvParams {
     const float* wblob2 = nullptr;     // 1x1 conv weight blob (same tile N), when fused
     const float* bias2 = nullptr;
     int nchunk2 = 0;
+    int occ2_maxn = 0;                 // > 0: tiles with N <= occ2_maxn are planned for TWO resident CTAs per SM
+                                       // (<= 256 TMEM columns, <= 112 KB smem each) so one CTA's MMAs overlap the other's
+                                       // produce / epilogue phases
     // plan (tc_conv_plan)
     int promote_every = 1;
     int N = 0, MT = 0, nchunk = 0, Rpad = 0, stagesB = 0, tmem_cols = 0;
+    int R2pad = 0;                     // fused: row pitch (rows) of the resident GEMM-2 operand chunks
     size_t smem_bytes = 0;
     size_t x_bstride = 0, y_bstride = 0;
 };
@@ -65,6 +69,8 @@ cudaError_t tc_read_phase_clocks(long long* out8);   // probe-CTA phase timestam
 struct LstmParams {
     const float* xg = nullptr;    // [B][T][4H] = x W_ih^T + b_ih + b_hh, gate order i,f,g,o
     const float* whh_p = nullptr; // packed per CTA: [G][H][4U]  (r = gate*U + u)
+    const float* whh_p16 = nullptr; // bf16 split: [G][H/16][hi|lo][8 k-pairs][4U] 32-bit words (k even in the low half)
+    int bf16 = 0;                 // 1 = bf16 hi/lo recurrence (downstream of the VQ only)
     const float* skip = nullptr;  // [B][T][H] added to the output (SLSTM skip) or null
     float* y = nullptr;           // [B][T][H]
     float* hT = nullptr;          // scratch [2][H][32]

@@ -32,7 +32,9 @@ constexpr int LSTM_KS = 16;     // k rows per cp.async sub-chunk
 // cp.async pipeline depth (stages per warp): as deep as shared memory allows -- the K loop is bound by
 // bytes in flight x L2 latency, not by the MMAs.  The cross-warp reduction buffer aliases the stage memory.
 template <int U> struct LstmDepth { static constexpr int D = (U == 8) ? 5 : 4; };
-constexpr int LSTM_HP = LSTM_BT + 8;   // padded smem row of the h sub-chunk (conflict-free fragments)
+// padded smem row of the h sub-chunk (conflict-free B fragments): TF32 fragments read rows k0+t and k0+t+4
+// (pitch 40: 8t + g), bf16 fragments read row pairs 2t, 2t+1 (pitch 36: 2*36*t = 8t mod 32)
+template <bool BF16> struct LstmHP { static constexpr int V = BF16 ? LSTM_BT + 4 : LSTM_BT + 8; };
 
 __device__ __forceinline__ float tf32_rn(float x) {
     uint32_t r;
@@ -47,6 +49,19 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[
           "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
 }
 
+__device__ __forceinline__ void mma_bf16_16x8x16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// (x0, x1) -> bf16x2 hi word (x0 in the low half) and the bf16x2 word of the residuals
+__device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -55,8 +70,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int U>
+// BF16 = true (layers downstream of the VQ only): W_hh arrives pre-split into bf16 hi / bf16 lo words (two
+// consecutive k per 32-bit word, per 16-k sub-chunk [hi|lo][8 k-pairs][4U]), h is split in registers, and the
+// product runs as 3 m16n8k16 bf16 MMAs per 16 k instead of 6 m16n8k8 TF32 MMAs (the K loop is HMMA-bound).
+template <int U, bool BF16>
 __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams p) {
+    constexpr int LSTM_HP = LstmHP<BF16>::V;
     constexpr int R = 4 * U;
     constexpr int RP = R + 1;   // padded row of the reduction buffer (bank-conflict-free reads)
     constexpr int WP = R + 8;                   // padded smem row of the W sub-chunk
@@ -80,7 +99,7 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
     for (int i = tid; i < LSTM_BT * U; i += blockDim.x) cstate[i] = 0.f;
     __syncthreads();
 
-    const float* wsrc = p.whh_p + (size_t)cta * H * R;
+    const float* wsrc = (BF16 ? p.whh_p16 : p.whh_p) + (size_t)cta * H * R;
     float* my_stage = stage_base + warp * LSTM_D * STAGE_F;
 
     constexpr int PAIRS = (LSTM_BT * U + LSTM_WARPS * 32 - 1) / (LSTM_WARPS * 32);
@@ -163,6 +182,32 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
             __syncwarp();
             const float* hs = my_stage + (sub % LSTM_D) * STAGE_F;
             const float* wsm = hs + LSTM_KS * LSTM_HP;
+            if constexpr (BF16) {
+                // one k16 step per sub-chunk.  B fragments: b0 = h[2t..2t+1][n0+g], b1 = h[2t+8..2t+9][n0+g]
+                uint32_t bh[NTL][2], bl[NTL][2];
+#pragma unroll
+                for (int j = 0; j < NTL; ++j) {
+                    const float* hp = hs + (2 * ft) * LSTM_HP + j * 8 + fg;
+                    bf16_split2(hp[0], hp[LSTM_HP], bh[j][0], bl[j][0]);
+                    bf16_split2(hp[8 * LSTM_HP], hp[9 * LSTM_HP], bh[j][1], bl[j][1]);
+                }
+                const uint32_t* wh = reinterpret_cast<const uint32_t*>(wsm);   // rows 0..7: hi k-pairs, 8..15: lo
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    // A fragments: a0 = (g, k 2t..), a1 = (g+8, k 2t..), a2 = (g, k 2t+8..), a3 = (g+8, k 2t+8..)
+                    uint32_t ah[4], al[4];
+                    ah[0] = wh[ft * WP + i * 16 + fg];           ah[1] = wh[ft * WP + i * 16 + fg + 8];
+                    ah[2] = wh[(ft + 4) * WP + i * 16 + fg];     ah[3] = wh[(ft + 4) * WP + i * 16 + fg + 8];
+                    al[0] = wh[(8 + ft) * WP + i * 16 + fg];     al[1] = wh[(8 + ft) * WP + i * 16 + fg + 8];
+                    al[2] = wh[(12 + ft) * WP + i * 16 + fg];    al[3] = wh[(12 + ft) * WP + i * 16 + fg + 8];
+#pragma unroll
+                    for (int j = 0; j < NTL; ++j) {
+                        mma_bf16_16x8x16(acc[i][j], al, bh[j]);    // small terms first
+                        mma_bf16_16x8x16(acc[i][j], ah, bl[j]);
+                        mma_bf16_16x8x16(acc[i][j], ah, bh[j]);
+                    }
+                }
+            } else {
 #pragma unroll
             for (int ks = 0; ks < LSTM_KS / 8; ++ks) {
                 const int k0 = ks * 8;
@@ -194,6 +239,7 @@ __global__ void __launch_bounds__(LSTM_WARPS * 32, 1) lstm_rec_kernel(LstmParams
                         mma_tf32_16x8x8(acc[i][j], ah, bh[j]);
                     }
                 }
+            }
             }
             __syncwarp();   // everyone done with this stage before it is refilled
         }
@@ -257,11 +303,11 @@ int lstm_units_per_cta(int H) {
     return 0;
 }
 
-template <int U>
+template <int U, bool BF16>
 static cudaError_t launch_u(const LstmParams& p, cudaStream_t st) {
     constexpr int R = 4 * U;
-    size_t smem = sizeof(float) * (LSTM_WARPS * LstmDepth<U>::D * LSTM_KS * (LSTM_HP + R + 8) + LSTM_BT * U);
-    cudaError_t e = cudaFuncSetAttribute(lstm_rec_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = sizeof(float) * (LSTM_WARPS * LstmDepth<U>::D * LSTM_KS * (LstmHP<BF16>::V + R + 8) + LSTM_BT * U);
+    cudaError_t e = cudaFuncSetAttribute(lstm_rec_kernel<U, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(p.bar, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
@@ -270,13 +316,14 @@ static cudaError_t launch_u(const LstmParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     LstmParams pp = p;
     void* args[] = {&pp};
-    return cudaLaunchCooperativeKernel((void*)lstm_rec_kernel<U>, dim3(p.G), dim3(LSTM_WARPS * 32), args, smem, st);
+    return cudaLaunchCooperativeKernel((void*)lstm_rec_kernel<U, BF16>, dim3(p.G), dim3(LSTM_WARPS * 32), args, smem, st);
 }
 
 cudaError_t launch_lstm_layer(const LstmParams& p, cudaStream_t st) {
     if (p.B > LSTM_BT || p.B <= 0) return cudaErrorInvalidValue;
-    if (p.U == 8) return launch_u<8>(p, st);
-    if (p.U == 12) return launch_u<12>(p, st);
+    if (p.bf16 && !p.whh_p16) return cudaErrorInvalidValue;
+    if (p.U == 8) return p.bf16 ? launch_u<8, true>(p, st) : launch_u<8, false>(p, st);
+    if (p.U == 12) return p.bf16 ? launch_u<12, true>(p, st) : launch_u<12, false>(p, st);
     return cudaErrorInvalidValue;
 }
 

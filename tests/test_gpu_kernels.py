@@ -87,9 +87,13 @@ def test_conv_kernel_vs_torch(case, built_lib):
     assert err <= 2e-5 * max(scale, 1.0), f"max err {err} (scale {scale})"
 
 
-@pytest.mark.parametrize("B,T,H", [(2, 5, 1024), (3, 17, 1536), (32, 4, 1024)])
-def test_slstm_vs_torch(B, T, H, built_lib):
+@pytest.mark.parametrize("bf16", [0, 1])
+@pytest.mark.parametrize("B,T,H", [(2, 5, 1024), (3, 17, 1536), (32, 4, 1024), (5, 40, 1536)])
+def test_slstm_vs_torch(B, T, H, bf16, built_lib):
+    """bf16 = 0: 3xTF32 recurrence + input projections (the class used upstream of the VQ); bf16 = 1: bf16 hi/lo
+    split (16 mantissa bits per operand; decoder only), looser bound."""
     e = _engine()
+    e.set_option("decoder_bf16", bf16)
     g = torch.Generator().manual_seed(H + B)
     lstm = torch.nn.LSTM(H, H, 2)
     with torch.no_grad():
@@ -107,7 +111,9 @@ def test_slstm_vs_torch(B, T, H, built_lib):
     rc = e.L.fac_debug_slstm(e.handle, _p(xd), arr, B, T, H, _p(yd), None)
     assert rc == 0, e.L.fac_last_error(e.handle)
     y = yd.cpu().transpose(1, 2)
-    assert (y - ref).abs().max().item() <= 2e-5
+    err = (y - ref).abs().max().item()
+    print(f"SLSTM bf16={bf16} B={B} T={T} H={H} maxerr={err:.3e}")
+    assert err <= (2e-4 if bf16 else 2e-5)
 
 
 TC_CASES = [
@@ -131,15 +137,19 @@ TC_CASES = [
 ]
 
 
+@pytest.mark.parametrize("occ2", [0, 256])
 @pytest.mark.parametrize("promoted", [0, 1, 2])
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv_tc_kernel_vs_torch(case, promoted, built_lib):
+def test_conv_tc_kernel_vs_torch(case, promoted, occ2, built_lib):
     """tcgen05 3xTF32 conv vs fp32 torch.  Operands are split exactly (hi + lo), but the tensor core adds
     into its fp32 TMEM accumulator with truncation, so the error grows ~0.5 ulp per chained MMA
     (measured ~1e-5 relative after 168 MMAs); tolerance 6e-5 * scale.  promoted=1 is the variant that
     drains TMEM into fp32 registers every ~48 MMAs: held to 4e-6 * scale like the fp32 FMA kernel."""
     B, T, Cin, Cout, K, dil, stride, pl, pr, reflect, ins, outs, act, res = case
+    if occ2 and promoted == 1:
+        pytest.skip("the promoted kernel has a single residency plan")
     e = _engine()
+    e.set_option("tc_occ2_maxn", occ2)      # 256: tiles planned for two resident CTAs per SM (MT * N <= 256)
     g = torch.Generator().manual_seed(hash(case) % 1000 + 7)
     x = torch.randn(B, Cin, T, generator=g) * 0.5
     w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
@@ -160,17 +170,23 @@ def test_conv_tc_kernel_vs_torch(case, promoted, built_lib):
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item()
     rel_rms = ((y - ref).double().pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt()).item()
-    print(f"TCERR promoted={promoted} case={case} maxerr={err:.3e} scale={scale:.3f} rel_rms={rel_rms:.3e}")
+    print(f"TCERR promoted={promoted} occ2={occ2} case={case} maxerr={err:.3e} scale={scale:.3f} rel_rms={rel_rms:.3e}")
     tol = {0: 6e-5, 1: 4e-6, 2: 2e-4}[promoted]   # TMEM-truncating 3xTF32 / promoted (fp32-grade) / bf16 hi+lo
     assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
 
 
+@pytest.mark.parametrize("occ2", [0, 256])
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
-@pytest.mark.parametrize("B,T,C,dil", [(2, 300, 96, 1), (1, 520, 96, 9), (2, 200, 192, 3), (1, 130, 256, 1), (2, 40, 96, 9)])
-def test_residual_unit_modes(B, T, C, dil, mode, built_lib):
-    """ResidualUnit (dac.py:25-42) through the fp32 FMA path, two tcgen05 launches, and the fused launch."""
+@pytest.mark.parametrize("B,T,C,dil", [(2, 300, 96, 1), (1, 520, 96, 9), (2, 200, 192, 3), (1, 130, 256, 1), (2, 40, 96, 9),
+                                       (1, 700, 64, 3)])
+def test_residual_unit_modes(B, T, C, dil, mode, occ2, built_lib):
+    """ResidualUnit (dac.py:25-42) through the fp32 FMA path (0), two tcgen05 launches (1 tf32, 3 bf16 split), and the
+    fused launch (2 tf32, 4 bf16 split); occ2 = tiles planned for two CTAs per SM."""
     from oracle import facodec_oracle as O
+    if occ2 and mode == 0:
+        pytest.skip("fp32 FMA path has no residency option")
     e = _engine()
+    e.set_option("tc_occ2_maxn", occ2)
     g = torch.Generator().manual_seed(C + dil + T)
     x = torch.randn(B, C, T, generator=g) * 0.5
     w7 = torch.randn(C, C, 7, generator=g) / math.sqrt(C * 7)
@@ -186,6 +202,11 @@ def test_residual_unit_modes(B, T, C, dil, mode, built_lib):
     yd = torch.full((B, T, C), float("nan"), device="cuda")
     rc = e.L.fac_debug_resunit(e.handle, _p(xd), _p(w7.contiguous()), _p(b7), _p(w1.contiguous()), _p(b1), _p(a1), _p(a2),
                                B, T, C, dil, mode, _p(yd), None)
+    if mode == 2 and C > 128:
+        # the fused kernel keeps the whole GEMM-2 operand in shared memory: with the tf32 split that only fits up to
+        # C = 128 (the product runs fused units with the bf16 split, mode 4)
+        assert rc != 0
+        return
     assert rc == 0, e.L.fac_last_error(e.handle)
     y = yd.cpu().transpose(1, 2)
     assert torch.isfinite(y).all()

@@ -226,4 +226,4 @@ def test_other_precision_modes_keep_parity(mode, built_lib):
     for k, t in zip(("codes_p", "codes_c", "codes_r"), q[5]):
         assert np.array_equal(t.cpu().numpy(), g[k]), k
     assert np.abs(z.cpu().numpy() - g["z"]).max() <= Z_RTOL * np.abs(g["z"]).max()
-    assert rms(y, g["y"]) <= (2e-7 if mode == 0 else RMS_TOL)
+    assert rms(y, g["y"]) <= (5e-7 if mode == 0 else RMS_TOL)
