@@ -820,12 +820,17 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
     uint8_t* b_base = a_base + 4 * a_half;
     const int S = p.stagesB;
     const int P = p.promote_every;
+    float* stage_base = reinterpret_cast<float*>(b_base + (size_t)S * 2 * b_half);   // [8 warps][32][36] epilogue transpose stage
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t0 = blockIdx.x * 128 * MT;
-    const int ntile = blockIdx.y;
-    const int b = blockIdx.z;
     const int nchunk = p.nchunk, Kr = p.Kr;
+    // PERSISTENT: one CTA per SM walks the tile list L = blockIdx.x, += gridDim.x.  L -> (time tile, channel tile, batch),
+    // time fastest.  Every role keeps its ring / phase counters running across tiles, so the producers and the MMA warp
+    // are already two chunks (and two TMEM buffers) into tile i+1 while the accumulator warps still run the epilogue of
+    // tile i (measured before: accumulators idle 2/3 of a CTA's life, producers idle during the epilogue).
+    const int gx = (p.Tout + 128 * MT - 1) / (128 * MT), gy = p.Cout / N;
+    const int ntiles = gx * gy * p.B;
+    const int G = (nchunk + P - 1) / P;
 
     if (tid == 0) {
         for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
@@ -844,78 +849,86 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
     if (warp < 4) reg_dec<32>();      // whole control warpgroup at one program point (4*32*32 + 8*32*64 + 8*32*160 == 640*96)
     if (warp == 0) {
         if (lane == 0) {
-            const float* wsrc = p.wblob + (size_t)ntile * nchunk * Kr * (size_t)(2 * b_half / 4);
             int it = 0;
-            for (int c = 0; c < nchunk; ++c)
-                for (int tap = 0; tap < Kr; ++tap, ++it) {
+            for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+                const int ntile = (L / gx) % gy;
+                const float* wsrc = p.wblob + (size_t)ntile * nchunk * Kr * (size_t)(2 * b_half / 4);
+                for (int j = 0; j < nchunk * Kr; ++j, ++it) {
                     int s = it % S;
                     mbar_wait(&sm->b_empty[s], ((it / S) & 1) ^ 1);
                     mbar_arrive_expect_tx(&sm->b_full[s], 2 * b_half);
-                    bulk_g2s(b_base + (size_t)s * 2 * b_half, wsrc + (size_t)it * (2 * b_half / 4), 2 * b_half, &sm->b_full[s]);
+                    bulk_g2s(b_base + (size_t)s * 2 * b_half, wsrc + (size_t)j * (2 * b_half / 4), 2 * b_half, &sm->b_full[s]);
                 }
+            }
         }
     } else if (warp == 1) {
         {   // whole warp converged; tcgen05 instructions are elect-predicated inside their asm blocks
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t a_lbo = (uint32_t)Rpad * 16, b_lbo = (uint32_t)N * 16;
-            int it = 0;
-            const int G = (nchunk + P - 1) / P;
-            for (int g = 0; g < G; ++g) {
-                const int abuf = g & 1;
-                mbar_wait(&sm->acc_free[abuf], ((g >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const int c_begin = g * P, c_end = (c_begin + P < nchunk) ? c_begin + P : nchunk;
-                for (int c = c_begin; c < c_end; ++c) {
-                    const int buf = c & 1;
-                    mbar_wait(&sm->a_full[buf], (c >> 1) & 1);
-                    const uint32_t a_hi = smem_u32(a_base + (size_t)buf * 2 * a_half);
-                    const uint32_t a_lo = a_hi + a_half;
-                    for (int tap = 0; tap < Kr; ++tap, ++it) {
-                        const int s = it % S;
-                        mbar_wait(&sm->b_full[s], (it / S) & 1);
-                        tc_fence_after();
-                        const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
-                        const uint32_t b_lo = b_hi + b_half;
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil) * 16;
-                            const uint32_t d_tmem = tmem + (uint32_t)(abuf * 256 + mt * N);
+            int it = 0, cg = 0, gg = 0;
+            for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+                for (int g = 0; g < G; ++g, ++gg) {
+                    const int abuf = gg & 1;
+                    mbar_wait(&sm->acc_free[abuf], ((gg >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const int c_begin = g * P, c_end = (c_begin + P < nchunk) ? c_begin + P : nchunk;
+                    for (int c = c_begin; c < c_end; ++c, ++cg) {
+                        const int buf = cg & 1;
+                        mbar_wait(&sm->a_full[buf], (cg >> 1) & 1);
+                        const uint32_t a_hi = smem_u32(a_base + (size_t)buf * 2 * a_half);
+                        const uint32_t a_lo = a_hi + a_half;
+                        for (int tap = 0; tap < Kr; ++tap, ++it) {
+                            const int s = it % S;
+                            mbar_wait(&sm->b_full[s], (it / S) & 1);
+                            tc_fence_after();
+                            const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
+                            const uint32_t b_lo = b_hi + b_half;
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil) * 16;
+                                const uint32_t d_tmem = tmem + (uint32_t)(abuf * 256 + mt * N);
 #pragma unroll
-                            for (int pass = 0; pass < 3; ++pass) {
-                                const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
-                                const uint32_t bb = (pass == 1 ? b_lo : b_hi);
+                                for (int pass = 0; pass < 3; ++pass) {
+                                    const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
+                                    const uint32_t bb = (pass == 1 ? b_lo : b_hi);
 #pragma unroll
-                                for (int ks = 0; ks < kChunk / 8; ++ks) {
-                                    uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
-                                    uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
-                                    uint32_t accum = ((c - c_begin) | tap | pass | ks) != 0;
-                                    umma_tf32(d_tmem, ad, bd, idesc, accum);
+                                    for (int ks = 0; ks < kChunk / 8; ++ks) {
+                                        uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
+                                        uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
+                                        uint32_t accum = ((c - c_begin) | tap | pass | ks) != 0;
+                                        umma_tf32(d_tmem, ad, bd, idesc, accum);
+                                    }
                                 }
                             }
+                            umma_commit(&sm->b_empty[s]);
                         }
-                        umma_commit(&sm->b_empty[s]);
+                        umma_commit(&sm->a_empty[buf]);
                     }
-                    umma_commit(&sm->a_empty[buf]);
+                    umma_commit(&sm->acc_ready[abuf]);
                 }
-                umma_commit(&sm->acc_ready[abuf]);
             }
         }
     } else if (warp >= 4 && warp < 12) {
         // ================= activation producers (warps 4..11, 64 registers each) =================
         reg_dec<64>();
         const int wtid = tid - 128;                                 // 0..255
-        const bool probe = (wtid == 0 && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0);
+        const bool probe = (wtid == 0 && blockIdx.x == 3);
         if (probe) g_tc_phase_clock[0] = clock64();
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
-        const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
-        for (int c = 0; c < nchunk; ++c) {
-            const int buf = c & 1;
-            uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
-            mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
-            produce_chunk<256, false, 4, true>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
-            fence_proxy_async();
-            mbar_arrive(&sm->a_full[buf]);
+        int cg = 0;
+        for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+            const int t0 = (L % gx) * 128 * MT;
+            const int b = L / (gx * gy);
+            const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
+            for (int c = 0; c < nchunk; ++c, ++cg) {
+                const int buf = cg & 1;
+                uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
+                mbar_wait(&sm->a_empty[buf], ((cg >> 1) & 1) ^ 1);
+                produce_chunk<256, false, 4, true>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
+                fence_proxy_async();
+                mbar_arrive(&sm->a_full[buf]);
+            }
+            if (probe && L == blockIdx.x) g_tc_phase_clock[1] = clock64();   // first tile: all chunks produced
         }
-        if (probe) g_tc_phase_clock[1] = clock64();                 // all chunks produced
     } else if (warp >= 12) {
         // ================= accumulators (warps 12..19, 160 registers each): promote + epilogue =================
         reg_inc<160>();
@@ -925,82 +938,95 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
         if (split > ncols) split = ncols;
         const int mycol0 = half ? split : 0;
         const int mycols = half ? ncols - split : split;
-        float acc[128];
-#pragma unroll
-        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-        const int G = (nchunk + P - 1) / P;
-        for (int g = 0; g < G; ++g) {
-            const int abuf = g & 1;
-            mbar_wait(&sm->acc_ready[abuf], (g >> 1) & 1);
-            tc_fence_after();
-            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + mycol0);
-#pragma unroll
-            for (int grp = 0; grp < 8; ++grp) {
-                if (grp * 16 < mycols) {
-                    uint32_t v[16];
-                    tmem_ld16(tbase + grp * 16, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[grp * 16 + i] += __uint_as_float(v[i]);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&sm->acc_free[abuf]);
-        }
-        // ---- epilogue: every MMA has retired and the producers are done, so the operand buffers are free.
-        // Park the whole register tile in shared memory ([32 rows][132] per warp, conflict-free both ways), then a
-        // ROLLED loop streams it out coalesced (8 lanes = 128 contiguous bytes of one row).  Rolled on purpose: the
-        // unrolled register epilogue was 20k SASS instructions and ran out of the instruction cache.
-        float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
-        const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
-        const bool aprobe = (tid == 12 * 32 && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0);
-        if (aprobe) g_tc_phase_clock[2] = clock64();                // last promotion done
-        float* stage = reinterpret_cast<float*>(a_base) + (size_t)(warp - 12) * (32 * 132);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j * 4 < mycols)
-                *reinterpret_cast<float4*>(stage + lane * 132 + j * 4) =
-                    make_float4(acc[j * 4], acc[j * 4 + 1], acc[j * 4 + 2], acc[j * 4 + 3]);
-        __syncwarp();
-        if (aprobe) g_tc_phase_clock[3] = clock64();                // register tile staged
+        float* stage = stage_base + (size_t)(warp - 12) * (32 * 36);
         const int c4 = lane & 7, rsub = lane >> 3;
         const int act = p.out_act;
+        const bool aprobe = (tid == 12 * 32 && blockIdx.x == 3);
+        int gg = 0;
+        for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+            const int t0 = (L % gx) * 128 * MT;
+            const int ntile = (L / gx) % gy;
+            const int b = L / (gx * gy);
+            float acc[128];
+#pragma unroll
+            for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+            for (int g = 0; g < G; ++g, ++gg) {
+                const int abuf = gg & 1;
+                mbar_wait(&sm->acc_ready[abuf], (gg >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + mycol0);
+#pragma unroll
+                for (int grp = 0; grp < 8; ++grp) {
+                    if (grp * 16 < mycols) {
+                        uint32_t v[16];
+                        tmem_ld16(tbase + grp * 16, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[grp * 16 + i] += __uint_as_float(v[i]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&sm->acc_free[abuf]);
+            }
+            // ---- epilogue.  The TMEM buffers are already released, so the MMA warp and the producers work on the next
+            // tile meanwhile.  32-column slabs of the register tile go through a private [32][36] shared-memory
+            // transpose stage (conflict-free both ways) and leave coalesced (8 lanes = 128 contiguous bytes of a row).
+            // The slab loop is ROLLED on purpose (the fully unrolled register epilogue was 20k SASS instructions and ran
+            // out of the instruction cache); only the register -> stage copy is selected by a switch.
+            float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
+            const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
+            if (aprobe && L == blockIdx.x) g_tc_phase_clock[2] = clock64();   // first tile: last promotion done
 #pragma unroll 1
-        for (int cb = 0; cb < mycols; cb += 32) {                   // 32-column block of this thread's range
-            const int jc = cb + c4 * 4;                             // column inside my range handled by this lane
-            if (jc >= mycols) continue;
-            const int jflat = mycol0 + jc;
-            const int mt = jflat / N, col = jflat - mt * N;
-            const int co = ntile * N + col;
-            float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), al = bi, ia = bi;
-            if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-            if (act == ACT_SNAKE) {
-                al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
-                ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
-            }
-            const int tbase_row = t0 + mt * 128 + q * 32;
+            for (int sl = 0; sl * 32 < mycols; ++sl) {
+#define FAC_PARK(S0)                                                                                              \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j)                                                                \
+        *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =                                                  \
+            make_float4(acc[(S0) + j * 4], acc[(S0) + j * 4 + 1], acc[(S0) + j * 4 + 2], acc[(S0) + j * 4 + 3]);
+                switch (sl) {
+                    case 0: FAC_PARK(0) break;
+                    case 1: FAC_PARK(32) break;
+                    case 2: FAC_PARK(64) break;
+                    default: FAC_PARK(96) break;
+                }
+#undef FAC_PARK
+                __syncwarp();
+                const int jc = sl * 32 + c4 * 4;                        // column inside my range handled by this lane
+                if (jc < mycols) {
+                    const int jflat = mycol0 + jc;
+                    const int mt = jflat / N, col = jflat - mt * N;
+                    const int co = ntile * N + col;
+                    float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), al = bi, ia = bi;
+                    if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+                    if (act == ACT_SNAKE) {
+                        al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
+                        ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
+                    }
+                    const int tbase_row = t0 + mt * 128 + q * 32;
 #pragma unroll 2
-            for (int i = 0; i < 8; ++i) {
-                const int row = 4 * i + rsub;
-                const int t = tbase_row + row;
-                if (t >= p.Tout) continue;
-                float4 o = *reinterpret_cast<const float4*>(stage + row * 132 + jc);
-                o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
-                if (act == ACT_SNAKE) {
-                    o.x = snake_fast<true>(o.x, al.x, ia.x); o.y = snake_fast<true>(o.y, al.y, ia.y);
-                    o.z = snake_fast<true>(o.z, al.z, ia.z); o.w = snake_fast<true>(o.w, al.w, ia.w);
-                } else if (act == ACT_TANH) {
-                    o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
-                } else if (act == ACT_MISH) {
-                    o.x = mish_f(o.x); o.y = mish_f(o.y); o.z = mish_f(o.z); o.w = mish_f(o.w);
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = 4 * i + rsub;
+                        const int t = tbase_row + row;
+                        if (t >= p.Tout) continue;
+                        float4 o = *reinterpret_cast<const float4*>(stage + row * 36 + c4 * 4);
+                        o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
+                        if (act == ACT_SNAKE) {
+                            o.x = snake_fast<true>(o.x, al.x, ia.x); o.y = snake_fast<true>(o.y, al.y, ia.y);
+                            o.z = snake_fast<true>(o.z, al.z, ia.z); o.w = snake_fast<true>(o.w, al.w, ia.w);
+                        } else if (act == ACT_TANH) {
+                            o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
+                        } else if (act == ACT_MISH) {
+                            o.x = mish_f(o.x); o.y = mish_f(o.y); o.z = mish_f(o.z); o.w = mish_f(o.w);
+                        }
+                        if (rb) {
+                            float4 r1 = *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co);
+                            o.x += r1.x; o.y += r1.y; o.z += r1.z; o.w += r1.w;
+                        }
+                        *reinterpret_cast<float4*>(yb + (size_t)t * p.ldy + co) = o;
+                    }
                 }
-                if (rb) {
-                    float4 r1 = *reinterpret_cast<const float4*>(rb + (size_t)t * p.ldy + co);
-                    o.x += r1.x; o.y += r1.y; o.z += r1.z; o.w += r1.w;
-                }
-                *reinterpret_cast<float4*>(yb + (size_t)t * p.ldy + co) = o;
+                __syncwarp();
             }
+            if (aprobe && L == blockIdx.x) g_tc_phase_clock[5] = clock64();   // first tile: epilogue done
         }
-        if (aprobe) g_tc_phase_clock[5] = clock64();                // epilogue done
     }
     tc_fence_before();
     __syncthreads();
@@ -1029,14 +1055,12 @@ bool tc_conv_plan(TcConvParams& p) {
         p.Rpad = Rpad;
         p.tmem_cols = 512;
         size_t a_bytes = (size_t)4 * Rpad * 16 * KG, b_stage = (size_t)2 * N * 16 * KG;
+        const size_t stage_bytes = (size_t)8 * 32 * 36 * 4;     // accumulator warps' private epilogue transpose stage
         int S = tc::kMaxStagesB;
-        while (S > 2 && 128 + a_bytes + S * b_stage > 225 * 1024) --S;
-        if (128 + a_bytes + S * b_stage > 225 * 1024) return false;
+        while (S > 2 && 128 + a_bytes + S * b_stage + stage_bytes > 225 * 1024) --S;
+        if (128 + a_bytes + S * b_stage + stage_bytes > 225 * 1024) return false;
         p.stagesB = S;
-        p.smem_bytes = 128 + a_bytes + S * b_stage;
-        // the accumulator warps reuse the operand buffers as an [8 warps][32][132] transpose stage
-        size_t stage = (size_t)8 * 32 * 132 * 4 + 128;
-        if (p.smem_bytes < stage) p.smem_bytes = stage;
+        p.smem_bytes = 128 + a_bytes + S * b_stage + stage_bytes;
         return true;
     }
     // conv_tc_kernel.  A tile is MT accumulators of 128 rows x N columns (x2 when fused: D1 and D2) sharing every weight
@@ -1156,7 +1180,15 @@ cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
             if (e != cudaSuccess) return e;
             configured_p = true;
         }
-        conv_tcp_kernel<<<grid, tc::kThreadsP, p.smem_bytes, st>>>(p);
+        static int sm_count = 0;
+        if (sm_count == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+        }
+        const long long ntiles = (long long)grid.x * grid.y * grid.z;
+        const unsigned nctas = (unsigned)(ntiles < sm_count ? ntiles : sm_count);   // persistent: one CTA per SM
+        conv_tcp_kernel<<<dim3(nctas), tc::kThreadsP, p.smem_bytes, st>>>(p);
     } else {
         if (p.fused && p.bf16) conv_tc_kernel<true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.fused) conv_tc_kernel<true, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
