@@ -34,7 +34,10 @@
 
 namespace fac {
 
-// phase timestamps (clock64) of one probe CTA of the last conv_tc_kernel launch: kernel-tuning aid
+// Kernel-tuning aid (fac_debug_tc_phase_clocks).  conv_tc_kernel: phase timestamps (clock64) of one probe CTA of the last
+// launch.  conv_tcp_kernel (persistent): totals over CTA 3's whole tile list -- [0] cycles the CTA ran, [1] producers waiting
+// for a free operand buffer, [2]/[3]/[4] MMA warp waiting for operands / weights / a free TMEM buffer, [5] accumulators
+// waiting for MMAs, [6] accumulators in the epilogue, [7] tiles processed.
 __device__ long long g_tc_phase_clock[8];
 
 namespace tc {
@@ -55,25 +58,45 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// Two flavours of waiting.  The hand-offs on the critical path (weight ring, operand ring, TMEM buffers seen from the
+// MMA warp and the producers) poll try_wait back to back.  Warps that wait for a long time for something that is not
+// latency critical (accumulator / epilogue warps waiting for a whole GEMM group) pass a suspend-time hint, which parks
+// the thread in hardware: polled, those ~8 warps took a measurable share of the issue slots (ncu: ~60k warp-instructions
+// of spinning per 512-row tile next to 160k of useful work) -- but a parked thread wakes up later, which costs more than
+// it saves on the critical hand-offs (measured).
+template <bool RELAXED>
+__device__ __forceinline__ bool mbar_try_wait_t(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
+    if constexpr (RELAXED) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (kernel aborts with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+template <bool RELAXED = false>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_t<RELAXED>(bar, parity)) return;
     long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_t<RELAXED>(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_t<false>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait_t<true>(bar, parity); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
@@ -195,6 +218,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// Same descriptor from warp-uniform pieces: lo = (address >> 4) + (LBO/16 << 16), hi = SBO/16 (= 8) | version bit 46.
+// The MMA warp keeps every ingredient warp-uniform (values broadcast with __shfl_sync, loop counters, kernel
+// parameters) so the descriptor arithmetic runs on the uniform datapath instead of R2UR round trips: the single
+// issuing warp was the critical resource for N <= 128 tiles (measured ~88 cycles per MMA issued, 35 on the tensor pipe).
+__device__ __forceinline__ uint64_t desc_u(uint32_t addr16, uint32_t lbo16) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(addr16 + (lbo16 << 16)), "r"(0x4008u));
+    return d;
+}
+
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -269,12 +302,7 @@ __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMa
             const int rr = r + u * RSTEP;
             if (rr < R) {
                 float4 x4 = v[u];
-                if (has_alpha) {            // snake(0) == 0, so padded zeros stay zero
-                    x4.x = snake_fast<INL>(x4.x, al.x, ia.x);
-                    x4.y = snake_fast<INL>(x4.y, al.y, ia.y);
-                    x4.z = snake_fast<INL>(x4.z, al.z, ia.z);
-                    x4.w = snake_fast<INL>(x4.w, al.w, ia.w);
-                }
+                if (has_alpha) x4 = snake4_sel<BF16, INL>(x4, al, ia);   // snake(0) == 0, so padded zeros stay zero
                 split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
             }
         }
@@ -327,12 +355,7 @@ __device__ __forceinline__ void store_chunk_regs(const TcConvParams& p, int c, i
         const int rr = (ptid >> 2) + u * RSTEP;
         if (rr < R) {
             float4 x4 = cr.v[u];
-            if (has_alpha) {
-                x4.x = snake_fast(x4.x, al.x, ia.x);
-                x4.y = snake_fast(x4.y, al.y, ia.y);
-                x4.z = snake_fast(x4.z, al.z, ia.z);
-                x4.w = snake_fast(x4.w, al.w, ia.w);
-            }
+            if (has_alpha) x4 = snake4_sel<BF16>(x4, al, ia);
             split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
         }
     }
@@ -369,7 +392,7 @@ __device__ __forceinline__ void epilogue_store4(const TcConvParams& p, const flo
 // shared memory (row pitch 36 floats: conflict-free 16-byte accesses both ways) and reads it back
 // so that 8 lanes cover 128 contiguous bytes of one row: every global load/store instruction
 // (residual in, result out) then touches 4 full lines instead of 32 partial ones.
-template <bool PREFETCH_RES = true>
+template <bool PREFETCH_RES = true, bool MUFU = false>
 __device__ __forceinline__ void epilogue_tile32(const TcConvParams& p, const float* __restrict__ bias, int act,
                                                 const float (&v)[32], float* stage /* [32][36] per warp */, int lane,
                                                 int t_first /* time step of tile row 0 */, int co0 /* channel of col 0 */,
@@ -403,8 +426,7 @@ __device__ __forceinline__ void epilogue_tile32(const TcConvParams& p, const flo
         float4 o = *reinterpret_cast<const float4*>(stage + row * 36 + c4 * 4);
         o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
         if (act == ACT_SNAKE) {
-            o.x = snake_fast(o.x, al.x, ia.x); o.y = snake_fast(o.y, al.y, ia.y);
-            o.z = snake_fast(o.z, al.z, ia.z); o.w = snake_fast(o.w, al.w, ia.w);
+            o = snake4_sel<MUFU>(o, al, ia);
         } else if (act == ACT_TANH) {
             o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
         } else if (act == ACT_MISH) {
@@ -513,32 +535,35 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
             // instruction descriptor: D=f32, A=B=tf32, K-major both, N>>3, M=128>>4
             const uint32_t fmt = BF16 ? 1u : 2u;   // F16F32Format: BF16 = 1, TF32 = 2
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t a_lbo = (uint32_t)Rpad * 16, b_lbo = (uint32_t)N * 16;
+            // everything below is in 16-byte units and warp-uniform
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint32_t a_base16 = __shfl_sync(0xffffffffu, smem_u32(a_base), 0) >> 4;
+            const uint32_t b_base16 = __shfl_sync(0xffffffffu, smem_u32(b_base), 0) >> 4;
+            const uint32_t a_lbo16 = (uint32_t)Rpad, b_lbo16 = (uint32_t)N;
+            const uint32_t a_half16 = a_half >> 4, b_half16 = b_half >> 4;
             int it = 0;
             for (int c = 0; c < nchunk; ++c) {
                 const int buf = c & 1;
                 mbar_wait(&sm->a_full[buf], (c >> 1) & 1);
-                const uint32_t a_hi = smem_u32(a_base + (size_t)buf * 2 * a_half);
-                const uint32_t a_lo = a_hi + a_half;
+                const uint32_t a_hi = a_base16 + (uint32_t)buf * 2 * a_half16;
+                const uint32_t a_lo = a_hi + a_half16;
                 for (int tap = 0; tap < Kr; ++tap, ++it) {
                     const int s = it % S;
                     mbar_wait(&sm->b_full[s], (it / S) & 1);
                     tc_fence_after();
-                    const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
-                    const uint32_t b_lo = b_hi + b_half;
+                    const uint32_t b_hi = b_base16 + (uint32_t)s * 2 * b_half16;
+                    const uint32_t b_lo = b_hi + b_half16;
                     for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil) * 16;
-                        const uint32_t d_tmem = tmem + (uint32_t)(mt * N);
+                        const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil);
+                        const uint32_t d_tmem = tmem_u + (uint32_t)(mt * N);
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
                             const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
                             const uint32_t bb = (pass == 1 ? b_lo : b_hi);
 #pragma unroll
                             for (int ks = 0; ks < KSTEPS; ++ks) {
-                                uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
-                                uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
                                 uint32_t accum = (c | tap | pass | ks) != 0;
-                                umma<BF16>(d_tmem, ad, bd, idesc, accum);
+                                umma<BF16>(d_tmem, desc_u(aa + ks * 2 * a_lbo16, a_lbo16), desc_u(bb + ks * 2 * b_lbo16, b_lbo16), idesc, accum);
                             }
                         }
                     }
@@ -548,29 +573,28 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
             }
             umma_commit(&sm->acc_full);
             if (FUSED) {
-                const uint32_t a2_lbo = (uint32_t)p.R2pad * 16;
+                const uint32_t a2_lbo16 = (uint32_t)p.R2pad, a2_half16 = a2_half >> 4;
+                const uint32_t a2_base16 = __shfl_sync(0xffffffffu, smem_u32(a2_base), 0) >> 4;
                 for (int c2 = 0; c2 < p.nchunk2; ++c2, ++it) {
                     mbar_wait(&sm->a2_full[c2], 0);
                     const int s = it % S;
                     mbar_wait(&sm->b_full[s], (it / S) & 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(a2_base + (size_t)c2 * 2 * a2_half);
-                    const uint32_t a_lo = a_hi + a2_half;
-                    const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
-                    const uint32_t b_lo = b_hi + b_half;
+                    const uint32_t a_hi = a2_base16 + (uint32_t)c2 * 2 * a2_half16;
+                    const uint32_t a_lo = a_hi + a2_half16;
+                    const uint32_t b_hi = b_base16 + (uint32_t)s * 2 * b_half16;
+                    const uint32_t b_lo = b_hi + b_half16;
                     for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t row_off = (uint32_t)(mt * 128) * 16;
-                        const uint32_t d_tmem = tmem + (uint32_t)(MT * N + mt * N);
+                        const uint32_t row_off = (uint32_t)(mt * 128);
+                        const uint32_t d_tmem = tmem_u + (uint32_t)(MT * N + mt * N);
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
                             const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
                             const uint32_t bb = (pass == 1 ? b_lo : b_hi);
 #pragma unroll
                             for (int ks = 0; ks < KSTEPS; ++ks) {
-                                uint64_t ad = smem_desc(aa + ks * 2 * a2_lbo, a2_lbo, 128);
-                                uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
                                 uint32_t accum = (c2 | pass | ks) != 0;
-                                umma<BF16>(d_tmem, ad, bd, idesc, accum);
+                                umma<BF16>(d_tmem, desc_u(aa + ks * 2 * a2_lbo16, a2_lbo16), desc_u(bb + ks * 2 * b_lbo16, b_lbo16), idesc, accum);
                             }
                         }
                     }
@@ -612,7 +636,7 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
         }
         // ================= epilogue =================
         if (probe) g_tc_phase_clock[1] = clock64();                 // all activation chunks produced
-        mbar_wait(&sm->acc_full, 0);
+        mbar_wait_relaxed(&sm->acc_full, 0);
         tc_fence_after();
         if (probe) g_tc_phase_clock[2] = clock64();                 // GEMM 1 retired
         const int q = warp & 3;                                     // TMEM lane quarter of this warp
@@ -644,11 +668,9 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
                         float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
                         float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
                         float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
-                        float4 x4;
-                        x4.x = snake_fast(__uint_as_float(v[pc * 4 + 0]) + bi.x, al.x, ia.x);
-                        x4.y = snake_fast(__uint_as_float(v[pc * 4 + 1]) + bi.y, al.y, ia.y);
-                        x4.z = snake_fast(__uint_as_float(v[pc * 4 + 2]) + bi.z, al.z, ia.z);
-                        x4.w = snake_fast(__uint_as_float(v[pc * 4 + 3]) + bi.w, al.w, ia.w);
+                        float4 x4 = make_float4(__uint_as_float(v[pc * 4 + 0]) + bi.x, __uint_as_float(v[pc * 4 + 1]) + bi.y,
+                                                __uint_as_float(v[pc * 4 + 2]) + bi.z, __uint_as_float(v[pc * 4 + 3]) + bi.w);
+                        x4 = snake4_sel<BF16>(x4, al, ia);
                         split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
                     }
                     fence_proxy_async();
@@ -678,11 +700,9 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
                         float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
                         float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
                         float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
-                        float4 x4;
-                        x4.x = snake_fast(__uint_as_float(v[pp * 4 + 0]) + bi.x, al.x, ia.x);
-                        x4.y = snake_fast(__uint_as_float(v[pp * 4 + 1]) + bi.y, al.y, ia.y);
-                        x4.z = snake_fast(__uint_as_float(v[pp * 4 + 2]) + bi.z, al.z, ia.z);
-                        x4.w = snake_fast(__uint_as_float(v[pp * 4 + 3]) + bi.w, al.w, ia.w);
+                        float4 x4 = make_float4(__uint_as_float(v[pp * 4 + 0]) + bi.x, __uint_as_float(v[pp * 4 + 1]) + bi.y,
+                                                __uint_as_float(v[pp * 4 + 2]) + bi.z, __uint_as_float(v[pp * 4 + 3]) + bi.w);
+                        x4 = snake4_sel<BF16>(x4, al, ia);
                         split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
                     }
                     fence_proxy_async();
@@ -696,7 +716,7 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
             }
             tc_fence_before();
             if (probe) g_tc_phase_clock[3] = clock64();             // GEMM-2 operand produced
-            mbar_wait(&sm->acc2_full, 0);
+            mbar_wait_relaxed(&sm->acc2_full, 0);
             tc_fence_after();
             if (probe) g_tc_phase_clock[4] = clock64();             // GEMM 2 retired
             d_base = tmem + (uint32_t)(MT * N);
@@ -722,7 +742,7 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-                    epilogue_tile32(p, ep_bias, ep_act, v, stage, lane, t0 + mt * 128 + q * 32, ntile * N + g * 32, yb, rb);
+                    epilogue_tile32<true, BF16>(p, ep_bias, ep_act, v, stage, lane, t0 + mt * 128 + q * 32, ntile * N + g * 32, yb, rb);
                 }
             }
             if (probe) g_tc_phase_clock[5] = clock64();
@@ -864,38 +884,48 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
     } else if (warp == 1) {
         {   // whole warp converged; tcgen05 instructions are elect-predicated inside their asm blocks
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t a_lbo = (uint32_t)Rpad * 16, b_lbo = (uint32_t)N * 16;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint32_t a_base16 = __shfl_sync(0xffffffffu, smem_u32(a_base), 0) >> 4;
+            const uint32_t b_base16 = __shfl_sync(0xffffffffu, smem_u32(b_base), 0) >> 4;
+            const uint32_t a_lbo16 = (uint32_t)Rpad, b_lbo16 = (uint32_t)N;
+            const uint32_t a_half16 = a_half >> 4, b_half16 = b_half >> 4;
             int it = 0, cg = 0, gg = 0;
+            const bool mprobe = blockIdx.x == 3;
+            long long w_a = 0, w_b = 0, w_acc = 0, tq;
             for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
                 for (int g = 0; g < G; ++g, ++gg) {
                     const int abuf = gg & 1;
+                    if (mprobe) tq = clock64();
                     mbar_wait(&sm->acc_free[abuf], ((gg >> 1) & 1) ^ 1);
+                    if (mprobe) w_acc += clock64() - tq;
                     tc_fence_after();
                     const int c_begin = g * P, c_end = (c_begin + P < nchunk) ? c_begin + P : nchunk;
                     for (int c = c_begin; c < c_end; ++c, ++cg) {
                         const int buf = cg & 1;
+                        if (mprobe) tq = clock64();
                         mbar_wait(&sm->a_full[buf], (cg >> 1) & 1);
-                        const uint32_t a_hi = smem_u32(a_base + (size_t)buf * 2 * a_half);
-                        const uint32_t a_lo = a_hi + a_half;
+                        if (mprobe) w_a += clock64() - tq;
+                        const uint32_t a_hi = a_base16 + (uint32_t)buf * 2 * a_half16;
+                        const uint32_t a_lo = a_hi + a_half16;
                         for (int tap = 0; tap < Kr; ++tap, ++it) {
                             const int s = it % S;
+                            if (mprobe) tq = clock64();
                             mbar_wait(&sm->b_full[s], (it / S) & 1);
+                            if (mprobe) w_b += clock64() - tq;
                             tc_fence_after();
-                            const uint32_t b_hi = smem_u32(b_base + (size_t)s * 2 * b_half);
-                            const uint32_t b_lo = b_hi + b_half;
+                            const uint32_t b_hi = b_base16 + (uint32_t)s * 2 * b_half16;
+                            const uint32_t b_lo = b_hi + b_half16;
                             for (int mt = 0; mt < MT; ++mt) {
-                                const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil) * 16;
-                                const uint32_t d_tmem = tmem + (uint32_t)(abuf * 256 + mt * N);
+                                const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil);
+                                const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * 256 + mt * N);
 #pragma unroll
                                 for (int pass = 0; pass < 3; ++pass) {
                                     const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
                                     const uint32_t bb = (pass == 1 ? b_lo : b_hi);
 #pragma unroll
                                     for (int ks = 0; ks < kChunk / 8; ++ks) {
-                                        uint64_t ad = smem_desc(aa + ks * 2 * a_lbo, a_lbo, 128);
-                                        uint64_t bd = smem_desc(bb + ks * 2 * b_lbo, b_lbo, 128);
                                         uint32_t accum = ((c - c_begin) | tap | pass | ks) != 0;
-                                        umma_tf32(d_tmem, ad, bd, idesc, accum);
+                                        umma_tf32(d_tmem, desc_u(aa + ks * 2 * a_lbo16, a_lbo16), desc_u(bb + ks * 2 * b_lbo16, b_lbo16), idesc, accum);
                                     }
                                 }
                             }
@@ -906,13 +936,15 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                     umma_commit(&sm->acc_ready[abuf]);
                 }
             }
+            if (mprobe && lane == 0) { g_tc_phase_clock[2] = w_a; g_tc_phase_clock[3] = w_b; g_tc_phase_clock[4] = w_acc; }
         }
     } else if (warp >= 4 && warp < 12) {
         // ================= activation producers (warps 4..11, 64 registers each) =================
         reg_dec<64>();
         const int wtid = tid - 128;                                 // 0..255
         const bool probe = (wtid == 0 && blockIdx.x == 3);
-        if (probe) g_tc_phase_clock[0] = clock64();
+        const long long t_start = probe ? clock64() : 0;
+        long long w_ae = 0, tq = 0;
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
         int cg = 0;
         for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
@@ -922,13 +954,15 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
             for (int c = 0; c < nchunk; ++c, ++cg) {
                 const int buf = cg & 1;
                 uint8_t* ahi = a_base + (size_t)buf * 2 * a_half;
+                if (probe) tq = clock64();
                 mbar_wait(&sm->a_empty[buf], ((cg >> 1) & 1) ^ 1);
+                if (probe) w_ae += clock64() - tq;
                 produce_chunk<256, false, 4, true>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
                 fence_proxy_async();
                 mbar_arrive(&sm->a_full[buf]);
             }
-            if (probe && L == blockIdx.x) g_tc_phase_clock[1] = clock64();   // first tile: all chunks produced
         }
+        if (probe) { g_tc_phase_clock[0] = clock64() - t_start; g_tc_phase_clock[1] = w_ae; g_tc_phase_clock[7] = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x; }
     } else if (warp >= 12) {
         // ================= accumulators (warps 12..19, 160 registers each): promote + epilogue =================
         reg_inc<160>();
@@ -943,6 +977,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
         const int act = p.out_act;
         const bool aprobe = (tid == 12 * 32 && blockIdx.x == 3);
         int gg = 0;
+        long long w_ar = 0, t_ep = 0, tq = 0;
         for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
             const int t0 = (L % gx) * 128 * MT;
             const int ntile = (L / gx) % gy;
@@ -952,7 +987,9 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
             for (int i = 0; i < 128; ++i) acc[i] = 0.f;
             for (int g = 0; g < G; ++g, ++gg) {
                 const int abuf = gg & 1;
-                mbar_wait(&sm->acc_ready[abuf], (gg >> 1) & 1);
+                if (aprobe) tq = clock64();
+                mbar_wait_relaxed(&sm->acc_ready[abuf], (gg >> 1) & 1);
+                if (aprobe) w_ar += clock64() - tq;
                 tc_fence_after();
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + mycol0);
 #pragma unroll
@@ -974,7 +1011,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
             // out of the instruction cache); only the register -> stage copy is selected by a switch.
             float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
             const float* __restrict__ rb = p.res ? p.res + (size_t)b * p.y_bstride : nullptr;
-            if (aprobe && L == blockIdx.x) g_tc_phase_clock[2] = clock64();   // first tile: last promotion done
+            if (aprobe) tq = clock64();
 #pragma unroll 1
             for (int sl = 0; sl * 32 < mycols; ++sl) {
 #define FAC_PARK(S0)                                                                                              \
@@ -1009,8 +1046,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                         float4 o = *reinterpret_cast<const float4*>(stage + row * 36 + c4 * 4);
                         o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
                         if (act == ACT_SNAKE) {
-                            o.x = snake_fast<true>(o.x, al.x, ia.x); o.y = snake_fast<true>(o.y, al.y, ia.y);
-                            o.z = snake_fast<true>(o.z, al.z, ia.z); o.w = snake_fast<true>(o.w, al.w, ia.w);
+                            o = snake4<true>(o, al, ia);
                         } else if (act == ACT_TANH) {
                             o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
                         } else if (act == ACT_MISH) {
@@ -1025,8 +1061,9 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                 }
                 __syncwarp();
             }
-            if (aprobe && L == blockIdx.x) g_tc_phase_clock[5] = clock64();   // first tile: epilogue done
+            if (aprobe) t_ep += clock64() - tq;
         }
+        if (aprobe) { g_tc_phase_clock[5] = w_ar; g_tc_phase_clock[6] = t_ep; }
     }
     tc_fence_before();
     __syncthreads();

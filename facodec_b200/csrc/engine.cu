@@ -34,7 +34,7 @@ struct HostTensor {
 struct ConvW {
     size_t w = 0, b = 0; int Cin = 0, Cout = 0, K = 1, ldw = 0;
     // tensor-core blob (conv_tc.cu): present when the layer is eligible
-    bool tc = false; size_t tcw = 0; int vf = 1, Kr = 0;
+    bool tc = false; size_t tcw = 0; int vf = 1, Kr = 0, tcN = 0;   // tcN: channel tile the blob was laid out for
     bool promoted = false;   // blob built for conv_tcp_kernel (layers upstream of the VQ)
     bool has16 = false; size_t tcw16 = 0;   // bf16 hi/lo blob (non-promoted layers only)
 };
@@ -146,7 +146,7 @@ void attach_tc(fac_handle* h, ConvW& c, int stride, bool promoted) {
     else if (c.K == 2 * stride) { tp.vf = stride; tp.Kr = 2; }
     else return;
     if (!tc_conv_plan(tp)) return;
-    c.vf = tp.vf; c.Kr = tp.Kr; c.promoted = promoted;
+    c.vf = tp.vf; c.Kr = tp.Kr; c.promoted = promoted; c.tcN = tp.N;
     size_t n = tc_blob_floats(tp);
     c.tcw = pack_alloc(h, n);
     tc_pack_blob(tp, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw);
@@ -501,6 +501,15 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
         (o.ldy == 0 || o.ldy == w.Cout) && o.stride == w.vf && (w.vf == 1 || o.dil == 1) && !o.no_bias) {
         TcConvParams tp;
         tp.Cin = w.Cin; tp.Cout = w.Cout; tp.vf = w.vf; tp.Kr = w.Kr; tp.promoted = w.promoted ? 1 : 0;
+        // A layer whose whole K loop is at most one promotion window (<= 48 chained MMAs: the 1x1 convs of the 64- and
+        // 128-channel encoder stages) gains nothing from register promotion: same error class through conv_tc_kernel,
+        // which runs two CTAs per SM and prefetches the residual.
+        bool short_chain = false;
+        if (w.promoted && (w.Cin * w.vf / 16) * w.Kr * 6 <= 48) {
+            TcConvParams probe = tp;
+            probe.promoted = 0; probe.occ2_maxn = c.h->tc_occ2;
+            if (tc_conv_plan(probe) && probe.N == w.tcN) { tp.promoted = 0; short_chain = true; }
+        }
         tp.dil = w.vf == 1 ? o.dil : 1;
         tp.bf16 = (c.h->dec_bf16 && w.has16 && !c.vq_critical) ? 1 : 0;
         tp.occ2_maxn = c.h->tc_occ2;
@@ -519,7 +528,8 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
             double bytes = 4.0 * ((double)B * Tin * w.Cin + (double)B * Tout * w.Cout * (o.res ? 2 : 1) + (double)w.K * w.Cin * w.Cout);
             char det[96];
             snprintf(det, sizeof det, "%s Cin%d Cout%d K%d d%d T%d", name, w.Cin, w.Cout, w.K, o.dil, Tout);
-            c.begin(w.promoted ? "conv_tcp" : "conv_tc", flops, bytes, det);
+            c.begin(tp.promoted ? "conv_tcp" : "conv_tc", flops, bytes, det);
+            (void)short_chain;
             c.check(launch_conv_tc(tp, c.st), name);
             c.end();
             return;
