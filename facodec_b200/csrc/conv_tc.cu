@@ -62,8 +62,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // MMA warp and the producers) poll try_wait back to back.  Warps that wait for a long time for something that is not
 // latency critical (accumulator / epilogue warps waiting for a whole GEMM group) pass a suspend-time hint, which parks
 // the thread in hardware: polled, those ~8 warps took a measurable share of the issue slots (ncu: ~60k warp-instructions
-// of spinning per 512-row tile next to 160k of useful work) -- but a parked thread wakes up later, which costs more than
-// it saves on the critical hand-offs (measured).
+// of spinning per 512-row tile next to 160k of useful work) -- but a parked thread seems to wake at the END of the hint
+// rather than when the phase completes (a 4 us hint made every group hand-off ~8k cycles late: +30 % on layers with
+// short groups), so the hint is kept short (0.4 us) and never used on the critical hand-offs.
 template <bool RELAXED>
 __device__ __forceinline__ bool mbar_try_wait_t(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -73,7 +74,7 @@ __device__ __forceinline__ bool mbar_try_wait_t(uint64_t* bar, uint32_t parity) 
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(400u)
             : "memory");
     } else {
         asm volatile(
@@ -809,6 +810,12 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
 // a CTA, serially).
 // ================================================================================================
 namespace tc {
+// role wait-time probes of conv_tcp_kernel (fac_debug_tc_phase_clocks): compile with -DFAC_TCP_PROBE=1 to measure; the
+// counters cost registers in the 32-register MMA warp and the 160-register accumulators (spills: +20 % on conv7 layers)
+#ifndef FAC_TCP_PROBE
+#define FAC_TCP_PROBE 0
+#endif
+constexpr bool kTcpProbe = FAC_TCP_PROBE != 0;
 constexpr int kThreadsP = 640;     // warps 0-3: control (weights, MMA, 2 idle); 4-11: producers; 12-19: accumulators
 template <int R>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
@@ -890,7 +897,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
             const uint32_t a_lbo16 = (uint32_t)Rpad, b_lbo16 = (uint32_t)N;
             const uint32_t a_half16 = a_half >> 4, b_half16 = b_half >> 4;
             int it = 0, cg = 0, gg = 0;
-            const bool mprobe = blockIdx.x == 3;
+            const bool mprobe = kTcpProbe && blockIdx.x == 3;
             long long w_a = 0, w_b = 0, w_acc = 0, tq;
             for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
                 for (int g = 0; g < G; ++g, ++gg) {
@@ -942,7 +949,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
         // ================= activation producers (warps 4..11, 64 registers each) =================
         reg_dec<64>();
         const int wtid = tid - 128;                                 // 0..255
-        const bool probe = (wtid == 0 && blockIdx.x == 3);
+        const bool probe = kTcpProbe && (wtid == 0 && blockIdx.x == 3);
         const long long t_start = probe ? clock64() : 0;
         long long w_ae = 0, tq = 0;
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
@@ -975,7 +982,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
         float* stage = stage_base + (size_t)(warp - 12) * (32 * 36);
         const int c4 = lane & 7, rsub = lane >> 3;
         const int act = p.out_act;
-        const bool aprobe = (tid == 12 * 32 && blockIdx.x == 3);
+        const bool aprobe = kTcpProbe && (tid == 12 * 32 && blockIdx.x == 3);
         int gg = 0;
         long long w_ar = 0, t_ep = 0, tq = 0;
         for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
@@ -988,7 +995,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
             for (int g = 0; g < G; ++g, ++gg) {
                 const int abuf = gg & 1;
                 if (aprobe) tq = clock64();
-                mbar_wait_relaxed(&sm->acc_ready[abuf], (gg >> 1) & 1);
+                mbar_wait(&sm->acc_ready[abuf], (gg >> 1) & 1);   // on the critical path (2 TMEM buffers): polled, not parked
                 if (aprobe) w_ar += clock64() - tq;
                 tc_fence_after();
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + mycol0);

@@ -3,6 +3,9 @@ import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import facodec_b200.build as _b
+if os.environ.get('FAC_LIB_VARIANT'):
+    _b.LIB = os.path.join(ROOT, 'facodec_b200', '_C', os.environ['FAC_LIB_VARIANT'])
 import facodec_b200 as fb
 from facodec_b200 import synth
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 2
