@@ -9,8 +9,10 @@ is BASELINE configs[1]: 32 utterances per GPU (weak scaling: every rank gets its
 Prints ONE JSON line on rank 0 (contract in the task statement):
   value      = audio-seconds per second, whole job, inputs resident in HBM (CUDA events, max over ranks)
   e2e        = same metric through Codec.forward_host: pinned HOST buffers, H2D + D2H inside the timed region
-  roofline   = dominant kernel family (conv_cl_kernel): algorithmic FLOPs / device time, from CUDA events
-               recorded around every launch in a separate instrumented pass (fac_profile_*)
+  roofline   = dominant kernel family (the two tcgen05 conv kernels conv_tc_kernel + conv_tcp_kernel, ~80 % of a step):
+               algorithmic FLOPs / device time, from CUDA events recorded around every launch in a separate
+               instrumented pass (fac_profile_*); traffic = DRAM bytes per launch of that family from the committed
+               ncu launch list (profiles/roofline_r01.json)
   cpu_baseline = the oracle port (oracle/facodec_oracle.py = the reference's own ATen call sequence)
                timed on this box's host cores on a bounded sample
 --impl reference times that CPU path alone (the reference is 100% Python/PyTorch; /root/reference is
@@ -248,14 +250,25 @@ def main():
     # dominant kernels: the two tcgen05 conv kernels (same mainloop; conv_tcp adds register promotion)
     conv = {k: fam["conv_tc"][k] + fam["conv_tcp"][k] for k in ("ms", "flops", "bytes", "launches")}
     conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
-    roofline = {"kernel": "conv_tc_kernel + conv_tcp_kernel (tcgen05.mma kind::tf32, 3xTF32 split; all eligible "
-                          "Conv1d/ConvTranspose1d/Linear layers)",
+    traffic, traffic_src = None, None
+    try:
+        rj = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))
+        traffic = rj["conv_family"]["dram_bytes_per_launch"]
+        traffic_src = rj["conv_family"]["source"]
+    except Exception:
+        pass
+    pipe_ops = 3.0 * fam["conv_tc"]["flops"] + 6.0 * fam["conv_tcp"]["flops"]      # bf16-equivalent tensor work issued
+    roofline = {"kernel": "conv_tc_kernel (tcgen05.mma kind::f16, bf16 hi/lo split, layers downstream of the VQ) + "
+                          "conv_tcp_kernel (kind::tf32, 3xTF32 split with register-promoted accumulation, upstream): all "
+                          "eligible Conv1d/ConvTranspose1d/Linear layers",
                 "bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": conv_tflops / peaks["tflops"], "traffic": None,
+                "frac": conv_tflops / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": f"{peaks['source']} bf16 dense sustained (MEASURED_PEAKS.json)",
-                "note": "achieved counts ALGORITHMIC fp32 FLOPs (2*MACs); the kernel issues 3 TF32 MMAs per product and "
-                        "TF32 runs at half the bf16 rate, so tensor-pipe occupancy is ~6x this fraction",
-                "tensor_pipe_frac_est": 6.0 * conv_tflops / peaks["tflops"],
+                "note": "achieved counts ALGORITHMIC fp32 FLOPs (2*MACs) per launch / mean launch time; an fp32-faithful "
+                        "product costs 3 MMAs (bf16 split) or 3 MMAs at half rate (TF32 split), so the tensor pipe does 3-6x "
+                        "this work; traffic is DRAM read+write bytes per launch (ncu), to compare with "
+                        "per_launch.algorithmic_gb_per_step / launches_per_step",
+                "tensor_pipe_frac_est": pipe_ops / (conv["ms"] * 1e-3) / 1e12 / peaks["tflops"] if conv["ms"] > 0 else 0.0,
                 "per_launch": {"launches_per_step": conv["launches"], "avg_ms": conv["ms"] / max(1, conv["launches"]),
                                "algorithmic_gflop_per_step": conv["flops"] / 1e9,
                                "algorithmic_gb_per_step": conv["bytes"] / 1e9,

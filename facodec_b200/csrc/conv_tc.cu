@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
 // REGISTER accumulators with round-to-nearest (128 registers per thread hold the 128 x 256 tile),
 // while the MMA warp already fills the other TMEM buffer.
 // Warp-specialised with register re-allocation (setmaxnreg): 20 warps launch with 96 registers each;
-// the 4 control warps drop to 32, the 8 activation-producer warps to 64, and the 8 accumulator warps
+// the 4 control warps drop to 48, the 8 activation-producer warps to 56, and the 8 accumulator warps
 // grow to 160, so producing, MMA issue and promotion/epilogue all overlap instead of taking turns on
 // the same warps (measured before the split: produce 39 %, wait 19 %, promote 5 %, epilogue 36 % of
 // a CTA, serially).
@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
 
-    if (warp < 4) reg_dec<32>();      // whole control warpgroup at one program point (4*32*32 + 8*32*64 + 8*32*160 == 640*96)
+    if (warp < 4) reg_dec<48>();      // whole control warpgroup at one program point (4*32*48 + 8*32*56 + 8*32*160 == 640*96)
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
@@ -946,8 +946,8 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
             if (mprobe && lane == 0) { g_tc_phase_clock[2] = w_a; g_tc_phase_clock[3] = w_b; g_tc_phase_clock[4] = w_acc; }
         }
     } else if (warp >= 4 && warp < 12) {
-        // ================= activation producers (warps 4..11, 64 registers each) =================
-        reg_dec<64>();
+        // ================= activation producers (warps 4..11, 56 registers each) =================
+        reg_dec<56>();
         const int wtid = tid - 128;                                 // 0..255
         const bool probe = kTcpProbe && (wtid == 0 && blockIdx.x == 3);
         const long long t_start = probe ? clock64() : 0;

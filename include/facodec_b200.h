@@ -110,10 +110,14 @@ int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int a
  * (encoder, prosody branch); 2 (default) = tcgen05 everywhere, with the register-promoted accumulation
  * variant upstream of the VQ where the bit-exact argmin needs fp32-grade sums.
  * "fuse_resunit": 1 (default) runs each decoder ResidualUnit whose channels fit one CTA tile as a single
- * fused launch (conv7 -> Snake -> 1x1 conv -> +x with the intermediate kept in TMEM/SMEM); 0 = two launches.
+ * fused launch (conv7 -> Snake -> 1x1 conv -> +x with the intermediate kept in TMEM/SMEM); 0 = two launches;
+ * 2 = fuse only units of at most 128 channels (the ones whose fused tile still allows two CTAs per SM).
  * "decoder_bf16": 1 (default) = layers downstream of the VQ split operands into bf16 hi + bf16 lo
  * (tcgen05.mma.kind::f16, K = 16: half the MMAs and half the operand bytes of the TF32 split; waveform error
- * ~1e-5 RMS against the 1e-4 bar); 0 = TF32 hi/lo everywhere.  Never applied upstream of the VQ. */
+ * ~1e-5 RMS against the 1e-4 bar), evaluate Snake with the SFU sine and run the LSTM recurrence on bf16 hi/lo
+ * mma.sync tiles; 0 = TF32 hi/lo everywhere.  Never applied upstream of the VQ.
+ * "tc_occ2_maxn": channel tiles of at most this width (default 256; 0 = off) are planned for TWO resident CTAs per
+ * SM (<= 256 TMEM columns, <= 112 KB shared memory each) so one CTA's MMAs overlap the other's produce/epilogue. */
 int fac_set_option(fac_handle* h, const char* name, int value);
 
 /* Kernel-level test hooks (used by tests/test_gpu_kernels.py; not part of the drop-in surface).

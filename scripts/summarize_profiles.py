@@ -8,15 +8,30 @@ out = ["# ncu summary, round 1 (B200, `--clock-control none`)\n",
        "`launches_r01.csv` (`--metrics gpu__time_duration.sum`, one full B=32 x 4 s forward = 114 launches).\n",
        "Captures taken from `scripts/ncu_target.py` (second forward). Numbers under ncu are cold-cache and serialised: "
        "use SHARES, not absolutes; bench numbers come from `bench.py` only.\n"]
-rows = [r for r in csv.reader(open(os.path.join(D, "launches_r01.csv"))) if len(r) > 5 and r[0].isdigit()]
+# launch list: ncu --csv "long" format, one row per (launch, metric)
+allrows = list(csv.reader(open(os.path.join(D, "launches_r01.csv"))))
+hdr = next(r for r in allrows if "Kernel Name" in r)
+ix = {n: hdr.index(n) for n in ("ID", "Kernel Name", "Metric Name", "Metric Unit", "Metric Value")}
+launch = collections.OrderedDict()
+for r in allrows:
+    if len(r) <= ix["Metric Value"] or not r[ix["ID"]].isdigit():
+        continue
+    L = launch.setdefault(int(r[ix["ID"]]), {"name": r[ix["Kernel Name"]].split("(")[0].replace("void ", "")})
+    v = float(r[ix["Metric Value"]].replace(",", ""))
+    u = r[ix["Metric Unit"]]
+    v *= {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1, "second": 1e3}.get(u, 1)
+    L[r[ix["Metric Name"]]] = v
 agg = collections.OrderedDict()
-for r in rows:
-    k = r[4].split("(")[0].replace("void ", "")
-    agg.setdefault(k, [0, 0.0]); agg[k][0] += 1; agg[k][1] += float(r[-1]) / 1e6
+for L in launch.values():
+    a = agg.setdefault(L["name"], [0, 0.0, 0.0])
+    a[0] += 1; a[1] += L.get("gpu__time_duration.sum", 0.0)
+    a[2] += L.get("dram__bytes_read.sum", 0.0) + L.get("dram__bytes_write.sum", 0.0)
 tot = sum(v[1] for v in agg.values())
-out.append(f"\n## Launch list (one forward, {len(rows)} launches, {tot:.1f} ms under ncu)\n\n| kernel | launches | ms | share |\n|---|---|---|---|")
+out.append(f"\n## Launch list (one forward, {len(launch)} launches, {tot:.1f} ms under ncu)\n\n| kernel | launches | ms | share | DRAM read+write GB |\n|---|---|---|---|---|")
 for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
-    out.append(f"| `{k}` | {v[0]} | {v[1]:.2f} | {100*v[1]/tot:.1f} % |")
+    out.append(f"| `{k}` | {v[0]} | {v[1]:.2f} | {100*v[1]/tot:.1f} % | {v[2]/1e9:.2f} |")
+convk = [k for k in agg if k.startswith("fac::conv_tc_kernel") or k.startswith("fac::conv_tcp_kernel") or k.startswith("conv_tc")]
+cl = sum(agg[k][0] for k in convk); cb = sum(agg[k][2] for k in convk); cms = sum(agg[k][1] for k in convk)
 out.append("\n## Full captures\n\n| capture | kernel / layer | grid | time ms | DRAM read+write (traffic) | DRAM % | tensor pipe active % | L1TEX % | L2 % | regs | issue-active % |\n|---|---|---|---|---|---|---|---|---|---|---|")
 desc = {"tc_bf16_convtr192to96": "conv_tc_kernel<0,bf16>: decoder ConvTranspose 192->96 (x2), T 48000->96000 (launch 109)",
         "tc_bf16_c384k1": "conv_tc_kernel<0,bf16>: decoder ResidualUnit 1x1 conv C=384, T=9600 (launch 100)",
@@ -61,5 +76,9 @@ out.append("""
   loop around every UTCHMMA issued from a divergent region (+75 cycles per MMA) -> converged warp + elect.sync.
 """)
 open(os.path.join(ROOT, "profiles", "SUMMARY_r01.md"), "w").write("\n".join(out) + "\n")
+roof["conv_family"] = {"launches_per_forward": cl, "dram_bytes_per_forward": cb, "dram_bytes_per_launch": cb / max(1, cl),
+                       "ms_under_ncu": cms, "share_of_forward_under_ncu": cms / tot if tot else None,
+                       "source": "profiles/r01/launches_r01.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
+                                 "dram__bytes_write.sum --clock-control none, second forward of scripts/ncu_target.py)"}
 json.dump(roof, open(os.path.join(ROOT, "profiles", "roofline_r01.json"), "w"), indent=1)
 print("\n".join(out[-14:]))
