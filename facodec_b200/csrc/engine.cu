@@ -23,6 +23,7 @@ constexpr int N_FFT = 2048;
 constexpr int WIN = 1200;
 constexpr int N_BINS = 1025;
 constexpr int SPEC_LD = 2052;   // 2*1025 rounded up to a multiple of 4
+constexpr int SPEC_TC_LD = 2176; // ... and to 17 channel tiles of 128 for the tensor-core DFT
 constexpr int N_MELS = 80;
 
 struct HostTensor {
@@ -58,6 +59,7 @@ struct QuantW {
     ConvW spec0, spec3, glu[2], cq, ck, cv, co, fc, timbre_linear;
     ConvW mel_lin, wn_in[8], wn_rs[8], mel_lin2;
     ConvW dft; size_t fb = 0;
+    ConvW dft_tc;      // same basis as a K=1 GEMM over gathered frames: Cin = 1200, Cout padded to 2176 (17 x 128)
 };
 struct RvqSet { int nq; VqW vq[8]; };
 
@@ -410,6 +412,13 @@ void pack_quantizer(fac_handle* h) {
             h->pack[q.dft.w + (size_t)n * SPEC_LD + 2 * k] = (float)((double)win.data[n] * std::cos(ang));
             h->pack[q.dft.w + (size_t)n * SPEC_LD + 2 * k + 1] = (float)(-(double)win.data[n] * std::sin(ang));
         }
+    // tensor-core variant: [1200][2176] with zero columns beyond 2*1025, zero bias
+    q.dft_tc.Cin = WIN; q.dft_tc.Cout = SPEC_TC_LD; q.dft_tc.K = 1; q.dft_tc.ldw = SPEC_TC_LD;
+    q.dft_tc.w = pack_alloc(h, (size_t)WIN * SPEC_TC_LD);
+    for (int n = 0; n < WIN; ++n)
+        for (int k = 0; k < 2 * N_BINS; ++k) h->pack[q.dft_tc.w + (size_t)n * SPEC_TC_LD + k] = h->pack[q.dft.w + (size_t)n * SPEC_LD + k];
+    q.dft_tc.b = pack_alloc(h, SPEC_TC_LD);
+    attach_tc(h, q.dft_tc, 1, true);
     q.fb = pack_alloc(h, (size_t)N_BINS * N_MELS);
     for (size_t i = 0; i < (size_t)N_BINS * N_MELS; ++i) h->pack[q.fb + i] = fb.data[i];
 }
@@ -731,6 +740,17 @@ void decoder_forward(Ctx& c, const float* z, int B, int Tf, float* y) {
 // mel [B][Tm][80] from wave [B][T] (Tm = T/300), preprocess modules/quantize.py:239-242
 float* mel_forward(Ctx& c, const float* wave, int B, int T, int Tm) {
     const QuantW& q = c.h->qw;
+    if (c.h->use_tc >= 2 && q.dft_tc.tc) {
+        // frames gather + K=1 GEMM on the promoted tcgen05 kernel (the mel feeds the prosody VQ: fp32-grade sums)
+        float* frames = c.alloc<float>((size_t)B * Tm * WIN);
+        float* spec = c.alloc<float>((size_t)B * Tm * SPEC_TC_LD);
+        float* mel = c.alloc<float>((size_t)B * Tm * N_MELS);
+        if (!c.dry) c.check(launch_stft_frames(wave, frames, B, T, Tm, HOP, WIN, N_FFT / 2 - (N_FFT - WIN) / 2, c.st), "mel.frames");
+        run_conv(c, q.dft_tc, frames, spec, 1, B * Tm, B * Tm, ConvOpts(), "mel.dft");
+        if (!c.dry) c.check(launch_mel_from_spec(spec, SPEC_TC_LD, c.W(q.fb), mel, B, Tm, Tm, c.st), "mel.fb");
+        c.tap("mel80", mel, (size_t)B * Tm * N_MELS);
+        return mel;
+    }
     float* spec = c.alloc<float>((size_t)B * Tm * SPEC_LD);
     float* mel = c.alloc<float>((size_t)B * Tm * N_MELS);
     ConvOpts o;

@@ -44,6 +44,26 @@ __global__ void __launch_bounds__(128) mel_from_spec_kernel(const float* __restr
     }
 }
 
+// Frame gather for the tensor-core DFT: frames[b][f][j] = wave[b][reflect(f*hop - pad + j)], j < win.  The hop (300) is
+// not a multiple of the 16-channel chunk of the tcgen05 conv, so the strided "conv" view of the STFT cannot feed it
+// directly; the explicit [B*F][1200] matrix (49 MB at B=32) can, as a plain K=1 GEMM against the folded basis.
+__global__ void __launch_bounds__(256) stft_frames_kernel(const float* __restrict__ wave, float* __restrict__ frames, int T,
+                                                          int F, int hop, int win, int pad) {
+    const int b = blockIdx.y, f = blockIdx.x;
+    const PadMap pm = PadMap::make(T, pad, pad, 1);
+    const float* w = wave + (size_t)b * T;
+    float* o = frames + ((size_t)b * F + f) * win;
+    for (int j = threadIdx.x; j < win; j += blockDim.x) {
+        const int src = pm.src(f * hop - pad + j);
+        o[j] = src >= 0 ? __ldg(w + src) : 0.f;
+    }
+}
+cudaError_t launch_stft_frames(const float* wave, float* frames, int B, int T, int F, int hop, int win, int pad, cudaStream_t st) {
+    if (B <= 0 || F <= 0) return cudaSuccess;
+    stft_frames_kernel<<<dim3(F, B), 256, 0, st>>>(wave, frames, T, F, hop, win, pad);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mel_from_spec(const float* spec, int ldspec, const float* fb, float* mel, int B, int F, int Tm,
                                  cudaStream_t st) {
     if (B <= 0 || Tm <= 0) return cudaSuccess;

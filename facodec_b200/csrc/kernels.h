@@ -83,6 +83,8 @@ cudaError_t lstm_read_phase_clocks(long long* out4);   // CTA-0 accumulated phas
 
 // ---- mel front-end (frontend.cu) -----------------------------------------------------------
 // spec [B][F][ldspec] (re at 2*bin, im at 2*bin+1) -> mel [B][Tm][80] = (log(1e-5 + |.|^2 fb)+4)/4
+cudaError_t launch_stft_frames(const float* wave, float* frames /*[B][F][win]*/, int B, int T, int F, int hop, int win, int pad,
+                               cudaStream_t st);
 cudaError_t launch_mel_from_spec(const float* spec, int ldspec, const float* fb /*[1025][80]*/, float* mel,
                                  int B, int F, int Tm, cudaStream_t st);
 
