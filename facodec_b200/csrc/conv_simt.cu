@@ -300,8 +300,59 @@ __global__ void __launch_bounds__(256) conv_cout1_kernel(ConvParams p) {
     }
 }
 
+// ---- Cin == 1 (encoder's first conv, dac.py:79: SConv1d(1 -> 64, k=7)) ------------------------------
+// K FMAs per output and a 4*Cout-byte row to write per input sample: purely HBM-write-bound (786 MB at B=32).
+// CTA = C1I_T consecutive samples; thread (r, c4) keeps the K weights of its 4 channels in registers and walks the
+// tile's rows r, r + 256/(Cout/4), ...: the Cout/4 threads of a row write it as one contiguous segment.
+constexpr int C1I_T = 256;
+constexpr int C1I_MAXK = 16;
+__global__ void __launch_bounds__(256) conv_cin1_kernel(ConvParams p) {
+    __shared__ float xs[C1I_T + C1I_MAXK * 16];
+    const int halo = (p.K - 1) * p.dil;
+    const int b = blockIdx.y, t0 = blockIdx.x * C1I_T;
+    const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
+    const PadMap pm = PadMap::make(p.Tin, p.pad_left, p.pad_right, p.pad_reflect);
+    for (int i = threadIdx.x; i < C1I_T + halo; i += 256) {
+        const int src = pm.src(t0 + i - p.pad_left);
+        float v = src >= 0 ? __ldg(xb + (size_t)src * p.ldx) : 0.f;
+        if (p.in_alpha) v = snake_fast(v, p.in_alpha[0], p.in_inv_alpha[0]);
+        xs[i] = v;
+    }
+    const int c4n = p.Cout / 4, rows_per_pass = 256 / c4n;
+    const int c4 = threadIdx.x % c4n, r0 = threadIdx.x / c4n;
+    float4 w[C1I_MAXK];
+#pragma unroll
+    for (int k = 0; k < C1I_MAXK; ++k)
+        w[k] = k < p.K ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * p.ldw + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bi = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (r0 >= rows_per_pass) return;
+    float* __restrict__ yb = p.y + (size_t)b * p.y_bstride;
+    for (int r = r0; r < C1I_T; r += rows_per_pass) {
+        const int t = t0 + r;
+        if (t >= p.Tout) break;
+        float4 a = bi;
+#pragma unroll
+        for (int k = 0; k < C1I_MAXK; ++k)
+            if (k < p.K) {
+                const float xv = xs[r + k * p.dil];
+                a.x = fmaf(xv, w[k].x, a.x); a.y = fmaf(xv, w[k].y, a.y);
+                a.z = fmaf(xv, w[k].z, a.z); a.w = fmaf(xv, w[k].w, a.w);
+            }
+        if (p.out_act == ACT_TANH) { a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w); }
+        *reinterpret_cast<float4*>(yb + (size_t)t * p.ldy + c4 * 4) = a;
+    }
+}
+
 cudaError_t launch_conv(const ConvParams& p, cudaStream_t st) {
     if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
+    if (p.Cin == 1 && p.stride == 1 && p.K <= C1I_MAXK && (p.K - 1) * p.dil <= C1I_MAXK * 16 && (p.Cout % 4) == 0 &&
+        p.Cout <= 1024 && (256 % (p.Cout / 4)) == 0 && (p.ldw % 4) == 0 && (p.ldy % 4) == 0 && !p.res && !p.valid_len &&
+        !p.y_transposed && (p.out_act == ACT_NONE || p.out_act == ACT_TANH)) {
+        dim3 grid((p.Tout + C1I_T - 1) / C1I_T, p.B);
+        conv_cin1_kernel<<<grid, 256, 0, st>>>(p);
+        return cudaGetLastError();
+    }
     if (p.Cout == 1 && p.stride == 1 && (p.Cin % 4) == 0 && !p.res && !p.valid_len && !p.y_transposed &&
         (p.out_act == ACT_NONE || p.out_act == ACT_TANH)) {
         size_t smem = sizeof(float) * ((size_t)(C1_TILE + (p.K - 1) * p.dil) * c1_pitch(p.Cin) + (size_t)p.K * p.Cin + C1_TILE);

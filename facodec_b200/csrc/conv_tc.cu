@@ -1091,8 +1091,16 @@ bool tc_conv_plan(TcConvParams& p) {
     if (p.fused && (N != p.Cout || p.Cin != p.Cout || p.vf != 1 || N > 256)) return false;
     p.nchunk = p.Cin * p.vf / tc::kChunk;
     p.nchunk2 = p.fused ? p.Cout / tc::kChunk : 0;
+    // rows the tile grid actually covers for a given MT: short sequences (T' = 320 stages) waste up to 37 % of the MMAs in
+    // the padded tail of a 256-row tile, so MT is halved while that saves more than 10 % (only when the caller set Tout)
+    auto padded_rows = [&](int mt) { const long long tile = 128LL * mt; return (p.Tout + tile - 1) / tile * tile; };
+    auto trim_mt = [&](int mt) {
+        if (p.Tout > 0)
+            while (mt > 1 && padded_rows(mt) * 10 > padded_rows(mt / 2) * 11) mt >>= 1;
+        return mt;
+    };
     if (p.promoted) {
-        p.MT = (N <= 64) ? 4 : 2;              // MT * N <= 256 columns per TMEM buffer
+        p.MT = trim_mt((N <= 64) ? 4 : 2);     // MT * N <= 256 columns per TMEM buffer
         p.promote_every = 8 / p.Kr < 1 ? 1 : 8 / p.Kr;
         int R = 128 * p.MT + (p.Kr - 1) * p.dil, Rpad = R;
         while (Rpad % 8 != 2) ++Rpad;
@@ -1117,6 +1125,7 @@ bool tc_conv_plan(TcConvParams& p) {
         int MT = colcap / per;
         MT = MT >= 4 ? 4 : (MT >= 2 ? 2 : MT);
         if (p.fused && MT > 2) MT = 2;
+        if (MT >= 1) MT = trim_mt(MT);
         for (; MT >= 1; MT >>= 1) {
             int R = 128 * MT + (p.Kr - 1) * p.dil, Rpad = R;
             while (Rpad % 8 != 2) ++Rpad;

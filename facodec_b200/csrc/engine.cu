@@ -522,6 +522,7 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
         tp.dil = w.vf == 1 ? o.dil : 1;
         tp.bf16 = (c.h->dec_bf16 && w.has16 && !c.vq_critical) ? 1 : 0;
         tp.occ2_maxn = c.h->tc_occ2;
+        tp.Tout = Tout;
         if (tc_conv_plan(tp)) {
             tp.x = x; tp.y = y; tp.wblob = c.W(tp.bf16 ? w.tcw16 : w.tcw); tp.bias = c.W(w.b);
             if (o.in_snake) { tp.in_alpha = c.W(o.in_snake->a); tp.in_inv_alpha = c.W(o.in_snake->ia); }
@@ -591,6 +592,7 @@ bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B,
     tp.Cin = r.c7.Cin; tp.Cout = r.c7.Cout; tp.vf = 1; tp.Kr = r.c7.K; tp.dil = r.dil; tp.fused = 1;
     tp.bf16 = (c.h->dec_bf16 && r.c7.has16 && r.c1.has16) ? 1 : 0;
     tp.occ2_maxn = c.h->tc_occ2;
+    tp.Tout = T;
     if (c.h->fuse_res == 2 && r.c7.Cout > 128) return false;
     if (!tc_conv_plan(tp)) return false;
     if (c.dry) return true;
@@ -1279,6 +1281,7 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
     TcConvParams tp;
     tp.Cin = Cin; tp.Cout = Cout; tp.promoted = promoted == 1 ? 1 : 0; tp.bf16 = promoted == 2 ? 1 : 0;
     tp.occ2_maxn = h->tc_occ2;
+    tp.Tout = Tout;
     if (stride == 1) { tp.vf = 1; tp.Kr = K; tp.dil = dil; }
     else if (K == 2 * stride && dil == 1) { tp.vf = stride; tp.Kr = 2; tp.dil = 1; }
     else { h->err = "fac_debug_conv_tc: unsupported stride/kernel"; return FAC_ERR_UNSUPPORTED; }

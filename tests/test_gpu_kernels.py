@@ -44,7 +44,11 @@ def ref_conv(x, w, b, dil, stride, pl, pr, reflect, in_alpha, out_alpha, act, re
 
 CASES = [
     # B, T, Cin, Cout, K, dil, stride, pl, pr, reflect, in_snake, out_snake, act, res
-    (2, 300, 1, 64, 7, 1, 1, 6, 0, 1, 0, 0, 0, 0),        # encoder conv0
+    (2, 300, 1, 64, 7, 1, 1, 6, 0, 1, 0, 0, 0, 0),        # encoder conv0 (conv_cin1_kernel)
+    (1, 1031, 1, 64, 7, 1, 1, 6, 0, 1, 0, 0, 0, 0),       # ... several CTAs, ragged tail
+    (2, 5, 1, 64, 7, 1, 1, 6, 0, 1, 0, 0, 0, 0),          # ... short-input reflect branch (L <= pad)
+    (1, 600, 1, 32, 3, 2, 1, 4, 0, 0, 0, 0, 1, 0),        # ... dilated, zero pad, tanh, 32 channels
+    (2, 4000, 96, 1, 7, 1, 1, 6, 0, 1, 1, 0, 1, 0),       # final conv + tanh over several CTAs (conv_cout1_kernel)
     (2, 333, 64, 64, 7, 1, 1, 6, 0, 1, 1, 1, 0, 0),       # residual conv7 d=1
     (1, 200, 64, 64, 7, 9, 1, 54, 0, 1, 1, 1, 0, 0),      # d=9
     (2, 40, 96, 96, 7, 9, 1, 54, 0, 1, 1, 1, 0, 0),       # short-input reflect branch (L <= pad), BN=96
