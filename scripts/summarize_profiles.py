@@ -21,6 +21,10 @@ for r in allrows:
     u = r[ix["Metric Unit"]]
     v *= {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1, "second": 1e3}.get(u, 1)
     L[r[ix["Metric Name"]]] = v
+# the target runs two identical forwards: keep the second (warm) one
+ids = sorted(launch)
+if len(ids) % 2 == 0 and [launch[i]["name"] for i in ids[:len(ids) // 2]] == [launch[i]["name"] for i in ids[len(ids) // 2:]]:
+    launch = collections.OrderedDict((i, launch[i]) for i in ids[len(ids) // 2:])
 agg = collections.OrderedDict()
 for L in launch.values():
     a = agg.setdefault(L["name"], [0, 0.0, 0.0])
@@ -33,7 +37,11 @@ for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
 convk = [k for k in agg if k.startswith("fac::conv_tc_kernel") or k.startswith("fac::conv_tcp_kernel") or k.startswith("conv_tc")]
 cl = sum(agg[k][0] for k in convk); cb = sum(agg[k][2] for k in convk); cms = sum(agg[k][1] for k in convk)
 out.append("\n## Full captures\n\n| capture | kernel / layer | grid | time ms | DRAM read+write (traffic) | DRAM % | tensor pipe active % | L1TEX % | L2 % | regs | issue-active % |\n|---|---|---|---|---|---|---|---|---|---|---|")
-desc = {"tc_bf16_convtr192to96": "conv_tc_kernel<0,bf16>: decoder ConvTranspose 192->96 (x2), T 48000->96000 (launch 109)",
+desc = {"tcp_c128k7": "conv_tcp_kernel: encoder conv7 C=128, T=48000",
+        "lstm_dec_bf16": "lstm_rec_kernel<12,bf16>: decoder LSTM layer, H=1536, 320 steps",
+        "tc_tf32_c64k1": "conv_tc_kernel<0,tf32>: encoder 1x1 conv C=64, T=96000 (short chain, 2 CTAs/SM)",
+        "tc_bf16_c384k7": "conv_tc_kernel<0,bf16>: decoder conv7 C=384, T=9600 (2 CTAs/SM)",
+        "tc_bf16_convtr192to96": "conv_tc_kernel<0,bf16>: decoder ConvTranspose 192->96 (x2), T 48000->96000 (launch 109)",
         "tc_bf16_c384k1": "conv_tc_kernel<0,bf16>: decoder ResidualUnit 1x1 conv C=384, T=9600 (launch 100)",
         "tc_bf16_convtr1536to768": "conv_tc_kernel<0,bf16>: decoder ConvTranspose 1536->768 (x6), T 320->1920 (launch 91)",
         "tc_fused_bf16_c192": "conv_tc_kernel<1,bf16>: decoder fused ResidualUnit C=192, T=48000 (launch 106)",
