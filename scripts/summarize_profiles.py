@@ -73,15 +73,32 @@ for f in sorted(glob.glob(os.path.join(D, "prof_*_raw.csv"))):
 out.append("""
 ## Reading
 
-* ConvTranspose 192->96 at T=48000, B=32: algorithmic bytes = x in 1.18 GB + y out 1.18 GB = 2.36 GB; measured DRAM
-  traffic 2.32 GB, so nothing is re-read from HBM.  The conv kernels sit at 2-25 % of DRAM bandwidth and 19-53 % tensor-pipe
-  activity: they are bound by the serial produce -> MMA -> epilogue phases of a CTA (one CTA per SM), not by HBM.
+* **Traffic vs algorithmic bytes.** Fused decoder ResidualUnit, C = 192, T = 48000, B = 32: algorithmic bytes = x in
+  1.18 GB + y out 1.18 GB = 2.36 GB (the residual re-read of x hits L2); measured DRAM traffic 2.32 GB. Encoder 1x1 conv,
+  C = 64: in + residual + out = 3 x 0.786 = 2.36 GB, measured 2.33 GB at 50 % of DRAM bandwidth (0.57 ms). Nothing is
+  re-read from HBM anywhere on the path; over the whole forward the two conv kernels move 65 GB in 84 launches
+  (`roofline_r01.json: conv_family`) against 72 GB of per-layer algorithmic bytes (L2 keeps part of the residuals).
+* **Tensor pipe.** Decoder conv7 at C = 384: 71 % tensor-pipe active, 634 GFLOP x 3 bf16 passes in 1.39 ms = 1.37 PFLOP/s
+  = 95 % of the measured sustained bf16 peak (MEASURED_PEAKS.json). Encoder conv7 (3xTF32 = 6 bf16-equivalent passes):
+  C = 512 / 256 / 128 run at 74-77 % of that peak, C = 64 at 50 %; `sm__pipe_tensor_cycles_active` reads 34-57 % there because
+  a kind::tf32 MMA occupies the pipe at half rate per flop. The fused 96/192-channel units reach 31-38 %: their CTAs are
+  bound by the worker warps (2.5-5 warps per scheduler, long_scoreboard + fixed-latency `wait` stalls dominate, see below).
 * SASS of the dominant kernels contains `UTCHMMA` (tcgen05.mma), `UBLKCP` (bulk TMA), `LDTM` (tcgen05.ld), `UTCBAR`
-  (tcgen05.commit): `cuobjdump -sass facodec_b200/_C/libfacodec_b200.so | grep -E 'UTCHMMA|UBLKCP|LDTM|UTCBAR'`.
-* Tuning history that these captures drove (details in DESIGN.md 4.1): I-cache thrash from unrolled sinf epilogues
-  (stall_no_inst 24 %) -> pi-periodic sin^2 polynomial + rolled loops; 32-line-per-instruction row stores in the
-  epilogue (~3000 cycles per 16-column group) -> shared-memory transpose, 4 lines per instruction; ELECT/BRA.U.ANY
-  loop around every UTCHMMA issued from a divergent region (+75 cycles per MMA) -> converged warp + elect.sync.
+  (tcgen05.commit), `USETMAXREG`: `cuobjdump -sass facodec_b200/_C/libfacodec_b200.so | grep -E 'UTCHMMA|UBLKCP|LDTM|UTCBAR|USETMAXREG'`.
+* **What the source-level captures (`--import-source on`, `--page source`) drove this round** (details in DESIGN.md 4.1):
+  - unrolled sinf epilogues thrashed the instruction cache (stall_no_inst 24 %) -> pi-periodic sin^2 polynomial, rolled loops;
+  - row-per-lane epilogue stores touched 32 lines per instruction (~3000 cycles per 16 columns) -> shared-memory transpose;
+  - every UTCHMMA issued from a divergent region sat in an ELECT / BRA.U.ANY loop (+75 cycles per MMA) -> converged warp + elect.sync;
+  - fused C = 192 unit, one CTA per SM: 28.8 % issue-active, 0.35 eligible warps per scheduler, workers stalled on
+    long_scoreboard (34 %) and `wait` (27 %), producers 19 % and epilogue warps 8 % of the time waiting for MMAs; weights never
+    waited for (b_full spin count 0) -> two-CTA-per-SM plan for every tile that fits 256 TMEM columns, resident GEMM-2 operand,
+    SFU sine in the bf16-class kernels, one range check per 4 channels;
+  - promoted kernel: accumulator warps waited 67 % of a CTA's life, producers idle during the epilogue -> persistent CTAs;
+    ~60k warp-instructions of mbarrier polling per tile; wait-time probes showed the MMA warp busy 85 % of a tile at
+    ~(A + B bytes) / 64 B per clock per MMA; register re-balancing (control 48 / producers 56 / accumulators 160) removed the
+    spills that a 32-register MMA warp had in its issue loop (conv7 C = 64: 1.74 -> 1.48 ms).
+* `profiles/r01_mid/` and `profiles/r01a/` hold the captures taken earlier in the round (before the two-CTA plan, the
+  persistent kernel and the bf16 LSTM) for comparison.
 """)
 open(os.path.join(ROOT, "profiles", "SUMMARY_r01.md"), "w").write("\n".join(out) + "\n")
 roof["conv_family"] = {"launches_per_forward": cl, "dram_bytes_per_forward": cb, "dram_bytes_per_launch": cb / max(1, cl),
