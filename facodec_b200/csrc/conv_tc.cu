@@ -26,6 +26,7 @@
 //               (taps are never re-loaded or im2col'ed).  Epilogue: tcgen05.ld -> bias ->
 //               Snake/tanh/Mish -> residual -> 128-byte row stores.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstring>
 
@@ -265,11 +266,29 @@ __device__ __forceinline__ void split_store(float4 x4, int pc, int row, int Rpad
     }
 }
 
+// fp16 hi + SCALED lo split (conv_tcp_kernel<true>): hi = rn_f16(x), lo' = rn_f16((x - hi) * 2^11).  hi + lo' * 2^-11
+// carries 22 mantissa bits like the TF32 pair, but both halves are 16-bit operands of a full-rate kind::f16 MMA; the
+// scaling keeps lo' in fp16's normal range (|lo'| <= |x|), and the cross terms are accumulated apart and scaled back
+// by 2^-11 at promotion.  Same 8-byte-per-4-channels layout as the bf16 split.
+constexpr float kLoScale = 2048.0f, kLoUnscale = 1.0f / 2048.0f;
+__device__ __forceinline__ void split_store_f16(float4 x4, int pc, int row, int Rpad, uint8_t* ahi, uint8_t* alo) {
+    __half2 h01 = __floats2half2_rn(x4.x, x4.y), h23 = __floats2half2_rn(x4.z, x4.w);
+    float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    __half2 l01 = __floats2half2_rn((x4.x - f01.x) * kLoScale, (x4.y - f01.y) * kLoScale);
+    __half2 l23 = __floats2half2_rn((x4.z - f23.x) * kLoScale, (x4.w - f23.y) * kLoScale);
+    const size_t off = ((size_t)(pc >> 1) * Rpad + row) * 16 + (size_t)(pc & 1) * 8;
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(ahi + off) = hv;
+    *reinterpret_cast<uint2*>(alo + off) = lv;
+}
+
 // ---- activation producer shared by both kernels ------------------------------------------------
 // Thread `ptid` of NT producer threads owns 16-byte piece pc = ptid & 3 (4 input channels) of
 // rows ptid/4, ptid/4 + NT/4, ...: channel offset, Snake parameters and the smem column are
 // per-thread constants for the whole chunk; only the row varies.
-template <int NT, bool BF16, int BATCH = 4, bool INL = false>
+template <int NT, bool BF16, int BATCH = 4, bool INL = false, bool F16 = false>
 __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMap& pm, const float* __restrict__ xb,
                                               int c, int t0, int R, int Rpad, uint8_t* ahi, uint8_t* alo, int ptid) {
     const int pc = ptid & 3;
@@ -304,7 +323,8 @@ __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMa
             if (rr < R) {
                 float4 x4 = v[u];
                 if (has_alpha) x4 = snake4_sel<BF16, INL>(x4, al, ia);   // snake(0) == 0, so padded zeros stay zero
-                split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
+                if constexpr (F16) split_store_f16(x4, pc, rr, Rpad, ahi, alo);
+                else split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
             }
         }
     }
@@ -833,16 +853,25 @@ struct SmemP {
 };
 }  // namespace tc
 
+// F16 = true: fp16 hi + scaled-lo split (see split_store_f16): kind::f16 MMAs with K = 16; per accumulator TWO TMEM
+// regions -- D0 += a_hi * b_hi (promoted to registers every <= 48 MMAs like before, double-buffered per group) and
+// D1 += a_hi * b_lo' + a_lo' * b_hi (2^11-scaled cross terms: their accumulation error is 2^-11 of D0's, so D1 lives
+// in TMEM for the whole tile, double-buffered per tile, and is added once, times 2^-11, after the last group).
+// TMEM map (MT * N <= 128): D0[g & 1] at columns (g & 1) * MT*N, D1[tile & 1] at (2 + (tile & 1)) * MT*N.
+template <bool F16>
 __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams p) {
+    constexpr int KG = F16 ? 2 : 4;                         // 16-byte k-groups per 16-channel chunk
+    constexpr int KSTEPS = F16 ? 1 : 2;                     // MMAs per chunk, tap and pass
+    constexpr int ACC = F16 ? 64 : 128;                     // fp32 register accumulators per accumulator thread
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemP* sm = reinterpret_cast<SmemP*>(smem_raw);
     const int N = p.N, MT = p.MT;
-    const int ncols = MT * N;                               // <= 256 columns per TMEM buffer
+    const int ncols = MT * N;                               // <= 256 (F16: 128) columns per TMEM region
     const int R = 128 * MT + (p.Kr - 1) * p.dil;
     const int Rpad = p.Rpad;
-    const uint32_t a_half = (uint32_t)Rpad * 16 * 4;
-    const uint32_t b_half = (uint32_t)N * 16 * 4;
+    const uint32_t a_half = (uint32_t)Rpad * 16 * KG;
+    const uint32_t b_half = (uint32_t)N * 16 * KG;
     uint8_t* a_base = smem_raw + 128;
     uint8_t* b_base = a_base + 4 * a_half;
     const int S = p.stagesB;
@@ -890,16 +919,17 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
         }
     } else if (warp == 1) {
         {   // whole warp converged; tcgen05 instructions are elect-predicated inside their asm blocks
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t fmt = F16 ? 0u : 2u;          // A/B format: F16 = 0, TF32 = 2
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
             const uint32_t a_base16 = __shfl_sync(0xffffffffu, smem_u32(a_base), 0) >> 4;
             const uint32_t b_base16 = __shfl_sync(0xffffffffu, smem_u32(b_base), 0) >> 4;
             const uint32_t a_lbo16 = (uint32_t)Rpad, b_lbo16 = (uint32_t)N;
             const uint32_t a_half16 = a_half >> 4, b_half16 = b_half >> 4;
-            int it = 0, cg = 0, gg = 0;
+            int it = 0, cg = 0, gg = 0, tl = 0;
             const bool mprobe = kTcpProbe && blockIdx.x == 3;
             long long w_a = 0, w_b = 0, w_acc = 0, tq;
-            for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+            for (int L = blockIdx.x; L < ntiles; L += gridDim.x, ++tl) {
                 for (int g = 0; g < G; ++g, ++gg) {
                     const int abuf = gg & 1;
                     if (mprobe) tq = clock64();
@@ -924,15 +954,24 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                             const uint32_t b_lo = b_hi + b_half16;
                             for (int mt = 0; mt < MT; ++mt) {
                                 const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil);
-                                const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * 256 + mt * N);
+                                if constexpr (F16) {
+                                    const uint32_t d0 = tmem_u + (uint32_t)(abuf * ncols + mt * N);
+                                    const uint32_t d1 = tmem_u + (uint32_t)((2 + (tl & 1)) * ncols + mt * N);
+                                    const uint32_t first0 = ((c - c_begin) | tap) != 0, first1 = (g | (c - c_begin) | tap) != 0;
+                                    umma_bf16(d0, desc_u(a_hi + row_off, a_lbo16), desc_u(b_hi, b_lbo16), idesc, first0);
+                                    umma_bf16(d1, desc_u(a_hi + row_off, a_lbo16), desc_u(b_lo, b_lbo16), idesc, first1);
+                                    umma_bf16(d1, desc_u(a_lo + row_off, a_lbo16), desc_u(b_hi, b_lbo16), idesc, 1u);
+                                } else {
+                                    const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * 256 + mt * N);
 #pragma unroll
-                                for (int pass = 0; pass < 3; ++pass) {
-                                    const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
-                                    const uint32_t bb = (pass == 1 ? b_lo : b_hi);
+                                    for (int pass = 0; pass < 3; ++pass) {
+                                        const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
+                                        const uint32_t bb = (pass == 1 ? b_lo : b_hi);
 #pragma unroll
-                                    for (int ks = 0; ks < kChunk / 8; ++ks) {
-                                        uint32_t accum = ((c - c_begin) | tap | pass | ks) != 0;
-                                        umma_tf32(d_tmem, desc_u(aa + ks * 2 * a_lbo16, a_lbo16), desc_u(bb + ks * 2 * b_lbo16, b_lbo16), idesc, accum);
+                                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                                            uint32_t accum = ((c - c_begin) | tap | pass | ks) != 0;
+                                            umma_tf32(d_tmem, desc_u(aa + ks * 2 * a_lbo16, a_lbo16), desc_u(bb + ks * 2 * b_lbo16, b_lbo16), idesc, accum);
+                                        }
                                     }
                                 }
                             }
@@ -964,7 +1003,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
                 if (probe) tq = clock64();
                 mbar_wait(&sm->a_empty[buf], ((cg >> 1) & 1) ^ 1);
                 if (probe) w_ae += clock64() - tq;
-                produce_chunk<256, false, 4, true>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
+                produce_chunk<256, false, 4, true, F16>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, wtid);
                 fence_proxy_async();
                 mbar_arrive(&sm->a_full[buf]);
             }
@@ -983,29 +1022,45 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
         const int c4 = lane & 7, rsub = lane >> 3;
         const int act = p.out_act;
         const bool aprobe = kTcpProbe && (tid == 12 * 32 && blockIdx.x == 3);
-        int gg = 0;
+        int gg = 0, tl = 0;
         long long w_ar = 0, t_ep = 0, tq = 0;
-        for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+        for (int L = blockIdx.x; L < ntiles; L += gridDim.x, ++tl) {
             const int t0 = (L % gx) * 128 * MT;
             const int ntile = (L / gx) % gy;
             const int b = L / (gx * gy);
-            float acc[128];
+            float acc[ACC];
 #pragma unroll
-            for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+            for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
             for (int g = 0; g < G; ++g, ++gg) {
                 const int abuf = gg & 1;
                 if (aprobe) tq = clock64();
                 mbar_wait(&sm->acc_ready[abuf], (gg >> 1) & 1);   // on the critical path (2 TMEM buffers): polled, not parked
                 if (aprobe) w_ar += clock64() - tq;
                 tc_fence_after();
-                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + mycol0);
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * (F16 ? ncols : 256) + mycol0);
 #pragma unroll
-                for (int grp = 0; grp < 8; ++grp) {
+                for (int grp = 0; grp < ACC / 16; ++grp) {
                     if (grp * 16 < mycols) {
                         uint32_t v[16];
                         tmem_ld16(tbase + grp * 16, v);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) acc[grp * 16 + i] += __uint_as_float(v[i]);
+                    }
+                }
+                if constexpr (F16) {
+                    if (g == G - 1) {
+                        // the last group's commit covers every MMA of the tile: add the scaled cross terms, then release
+                        // (acc_free of this group also tells the MMA warp that D1[tile & 1] may be overwritten two tiles on)
+                        const uint32_t t1 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + (tl & 1)) * ncols + mycol0);
+#pragma unroll
+                        for (int grp = 0; grp < ACC / 16; ++grp) {
+                            if (grp * 16 < mycols) {
+                                uint32_t v[16];
+                                tmem_ld16(t1 + grp * 16, v);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) acc[grp * 16 + i] = fmaf(__uint_as_float(v[i]), kLoUnscale, acc[grp * 16 + i]);
+                            }
+                        }
                     }
                 }
                 tc_fence_before();
@@ -1025,11 +1080,18 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
     _Pragma("unroll") for (int j = 0; j < 8; ++j)                                                                \
         *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =                                                  \
             make_float4(acc[(S0) + j * 4], acc[(S0) + j * 4 + 1], acc[(S0) + j * 4 + 2], acc[(S0) + j * 4 + 3]);
-                switch (sl) {
-                    case 0: FAC_PARK(0) break;
-                    case 1: FAC_PARK(32) break;
-                    case 2: FAC_PARK(64) break;
-                    default: FAC_PARK(96) break;
+                if constexpr (F16) {
+                    switch (sl) {
+                        case 0: FAC_PARK(0) break;
+                        default: FAC_PARK(32) break;
+                    }
+                } else {
+                    switch (sl) {
+                        case 0: FAC_PARK(0) break;
+                        case 1: FAC_PARK(32) break;
+                        case 2: FAC_PARK(64) break;
+                        default: FAC_PARK(96) break;
+                    }
                 }
 #undef FAC_PARK
                 __syncwarp();
@@ -1088,6 +1150,7 @@ bool tc_conv_plan(TcConvParams& p) {
     p.N = N;
     const int KG = p.bf16 ? 2 : 4;
     if (p.bf16 && p.promoted) return false;
+    if (p.f16x2 && !p.promoted) return false;
     if (p.fused && (N != p.Cout || p.Cin != p.Cout || p.vf != 1 || N > 256)) return false;
     p.nchunk = p.Cin * p.vf / tc::kChunk;
     p.nchunk2 = p.fused ? p.Cout / tc::kChunk : 0;
@@ -1100,13 +1163,20 @@ bool tc_conv_plan(TcConvParams& p) {
         return mt;
     };
     if (p.promoted) {
-        p.MT = trim_mt((N <= 64) ? 4 : 2);     // MT * N <= 256 columns per TMEM buffer
-        p.promote_every = 8 / p.Kr < 1 ? 1 : 8 / p.Kr;
+        const int KGp = p.f16x2 ? 2 : 4;
+        if (p.f16x2) {
+            // fp16 hi + scaled-lo: four TMEM regions of MT*N <= 128 columns; one MMA per chunk and tap into D0
+            p.MT = trim_mt(N <= 32 ? 4 : (N <= 64 ? 2 : 1));
+            p.promote_every = 48 / p.Kr < 1 ? 1 : 48 / p.Kr;
+        } else {
+            p.MT = trim_mt((N <= 64) ? 4 : 2);     // MT * N <= 256 columns per TMEM buffer
+            p.promote_every = 8 / p.Kr < 1 ? 1 : 8 / p.Kr;
+        }
         int R = 128 * p.MT + (p.Kr - 1) * p.dil, Rpad = R;
         while (Rpad % 8 != 2) ++Rpad;
         p.Rpad = Rpad;
         p.tmem_cols = 512;
-        size_t a_bytes = (size_t)4 * Rpad * 16 * KG, b_stage = (size_t)2 * N * 16 * KG;
+        size_t a_bytes = (size_t)4 * Rpad * 16 * KGp, b_stage = (size_t)2 * N * 16 * KGp;
         const size_t stage_bytes = (size_t)8 * 32 * 36 * 4;     // accumulator warps' private epilogue transpose stage
         int S = tc::kMaxStagesB;
         while (S > 2 && 128 + a_bytes + S * b_stage + stage_bytes > 225 * 1024) --S;
@@ -1150,7 +1220,7 @@ bool tc_conv_plan(TcConvParams& p) {
 }
 
 size_t tc_blob_floats(const TcConvParams& p) {
-    return (size_t)(p.Cout / p.N) * p.nchunk * p.Kr * 2 * (p.bf16 ? 2 : 4) * p.N * 4;
+    return (size_t)(p.Cout / p.N) * p.nchunk * p.Kr * 2 * ((p.bf16 || p.f16x2) ? 2 : 4) * p.N * 4;
 }
 
 static inline uint16_t bf16_rn_host(float f) {
@@ -1163,6 +1233,27 @@ static inline uint16_t bf16_rn_host(float f) {
 // wp: packed generic weights [Kr * vf*Cin][ldw] (conv_simt layout).  blob: see file header.
 void tc_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob) {
     const int Cw = p.Cin * p.vf;   // columns per row-tap
+    if (p.f16x2) {
+        // [ntile][chunk][tap][hi|lo'][k8 (2)][N][8 fp16], lo' = rn_f16((w - hi) * 2^11)
+        uint16_t* ob = reinterpret_cast<uint16_t*>(blob);
+        size_t o16 = 0;
+        for (int nt = 0; nt < p.Cout / p.N; ++nt)
+            for (int c = 0; c < p.nchunk; ++c)
+                for (int tap = 0; tap < p.Kr; ++tap)
+                    for (int hl = 0; hl < 2; ++hl)
+                        for (int k8 = 0; k8 < 2; ++k8)
+                            for (int n = 0; n < p.N; ++n)
+                                for (int e = 0; e < 8; ++e) {
+                                    int kk = tap * Cw + c * tc::kChunk + k8 * 8 + e;
+                                    float w = wp[(size_t)kk * ldw + nt * p.N + n];
+                                    __half hi = __float2half_rn(w);
+                                    __half v = hl == 0 ? hi : __float2half_rn((w - __half2float(hi)) * 2048.0f);
+                                    uint16_t bits;
+                                    memcpy(&bits, &v, 2);
+                                    ob[o16++] = bits;
+                                }
+        return;
+    }
     if (p.bf16) {
         // [ntile][chunk][tap][hi|lo][k8 (2)][N][8 bf16]
         uint16_t* ob = reinterpret_cast<uint16_t*>(blob);
@@ -1229,7 +1320,8 @@ cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
     if (p.promoted) {
         static bool configured_p = false;
         if (!configured_p) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+            cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
             if (e != cudaSuccess) return e;
             configured_p = true;
         }
@@ -1241,7 +1333,8 @@ cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
         }
         const long long ntiles = (long long)grid.x * grid.y * grid.z;
         const unsigned nctas = (unsigned)(ntiles < sm_count ? ntiles : sm_count);   // persistent: one CTA per SM
-        conv_tcp_kernel<<<dim3(nctas), tc::kThreadsP, p.smem_bytes, st>>>(p);
+        if (p.f16x2) conv_tcp_kernel<true><<<dim3(nctas), tc::kThreadsP, p.smem_bytes, st>>>(p);
+        else conv_tcp_kernel<false><<<dim3(nctas), tc::kThreadsP, p.smem_bytes, st>>>(p);
     } else {
         if (p.fused && p.bf16) conv_tc_kernel<true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.fused) conv_tc_kernel<true, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);

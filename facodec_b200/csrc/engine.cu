@@ -37,7 +37,7 @@ struct ConvW {
     // tensor-core blob (conv_tc.cu): present when the layer is eligible
     bool tc = false; size_t tcw = 0; int vf = 1, Kr = 0, tcN = 0;   // tcN: channel tile the blob was laid out for
     bool promoted = false;   // blob built for conv_tcp_kernel (layers upstream of the VQ)
-    bool has16 = false; size_t tcw16 = 0;   // bf16 hi/lo blob (non-promoted layers only)
+    bool has16 = false; size_t tcw16 = 0;   // 16-bit-operand blob: bf16 hi/lo (non-promoted layers) or fp16 hi / scaled lo (promoted)
 };
 struct SnakeW { size_t a = 0, ia = 0; int C = 0; };
 struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; size_t whh16[2] = {0, 0}; bool has16 = false; int H = 0, U = 0, G = 0; };
@@ -82,6 +82,7 @@ struct fac_handle {
     int use_tc = 2;
     int fuse_res = 1;               // fused ResidualUnit launches (fac_set_option "fuse_resunit"); 2 = only where the
                                     // fused tile still allows two CTAs per SM (C <= 128)
+    int enc_f16 = 0;                // fac_set_option "encoder_f16x2": promoted layers use the fp16 hi + scaled-lo split
     int tc_occ2 = 256;              // fac_set_option "tc_occ2_maxn": conv_tc tiles with N <= this are planned for two CTAs per SM (0 = off)
     bool dec_bf16 = true;           // decoder-side layers use the bf16x3 split (fac_set_option "decoder_bf16")
     float* aa_filter = nullptr;
@@ -153,7 +154,15 @@ void attach_tc(fac_handle* h, ConvW& c, int stride, bool promoted) {
     c.tcw = pack_alloc(h, n);
     tc_pack_blob(tp, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw);
     c.tc = true;
-    if (!promoted) {
+    if (promoted) {
+        TcConvParams t16 = tp;
+        t16.f16x2 = 1;
+        if (tc_conv_plan(t16) && t16.N == tp.N) {
+            c.tcw16 = pack_alloc(h, tc_blob_floats(t16));
+            tc_pack_blob(t16, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw16);
+            c.has16 = true;
+        }
+    } else {
         TcConvParams t16 = tp;
         t16.bf16 = 1;
         if (tc_conv_plan(t16) && t16.N == tp.N) {
@@ -520,11 +529,12 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
             if (tc_conv_plan(probe) && probe.N == w.tcN) { tp.promoted = 0; short_chain = true; }
         }
         tp.dil = w.vf == 1 ? o.dil : 1;
-        tp.bf16 = (c.h->dec_bf16 && w.has16 && !c.vq_critical) ? 1 : 0;
+        tp.bf16 = (c.h->dec_bf16 && w.has16 && !w.promoted && !c.vq_critical) ? 1 : 0;
+        tp.f16x2 = (tp.promoted && c.h->enc_f16 && w.has16) ? 1 : 0;
         tp.occ2_maxn = c.h->tc_occ2;
         tp.Tout = Tout;
         if (tc_conv_plan(tp)) {
-            tp.x = x; tp.y = y; tp.wblob = c.W(tp.bf16 ? w.tcw16 : w.tcw); tp.bias = c.W(w.b);
+            tp.x = x; tp.y = y; tp.wblob = c.W((tp.bf16 || tp.f16x2) ? w.tcw16 : w.tcw); tp.bias = c.W(w.b);
             if (o.in_snake) { tp.in_alpha = c.W(o.in_snake->a); tp.in_inv_alpha = c.W(o.in_snake->ia); }
             tp.out_act = o.act;
             if (o.out_snake) { tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(o.out_snake->a); tp.out_inv_alpha = c.W(o.out_snake->ia); }
@@ -1265,6 +1275,7 @@ int fac_set_option(fac_handle* h, const char* name, int value) {
     if (!h || !name) return FAC_ERR_INVALID;
     if (std::string(name) == "fuse_resunit") { h->fuse_res = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     if (std::string(name) == "tc_occ2_maxn") { h->tc_occ2 = value < 0 ? 0 : value; return FAC_OK; }
+    if (std::string(name) == "encoder_f16x2") { h->enc_f16 = value != 0; return FAC_OK; }
     if (std::string(name) == "decoder_bf16") { h->dec_bf16 = value != 0; return FAC_OK; }
     if (std::string(name) == "tensor_cores") { h->use_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     h->err = std::string("unknown option ") + name;
@@ -1279,7 +1290,8 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     TcConvParams tp;
-    tp.Cin = Cin; tp.Cout = Cout; tp.promoted = promoted == 1 ? 1 : 0; tp.bf16 = promoted == 2 ? 1 : 0;
+    tp.Cin = Cin; tp.Cout = Cout; tp.promoted = (promoted == 1 || promoted == 3) ? 1 : 0; tp.bf16 = promoted == 2 ? 1 : 0;
+    tp.f16x2 = promoted == 3 ? 1 : 0;
     tp.occ2_maxn = h->tc_occ2;
     tp.Tout = Tout;
     if (stride == 1) { tp.vf = 1; tp.Kr = K; tp.dil = dil; }

@@ -44,6 +44,7 @@ struct TcConvParams {
     int out_act = 0;
     int promoted = 0;                  // 1 = conv_tcp_kernel (register-promoted accumulation)
     int bf16 = 0;                      // 1 = bf16 hi/lo split (kind::f16, K = 16) instead of tf32 hi/lo; decoder only
+    int f16x2 = 0;                     // promoted only: fp16 hi + 2^11-scaled fp16 lo split (kind::f16, K = 16) instead of tf32 hi/lo
     int fused = 0;                     // 1 = whole ResidualUnit: conv7 -> +b7 -> Snake -> 1x1 conv -> +b1 -> +x
     const float* wblob2 = nullptr;     // 1x1 conv weight blob (same tile N), when fused
     const float* bias2 = nullptr;

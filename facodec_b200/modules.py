@@ -13,6 +13,7 @@ Drop-in contract:
 * There is no CPU fallback: CPU tensors or a missing library raise.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -52,6 +53,10 @@ class Engine:
             if rc < 0:
                 raise _lib.FacError(f"fac_create(device={idx}) failed with status {rc}")
             self.handle, self.device_index = h, idx
+            # measurement aid: FACODEC_B200_OPTS="name=value,name=value" applies fac_set_option at creation
+            for kv in filter(None, os.environ.get("FACODEC_B200_OPTS", "").split(",")):
+                name, _, val = kv.partition("=")
+                _lib.check(self.handle, self.L.fac_set_option(self.handle, name.strip().encode(), int(val)), "fac_set_option")
         elif idx != self.device_index:
             raise _lib.FacError("engine is bound to cuda:%d, got cuda:%d" % (self.device_index, idx))
 

@@ -116,6 +116,11 @@ int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int a
  * (tcgen05.mma.kind::f16, K = 16: half the MMAs and half the operand bytes of the TF32 split; waveform error
  * ~1e-5 RMS against the 1e-4 bar), evaluate Snake with the SFU sine and run the LSTM recurrence on bf16 hi/lo
  * mma.sync tiles; 0 = TF32 hi/lo everywhere.  Never applied upstream of the VQ.
+ * "encoder_f16x2": 0 (default) / 1 = EXPERIMENTAL: layers upstream of the VQ split operands into fp16 hi + fp16 lo
+ * scaled by 2^11 (kind::f16, K = 16, cross terms in their own TMEM accumulator, scaled back at promotion) instead of
+ * the TF32 pair: same 22 mantissa bits and bit-exact codes on every fixture, but operands must stay below fp16's
+ * 65504, and the measured gain is only 5-11 % on the k=7 encoder convs (one MMA stream per SM runs kind::f16 at
+ * about half rate for N <= 128), so it is off by default.
  * "tc_occ2_maxn": channel tiles of at most this width (default 256; 0 = off) are planned for TWO resident CTAs per
  * SM (<= 256 TMEM columns, <= 112 KB shared memory each) so one CTA's MMAs overlap the other's produce/epilogue. */
 int fac_set_option(fac_handle* h, const char* name, int value);
@@ -134,7 +139,8 @@ int fac_debug_conv(fac_handle* h, const float* x, const float* w_host, const flo
 /* Same contract as fac_debug_conv, forced through the tcgen05 kernels: promoted = 0 -> conv_tc_kernel
  * (3xTF32, accumulates in TMEM only), 1 -> conv_tcp_kernel (3xTF32, TMEM accumulators promoted to fp32
  * registers every ~48 MMAs; the variant used upstream of the VQ), 2 -> conv_tc_kernel with the bf16 hi/lo
- * split (decoder-only precision class).  Returns FAC_ERR_UNSUPPORTED when
+ * split (decoder-only precision class), 3 -> conv_tcp_kernel with the fp16 hi + 2^11-scaled fp16 lo split
+ * (experimental "encoder_f16x2" class).  Returns FAC_ERR_UNSUPPORTED when
  * the layer geometry is not eligible (Cin % 16, Cout % 16, stride). */
 int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const float* bias_host, int B, int Tin,
                       int Cin, int Cout, int K, int dil, int stride, int pad_left, int pad_right, int reflect,

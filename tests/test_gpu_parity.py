@@ -227,3 +227,23 @@ def test_other_precision_modes_keep_parity(mode, built_lib):
         assert np.array_equal(t.cpu().numpy(), g[k]), k
     assert np.abs(z.cpu().numpy() - g["z"]).max() <= Z_RTOL * np.abs(g["z"]).max()
     assert rms(y, g["y"]) <= (5e-7 if mode == 0 else RMS_TOL)
+
+
+def test_encoder_f16x2_option_keeps_parity(built_lib):
+    """fac_set_option("encoder_f16x2", 1) (experimental, default off): the promoted kernel with the fp16 hi + 2^11-scaled lo
+    split instead of the TF32 pair (22 mantissa bits either way).  Codes stay bit-exact on the fixtures."""
+    for name in ("b2_t7200", "b1_t96000"):
+        c = GOLDEN_CASES[name]
+        g = load_golden(name)
+        m = model_for(c["wseed"])
+        eng = m.encoder._engine
+        x, kw = case_inputs(c)
+        try:
+            eng.set_option("encoder_f16x2", 1, torch.device("cuda:0"))
+            z, q, y = run_model(m, x, c["n_c"], kw)
+        finally:
+            eng.set_option("encoder_f16x2", 0, torch.device("cuda:0"))
+        for k, t in zip(("codes_p", "codes_c", "codes_r"), q[5]):
+            assert np.array_equal(t.cpu().numpy(), g[k]), k
+        assert np.abs(z.cpu().numpy() - g["z"]).max() <= Z_RTOL * np.abs(g["z"]).max()
+        assert rms(y, g["y"]) <= RMS_TOL
