@@ -841,9 +841,11 @@ template <int R>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+constexpr int kMaxStagesP = 4;     // weight ring depth of the persistent kernel.  The MMA warp waits for weights ~10 % of the
+                                   // time (probes), but a 6-8 deep ring measured SLOWER (conv7 C=128: 1.98 -> 2.23 ms), so 4
 struct SmemP {
-    uint64_t b_full[kMaxStagesB];
-    uint64_t b_empty[kMaxStagesB];
+    uint64_t b_full[kMaxStagesP];
+    uint64_t b_empty[kMaxStagesP];
     uint64_t a_full[2];
     uint64_t a_empty[2];
     uint64_t acc_ready[2];
@@ -851,6 +853,7 @@ struct SmemP {
     uint32_t tmem_base;
     uint32_t pad;
 };
+static_assert(sizeof(SmemP) <= kSmemHdr, "SmemP header");
 }  // namespace tc
 
 // F16 = true: fp16 hi + scaled-lo split (see split_store_f16): kind::f16 MMAs with K = 16; per accumulator TWO TMEM
@@ -872,7 +875,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
     const int Rpad = p.Rpad;
     const uint32_t a_half = (uint32_t)Rpad * 16 * KG;
     const uint32_t b_half = (uint32_t)N * 16 * KG;
-    uint8_t* a_base = smem_raw + 128;
+    uint8_t* a_base = smem_raw + kSmemHdr;
     uint8_t* b_base = a_base + 4 * a_half;
     const int S = p.stagesB;
     const int P = p.promote_every;
@@ -889,7 +892,7 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
     const int G = (nchunk + P - 1) / P;
 
     if (tid == 0) {
-        for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
+        for (int i = 0; i < kMaxStagesP; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sm->a_full[i], 256); mbar_init(&sm->a_empty[i], 1);
             mbar_init(&sm->acc_ready[i], 1); mbar_init(&sm->acc_free[i], 256);
@@ -1178,11 +1181,11 @@ bool tc_conv_plan(TcConvParams& p) {
         p.tmem_cols = 512;
         size_t a_bytes = (size_t)4 * Rpad * 16 * KGp, b_stage = (size_t)2 * N * 16 * KGp;
         const size_t stage_bytes = (size_t)8 * 32 * 36 * 4;     // accumulator warps' private epilogue transpose stage
-        int S = tc::kMaxStagesB;
-        while (S > 2 && 128 + a_bytes + S * b_stage + stage_bytes > 225 * 1024) --S;
-        if (128 + a_bytes + S * b_stage + stage_bytes > 225 * 1024) return false;
+        int S = tc::kMaxStagesP;
+        while (S > 2 && tc::kSmemHdr + a_bytes + S * b_stage + stage_bytes > 225 * 1024) --S;
+        if (tc::kSmemHdr + a_bytes + S * b_stage + stage_bytes > 225 * 1024) return false;
         p.stagesB = S;
-        p.smem_bytes = 128 + a_bytes + S * b_stage + stage_bytes;
+        p.smem_bytes = tc::kSmemHdr + a_bytes + S * b_stage + stage_bytes;
         return true;
     }
     // conv_tc_kernel.  A tile is MT accumulators of 128 rows x N columns (x2 when fused: D1 and D2) sharing every weight
