@@ -7,24 +7,30 @@
 //   D[t][co] = sum_tap sum_j  A[t - PLr + tap*dil][j] * W[tap][j][co]
 //
 // Precision: bit-exact VQ indices need fp32-faithful sums, so every product is
-// formed as 3 TF32 MMAs (x = hi + lo, both exactly representable in TF32):
-//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi     (dropped term a_lo*b_lo ~ 2^-24 |ab|)
+// formed as 3 MMAs over split operands (x = hi + lo):
+//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi     (dropped term a_lo*b_lo ~ 2^-22 |ab|)
 // with fp32 accumulation in TMEM.  Weights are split offline; activations are split in-kernel.
+// Split classes: TF32 pairs (kind::tf32, K = 8) upstream of the VQ; bf16 pairs (kind::f16, K = 16) downstream;
+// experimental fp16 hi + 2^11-scaled fp16 lo upstream (conv_tcp_kernel<true>).
 //
-// CTA = 10 warps, one 128*MT-row x N-channel output tile (MT accumulators in TMEM share every
-// weight tile, which halves/quarters the L2->SMEM weight traffic per MMA):
+// Two kernels share the operand pipeline:
+//   conv_tc_kernel<FUSED, BF16>  accumulates in TMEM only (decoder, short K loops); 10 warps, planned for two CTAs per
+//                                SM wherever the tile fits 256 TMEM columns / 112 KB; FUSED = a whole ResidualUnit.
+//   conv_tcp_kernel<F16>         promotes TMEM accumulators into fp32 registers every <= 48 MMAs (everything upstream of
+//                                the VQ with a long K loop); 20 warps re-allocated with setmaxnreg, persistent.
+// Roles in conv_tc_kernel (the promoted kernel splits the last group into producers and accumulators):
 //   warp 0    : weight producer -- one elected lane streams pre-arranged [tap][16 ci] weight
 //               blobs (hi|lo, already in the UMMA K-major core-matrix layout) with 1-D bulk
 //               TMA copies (cp.async.bulk, UBLKCP) into a 4-deep mbarrier ring.
-//   warp 1    : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma.kind::tf32
-//               (M=128, N, K=8) and tcgen05.commit's to free ring slots.
+//   warp 1    : TMEM allocator + MMA issuer -- converged warp, every tcgen05.mma / tcgen05.commit predicated by
+//               elect.sync inside its asm block; descriptors assembled from warp-uniform 16-byte-unit offsets.
 //   warps 2-9 : activation producers, then epilogue.  Per 16-channel chunk they load the UNION
 //               of the rows all taps need (128*MT + (K-1)*dil rows) once from HBM with 16-byte
 //               loads (reflect/zero padding = index map, no padded copy), apply Snake, split into
 //               hi/lo and store them in a no-swizzle K-major layout whose row pitch is a uniform
 //               16 bytes, so each tap is just a descriptor start-address offset of tap*dil rows
-//               (taps are never re-loaded or im2col'ed).  Epilogue: tcgen05.ld -> bias ->
-//               Snake/tanh/Mish -> residual -> 128-byte row stores.
+//               (taps are never re-loaded or im2col'ed).  Epilogue: tcgen05.ld -> shared-memory transpose ->
+//               bias -> Snake/tanh/Mish -> residual -> coalesced 128-byte row segments.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 

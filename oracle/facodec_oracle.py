@@ -97,7 +97,7 @@ def slstm(x, sd, prefix, num_layers=2):
     for l in range(num_layers):
         flat += [sd[f"{prefix}.weight_ih_l{l}"], sd[f"{prefix}.weight_hh_l{l}"],
                  sd[f"{prefix}.bias_ih_l{l}"], sd[f"{prefix}.bias_hh_l{l}"]]
-    h0 = torch.zeros(num_layers, B, H, dtype=x.dtype)
+    h0 = torch.zeros(num_layers, B, H, dtype=x.dtype, device=x.device)
     y, _, _ = torch._VF.lstm(x, (h0, h0.clone()), flat, True, num_layers, 0.0, False, False, False)
     y = y + x
     return y.permute(1, 2, 0)
@@ -301,7 +301,7 @@ def residual_vq(sd, prefix, z, n_quantizers):
 # modules/quantize.py FAquantizer.forward_v2 (eval)
 # ----------------------------------------------------------------------------
 def sequence_mask(length, max_length):
-    x = torch.arange(max_length, dtype=length.dtype)
+    x = torch.arange(max_length, dtype=length.dtype, device=length.device)
     return x.unsqueeze(0) < length.unsqueeze(1)
 
 
