@@ -287,7 +287,7 @@ def residual_vq(sd, prefix, z, n_quantizers):
     codes, latents = [], []
     for i in range(n_quantizers):
         z_q_i, c_i, cb_i, idx_i, z_e_i = vector_quantize(sd, f"{prefix}.quantizers.{i}", residual)
-        mask = torch.full((z.shape[0],), fill_value=i) < n_quantizers
+        mask = torch.full((z.shape[0],), fill_value=i, device=z.device) < n_quantizers
         z_q = z_q + z_q_i * mask[:, None, None]
         residual = residual - z_q_i
         commitment_loss = commitment_loss + (c_i * mask).mean()
@@ -310,7 +310,7 @@ def quantizer_forward(sd, x, wave, n_c=1, n_t=2, full_waves=None, wave_lens=None
     """FAquantizer.forward_v2, modules/quantize.py:375-454, eval mode (res_mask == 1)."""
     if full_waves is None:
         mel = mel_preprocess(sd, wave, n_bins=80)
-        mask = torch.ones(mel.size(0), 1, mel.size(2)).bool()
+        mask = torch.ones(mel.size(0), 1, mel.size(2), device=mel.device).bool()
     else:
         mel = mel_preprocess(sd, full_waves.unsqueeze(1), n_bins=80)
         mask = sequence_mask(wave_lens // HOP, mel.size(-1)).unsqueeze(1)
@@ -331,7 +331,7 @@ def quantizer_forward(sd, x, wave, n_c=1, n_t=2, full_waves=None, wave_lens=None
     outs = outs + z_c
     residual_feature = x - z_p - z_c
     z_r, codes_r, _, cl_r, cbl_r = residual_vq(sd, "residual_quantizer", residual_feature, 3)
-    outs = outs + z_r * torch.ones(z_r.shape[0], 1, 1)
+    outs = outs + z_r * torch.ones(z_r.shape[0], 1, 1, device=z_r.device)
     quantized = [z_p, z_c, z_r]
     codes = [codes_p, codes_c, codes_r]
     commitment = cl_p + cl_c + cl_r
