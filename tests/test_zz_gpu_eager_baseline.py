@@ -2,7 +2,8 @@
 reference's nn.Modules execute) run by PyTorch eager on the same B200 in fp32 with TF32 disabled, at BASELINE
 configs[1] (32 x 4 s), timed beside this repo's path.  Informational numbers are printed (pytest -s); the assertions
 only pin that both paths agree (cuDNN picks its own summation orders, so a handful of near-tied VQ decisions may differ
-between eager-GPU and the CPU reference -- this repo matches the CPU reference bit for bit, see test_gpu_parity.py)."""
+between eager-GPU and the CPU reference -- this repo matches the CPU reference bit for bit, see test_gpu_parity.py).
+The file name sorts last so that `pytest -x` reaches it after the parity tests."""
 import pytest
 import torch
 
@@ -33,8 +34,11 @@ def test_reference_ops_eager_on_gpu_baseline(built_lib):
         torch.cuda.synchronize()
         return out, a.elapsed_time(b) / n
 
-    with torch.no_grad():
-        (zo, qo, yo), ms_eager = timed(lambda: O.codec_forward(sds_gpu, x, n_c=2), 2)
+    try:
+        with torch.no_grad():
+            (zo, qo, yo), ms_eager = timed(lambda: O.codec_forward(sds_gpu, x, n_c=2), 2)
+    except RuntimeError as e:      # e.g. out of memory on a smaller device: the baseline is informational
+        pytest.skip(f"eager baseline could not run here: {e}")
     m = fb.build_model()
     for k in ("encoder", "quantizer", "decoder"):
         m[k].load_state_dict(sds[k])
