@@ -157,6 +157,11 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
  * [0] start, [1] all activation chunks produced, [2] GEMM 1 retired, [3] GEMM-2 operand produced (fused),
  * [4] GEMM 2 retired (fused), [5] epilogue done.  Kernel-tuning aid. */
 int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8);
+/* Host-only (no GPU, no handle): the tile plan of the tcgen05 conv kernels for one layer geometry.  mode: 0 conv_tc TF32,
+ * 1 conv_tcp (promoted) TF32, 2 conv_tc bf16, 3 conv_tcp fp16 hi + scaled lo, 4 fused ResidualUnit bf16, 5 fused TF32.
+ * Tout may be 0 (unknown).  out8 = {N, MT, K chunks, weight-ring stages, TMEM columns, dynamic shared-memory bytes,
+ * padded rows of the operand buffer, chunks per promotion}.  FAC_ERR_UNSUPPORTED when the layer is not eligible. */
+int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, int mode, int occ2_maxn, int* out8);
 /* clock64() totals of CTA 0 of the most recent lstm_rec_kernel launch, summed over all steps:
  * [0] grid-barrier wait, [1] W_hh/h streaming + MMAs, [2] cross-warp reduce + gate math, [3] publish. */
 int fac_debug_lstm_phase_clocks(fac_handle* h, long long* out4);

@@ -106,3 +106,56 @@ def test_shard_range_partitions():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _plan(L, Cin, Cout, K, dil, stride, Tout, mode, occ2):
+    import ctypes
+    out = (ctypes.c_int * 8)()
+    rc = L.fac_debug_tc_plan(Cin, Cout, K, dil, stride, Tout, mode, occ2, out)
+    return rc, dict(zip(("N", "MT", "nchunk", "stages", "tmem_cols", "smem", "Rpad", "promote_every"), list(out)))
+
+
+def test_tcgen05_tile_plans_respect_hardware_limits(built_lib):
+    """Host logic of the tensor-core path (no GPU): every layer geometry of the model gets a plan inside the SM's
+    limits -- TMEM <= 512 columns (<= 256 for the two-CTA plan), dynamic shared memory <= 225 KB (<= 112 KB), N | Cout,
+    promotion window <= 48 chained MMAs -- and ineligible layers are refused."""
+    from facodec_b200 import _lib
+    L = _lib.load()
+    enc = [(64, 64, 7, d, 1, 96000) for d in (1, 3, 9)] + [(128, 128, 7, 9, 1, 48000), (256, 256, 7, 9, 1, 9600),
+           (512, 512, 7, 9, 1, 1920), (64, 128, 4, 1, 2, 48000), (128, 256, 10, 1, 5, 9600), (256, 512, 10, 1, 5, 1920),
+           (512, 1024, 12, 1, 6, 320), (1024, 1024, 3, 1, 1, 320), (1024, 4096, 1, 1, 1, 10240), (1200, 2176, 1, 1, 1, 10240),
+           (256, 512, 5, 1, 1, 320), (512, 1024, 5, 1, 1, 320)]
+    for (Cin, Cout, K, dil, stride, T) in enc:
+        for mode in (1, 3):
+            rc, p = _plan(L, Cin, Cout, K, dil, stride, T, mode, 256)
+            assert rc == 0, (Cin, Cout, K, mode)
+            assert Cout % p["N"] == 0 and p["N"] % 16 == 0 and p["N"] <= 128
+            assert p["MT"] * p["N"] <= (128 if mode == 3 else 256) and p["tmem_cols"] == 512
+            assert p["smem"] <= 225 * 1024 and 2 <= p["stages"] <= 8
+            Kr = K if stride == 1 else 2
+            chain = p["promote_every"] * Kr * (1 if mode == 3 else 6)
+            assert chain <= 48 or p["promote_every"] == 1
+    dec = [(1024, 1536, 7, 1, 1, 320), (1536, 6144, 1, 1, 1, 10240), (768, 768, 7, 9, 1, 1920), (384, 384, 7, 3, 1, 9600),
+           (384, 384, 1, 1, 1, 9600), (192, 192, 2, 1, 1, 48000), (1536, 4608, 2, 1, 1, 320)]
+    for (Cin, Cout, K, dil, stride, T) in dec:
+        for occ2 in (0, 256):
+            rc, p = _plan(L, Cin, Cout, K, dil, stride, T, 2, occ2)
+            assert rc == 0
+            assert Cout % p["N"] == 0 and p["N"] <= 256 and p["MT"] * p["N"] <= p["tmem_cols"] <= 512
+            if occ2:
+                assert p["tmem_cols"] <= 256 and p["smem"] <= 112 * 1024      # two CTAs per SM
+            assert p["smem"] <= 225 * 1024
+    # fused ResidualUnits: C = 96 fits the two-CTA plan, C = 192 needs 384 TMEM columns -> one CTA per SM
+    rc, p96 = _plan(L, 96, 96, 7, 9, 1, 96000, 4, 256)
+    rc2, p192 = _plan(L, 192, 192, 7, 9, 1, 48000, 4, 256)
+    assert rc == 0 and rc2 == 0
+    assert p96["tmem_cols"] <= 256 and p96["smem"] <= 112 * 1024
+    assert p192["MT"] == 1 and p192["tmem_cols"] == 512
+    # short sequences: MT trimmed so the padded tail of the tile grid stays small
+    _, long_t = _plan(L, 512, 512, 7, 1, 1, 1920, 1, 0)
+    _, short_t = _plan(L, 512, 512, 7, 1, 1, 320, 1, 0)
+    assert long_t["MT"] == 2 and short_t["MT"] == 1
+    # not eligible: Cin not a multiple of 16 per row, odd strides, fused with Cin != Cout
+    assert _plan(L, 20, 256, 1, 1, 1, 320, 1, 0)[0] != 0
+    assert _plan(L, 64, 64, 7, 1, 3, 100, 0, 0)[0] != 0
+    assert _plan(L, 96, 192, 7, 1, 1, 100, 4, 0)[0] != 0
