@@ -1397,6 +1397,29 @@ int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, i
     return FAC_OK;
 }
 
+// Host-only: the tensor-core weight blob (tc_pack_blob) for nn.Conv1d weights [Cout][Cin][K]; returns the number of
+// floats (32-bit words) of the blob, writes it when blob_out has room.
+long long fac_debug_tc_pack(const float* w_host, int Cin, int Cout, int K, int stride, int mode, float* blob_out,
+                            long long capacity_floats) {
+    if (!w_host || Cin <= 0 || Cout <= 0 || K <= 0 || stride <= 0 || mode < 0 || mode > 3) return FAC_ERR_INVALID;
+    TcConvParams tp;
+    tp.Cin = Cin; tp.Cout = Cout; tp.dil = 1;
+    tp.promoted = (mode == 1 || mode == 3) ? 1 : 0; tp.bf16 = mode == 2 ? 1 : 0; tp.f16x2 = mode == 3 ? 1 : 0;
+    if (stride == 1) { tp.vf = 1; tp.Kr = K; }
+    else if (K == 2 * stride) { tp.vf = stride; tp.Kr = 2; }
+    else return FAC_ERR_UNSUPPORTED;
+    if (!tc_conv_plan(tp)) return FAC_ERR_UNSUPPORTED;
+    const long long n = (long long)tc_blob_floats(tp);
+    if (!blob_out || capacity_floats < n) return n;
+    const int ldw = (Cout + 3) / 4 * 4;
+    std::vector<float> gen((size_t)K * Cin * ldw, 0.f);      // generic packed layout [K*Cin][ldw]
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int k = 0; k < K; ++k) gen[((size_t)k * Cin + ci) * ldw + co] = w_host[((size_t)co * Cin + ci) * K + k];
+    tc_pack_blob(tp, gen.data(), ldw, blob_out);
+    return n;
+}
+
 int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8) {
     if (!h || !out8) return FAC_ERR_INVALID;
     cudaSetDevice(h->device);

@@ -162,6 +162,12 @@ int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8);
  * Tout may be 0 (unknown).  out8 = {N, MT, K chunks, weight-ring stages, TMEM columns, dynamic shared-memory bytes,
  * padded rows of the operand buffer, chunks per promotion}.  FAC_ERR_UNSUPPORTED when the layer is not eligible. */
 int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, int mode, int occ2_maxn, int* out8);
+/* Host-only: packs nn.Conv1d weights [Cout][Cin][K] (HOST) into the tensor-core blob of mode 0..3 (see
+ * fac_debug_tc_plan): [Cout/N][K chunks][taps][hi|lo][k-groups][N][16 bytes], hi|lo = TF32 pair (4 k-groups of 4 fp32
+ * words), bf16 pair or fp16 hi / 2^11-scaled lo (2 k-groups of 8 halves).  Returns the blob size in 32-bit words (also
+ * when blob_out is NULL or too small), or a negative status. */
+long long fac_debug_tc_pack(const float* w_host, int Cin, int Cout, int K, int stride, int mode, float* blob_out,
+                            long long capacity_floats);
 /* clock64() totals of CTA 0 of the most recent lstm_rec_kernel launch, summed over all steps:
  * [0] grid-barrier wait, [1] W_hh/h streaming + MMAs, [2] cross-warp reduce + gate math, [3] publish. */
 int fac_debug_lstm_phase_clocks(fac_handle* h, long long* out4);

@@ -159,3 +159,53 @@ def test_tcgen05_tile_plans_respect_hardware_limits(built_lib):
     assert _plan(L, 20, 256, 1, 1, 1, 320, 1, 0)[0] != 0
     assert _plan(L, 64, 64, 7, 1, 3, 100, 0, 0)[0] != 0
     assert _plan(L, 96, 192, 7, 1, 1, 100, 4, 0)[0] != 0
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("geom", [(64, 64, 7, 1), (128, 256, 10, 5), (96, 96, 1, 1), (32, 48, 3, 1)])
+def test_tensor_core_weight_blob_layout_and_split(geom, mode, built_lib):
+    """Host logic (no GPU): the UMMA weight blob.  Decodes [ntile][chunk][tap][hi|lo][k-group][N][16 B] back to W and
+    checks the split classes: TF32 pair / bf16 pair / fp16 hi + 2^11-scaled lo reconstruct w to their mantissa budget
+    and each half is exactly representable in its format."""
+    import ctypes
+    import numpy as np
+    from facodec_b200 import _lib
+    L = _lib.load()
+    Cin, Cout, K, stride = geom
+    rng = np.random.RandomState(Cin + Cout + K)
+    w = (rng.randn(Cout, Cin, K) / np.sqrt(Cin * K)).astype(np.float32)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    n = L.fac_debug_tc_pack(P(w), Cin, Cout, K, stride, mode, None, 0)
+    if n < 0:
+        pytest.skip("geometry not eligible in this mode")
+    blob = np.zeros(n, np.float32)
+    assert L.fac_debug_tc_pack(P(w), Cin, Cout, K, stride, mode, P(blob), n) == n
+    out = (ctypes.c_int * 8)()
+    assert L.fac_debug_tc_plan(Cin, Cout, K, 1, stride, 0, mode, 0, out) == 0
+    N, nchunk = out[0], out[2]
+    Kr, vf = (K, 1) if stride == 1 else (2, stride)
+    # generic row-tap matrix the kernels contract over: Wg[tap][j][co], j = (sample-in-row, ci)
+    Wg = np.zeros((Kr, vf * Cin, Cout), np.float32)
+    for k in range(K):
+        Wg[k // vf, (k % vf) * Cin:(k % vf + 1) * Cin, :] = w[:, :, k].T
+    nt = Cout // N
+    if mode in (0, 1):
+        b = blob.reshape(nt, nchunk, Kr, 2, 4, N, 4)                 # [..][hl][k4][n][e]
+        hi = b[:, :, :, 0].transpose(0, 1, 2, 4, 3, 5).reshape(nt, nchunk, Kr, N, 16)
+        lo = b[:, :, :, 1].transpose(0, 1, 2, 4, 3, 5).reshape(nt, nchunk, Kr, N, 16)
+        assert not (hi.view(np.uint32) & 0x1FFF).any() and not (lo.view(np.uint32) & 0x1FFF).any()   # exact TF32
+        rec, tol = hi.astype(np.float64) + lo, 2.0 ** -20
+    else:
+        h16 = blob.view(np.uint16).reshape(nt, nchunk, Kr, 2, 2, N, 8)  # [..][hl][k8][n][e]
+        def dec(a):
+            a = a.transpose(0, 1, 2, 4, 3, 5).reshape(nt, nchunk, Kr, N, 16)
+            if mode == 2:
+                return (a.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+            return a.view(np.float16).astype(np.float64)
+        hi, lo = dec(np.ascontiguousarray(h16[:, :, :, 0])), dec(np.ascontiguousarray(h16[:, :, :, 1]))
+        rec = hi + (lo / 2048.0 if mode == 3 else lo)
+        tol = 2.0 ** -15 if mode == 2 else 2.0 ** -20
+    # rec[nt][chunk][tap][n][kk] == Wg[tap][chunk*16 + kk][nt*N + n]
+    ref = Wg.reshape(Kr, nchunk, 16, nt, N).transpose(3, 1, 0, 4, 2)
+    err = np.abs(rec - ref).max()
+    assert err <= tol * np.abs(ref).max(), (err, tol)
