@@ -5,7 +5,7 @@ D = os.path.join(ROOT, "profiles", "r01")
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6566.4, "bf16_tflops_sustained": 1439.1}
 out = ["# ncu summary, round 1 (B200, `--clock-control none`)\n",
        "Source files: `profiles/r01/*_raw.csv` (`ncu --set full ... --page raw --csv`), `*_details.txt`, "
-       "`launches_r01.csv` (`--metrics gpu__time_duration.sum`, one full B=32 x 4 s forward = 114 launches).\n",
+       "`launches_r01.csv` (`--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`, two full B=32 x 4 s forwards of 115 launches; the warm one is summarised), `layers_eventtimed_final.txt` (CUDA-event time of every call site, no profiler: `scripts/gpu_layer_profile.py`), `bench_1gpu.json` / `bench_2gpu.json` (bench.py lines), `memcheck_smoke.log` (compute-sanitizer, 0 errors).\n",
        "Captures taken from `scripts/ncu_target.py` (second forward). Numbers under ncu are cold-cache and serialised: "
        "use SHARES, not absolutes; bench numbers come from `bench.py` only.\n"]
 # launch list: ncu --csv "long" format, one row per (launch, metric)
