@@ -23,7 +23,7 @@ struct PadMap {
         m.Le = (reflect && L <= mp) ? mp + 1 : L;
         return m;
     }
-    __device__ __forceinline__ int src(int p) const {
+    __host__ __device__ __forceinline__ int src(int p) const {
         if (p >= 0 && p < L) return p;
         if (!reflect) return -1;
         int q = p < 0 ? -p : (p < Le ? p : 2 * Le - 2 - p);

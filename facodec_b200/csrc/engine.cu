@@ -1379,6 +1379,15 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
     return rc;
 }
 
+// Host-only: the padding index map every conv kernel uses (common.cuh PadMap): out[i] = source row of padded position
+// i - pad_left, or -1 where the padded value is zero.
+int fac_debug_pad_map(int L, int pad_left, int pad_right, int reflect, int* out, int n) {
+    if (!out || L < 0 || pad_left < 0 || pad_right < 0 || n != pad_left + L + pad_right) return FAC_ERR_INVALID;
+    const PadMap pm = PadMap::make(L, pad_left, pad_right, reflect);
+    for (int i = 0; i < n; ++i) out[i] = pm.src(i - pad_left);
+    return FAC_OK;
+}
+
 // Host-only: the tile plan the tcgen05 conv kernels would use for a layer geometry (no GPU, no handle).
 int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, int mode, int occ2_maxn, int* out8) {
     if (!out8 || Cin <= 0 || Cout <= 0 || K <= 0 || dil <= 0 || stride <= 0 || mode < 0 || mode > 5) return FAC_ERR_INVALID;

@@ -157,6 +157,10 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
  * [0] start, [1] all activation chunks produced, [2] GEMM 1 retired, [3] GEMM-2 operand produced (fused),
  * [4] GEMM 2 retired (fused), [5] epilogue done.  Kernel-tuning aid. */
 int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8);
+/* Host-only: the padding index map every conv kernel applies instead of materialising a padded copy
+ * (dac/model/encodec.py:96-113 pad1d incl. the short-input branch): out[i] = source row of padded position
+ * i - pad_left, or -1 where the padded value is zero; n must be pad_left + L + pad_right. */
+int fac_debug_pad_map(int L, int pad_left, int pad_right, int reflect, int* out, int n);
 /* Host-only (no GPU, no handle): the tile plan of the tcgen05 conv kernels for one layer geometry.  mode: 0 conv_tc TF32,
  * 1 conv_tcp (promoted) TF32, 2 conv_tc bf16, 3 conv_tcp fp16 hi + scaled lo, 4 fused ResidualUnit bf16, 5 fused TF32.
  * Tout may be 0 (unknown).  out8 = {N, MT, K chunks, weight-ring stages, TMEM columns, dynamic shared-memory bytes,

@@ -209,3 +209,24 @@ def test_tensor_core_weight_blob_layout_and_split(geom, mode, built_lib):
     ref = Wg.reshape(Kr, nchunk, 16, nt, N).transpose(3, 1, 0, 4, 2)
     err = np.abs(rec - ref).max()
     assert err <= tol * np.abs(ref).max(), (err, tol)
+
+
+@pytest.mark.parametrize("L,pl,pr", [(300, 6, 0), (40, 54, 0), (5, 6, 0), (7, 6, 2), (1, 6, 0), (55, 54, 3), (9000, 600, 600), (3, 18, 5)])
+def test_pad_index_map_matches_reference_pad1d(L, pl, pr, built_lib):
+    """Host logic (no GPU): the reflect-padding index map of the kernels == encodec.py:96-113 pad1d, including the
+    branch that zero-extends inputs shorter than the padding before reflecting (oracle restatement, pinned to the
+    reference by test_oracle.py)."""
+    import ctypes
+    import torch
+    from facodec_b200 import _lib
+    from oracle import facodec_oracle as O
+    Lb = _lib.load()
+    n = pl + L + pr
+    out = (ctypes.c_int * n)()
+    assert Lb.fac_debug_pad_map(L, pl, pr, 1, out, n) == 0
+    ramp = torch.arange(1, L + 1, dtype=torch.float32).view(1, 1, L)      # value i+1 marks source row i; 0 = zero fill
+    ref = O._pad1d_reflect(ramp, pl, pr).view(-1)
+    got = torch.tensor([0.0 if s < 0 else float(s + 1) for s in out])
+    assert torch.equal(got, ref)
+    assert Lb.fac_debug_pad_map(L, pl, pr, 0, out, n) == 0                  # zero padding
+    assert [s for s in out] == [-1] * pl + list(range(L)) + [-1] * pr
