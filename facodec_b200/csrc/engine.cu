@@ -1379,6 +1379,31 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
     return rc;
 }
 
+// Host-only: the recurrent-weight packing of lstm_rec_kernel for one nn.LSTM weight_hh [4H][H]:
+// bf16 = 0 -> fp32 [G][H][4U] (row r = gate*U + u of CTA g); bf16 = 1 -> [G][H/16][hi|lo][8 k-pairs][4U] 32-bit words.
+// Returns the number of 32-bit words (G*H*4U); info3 = {U, G, 4U}.
+long long fac_debug_lstm_pack(const float* whh_host, int H, int bf16, float* out, long long capacity_floats, int* info3) {
+    if (!whh_host || H <= 0) return FAC_ERR_INVALID;
+    fac_handle tmp;
+    const char* names[8] = {"weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0", "weight_ih_l1", "weight_hh_l1", "bias_ih_l1", "bias_hh_l1"};
+    for (int i = 0; i < 8; ++i) {
+        HostTensor t;
+        const bool mat = (i % 4) < 2;
+        if (mat) t.shape = {4 * H, H}; else t.shape = {4 * H};
+        if (i == 1) t.data.assign(whh_host, whh_host + (size_t)4 * H * H);
+        else t.data.assign(t.numel(), 0.f);
+        tmp.host[0][std::string("l.") + names[i]] = std::move(t);
+    }
+    LstmW L;
+    try { L = pack_lstm(&tmp, 0, "l"); } catch (const PackError&) { return FAC_ERR_UNSUPPORTED; }
+    const long long n = (long long)L.G * H * 4 * L.U;
+    if (info3) { info3[0] = L.U; info3[1] = L.G; info3[2] = 4 * L.U; }
+    if (bf16 && !L.has16) return FAC_ERR_UNSUPPORTED;
+    if (!out || capacity_floats < n) return n;
+    memcpy(out, tmp.pack.data() + (bf16 ? L.whh16[0] : L.whh[0]), sizeof(float) * (size_t)n);
+    return n;
+}
+
 // Host-only: the padding index map every conv kernel uses (common.cuh PadMap): out[i] = source row of padded position
 // i - pad_left, or -1 where the padded value is zero.
 int fac_debug_pad_map(int L, int pad_left, int pad_right, int reflect, int* out, int n) {

@@ -157,6 +157,11 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
  * [0] start, [1] all activation chunks produced, [2] GEMM 1 retired, [3] GEMM-2 operand produced (fused),
  * [4] GEMM 2 retired (fused), [5] epilogue done.  Kernel-tuning aid. */
 int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8);
+/* Host-only: the recurrent-weight packing of lstm_rec_kernel for one nn.LSTM weight_hh [4H][H] (HOST, gate order
+ * i,f,g,o): bf16 = 0 -> fp32 [G][H][4U] (row r = gate*U + u of the CTA owning hidden units g*U..g*U+U-1);
+ * bf16 = 1 -> [G][H/16][hi|lo][8 k-pairs][4U] words of two bf16 (even k in the low half), lo = rn_bf16(w - hi).
+ * Returns the number of 32-bit words (G*H*4U) also when out is NULL/too small; info3 = {U, G, 4U}. */
+long long fac_debug_lstm_pack(const float* whh_host, int H, int bf16, float* out, long long capacity_floats, int* info3);
 /* Host-only: the padding index map every conv kernel applies instead of materialising a padded copy
  * (dac/model/encodec.py:96-113 pad1d incl. the short-input branch): out[i] = source row of padded position
  * i - pad_left, or -1 where the padded value is zero; n must be pad_left + L + pad_right. */

@@ -230,3 +230,36 @@ def test_pad_index_map_matches_reference_pad1d(L, pl, pr, built_lib):
     assert torch.equal(got, ref)
     assert Lb.fac_debug_pad_map(L, pl, pr, 0, out, n) == 0                  # zero padding
     assert [s for s in out] == [-1] * pl + list(range(L)) + [-1] * pr
+
+
+@pytest.mark.parametrize("H", [1024, 1536])
+def test_lstm_recurrent_weight_packing(H, built_lib):
+    """Host logic (no GPU): W_hh [4H][H] -> per-CTA slices.  fp32 layout: CTA g holds rows gate*U + u = W[gate*H + g*U + u]
+    as [k][4U]; bf16 layout: the same slice as hi/lo words of two consecutive k (hi + lo reproduces w to 2^-16)."""
+    import ctypes
+    import numpy as np
+    from facodec_b200 import _lib
+    L = _lib.load()
+    rng = np.random.RandomState(H)
+    w = (rng.uniform(-1, 1, size=(4 * H, H)) / np.sqrt(H)).astype(np.float32)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    info = (ctypes.c_int * 3)()
+    n = L.fac_debug_lstm_pack(P(w), H, 0, None, 0, info)
+    U, G, R = info[0], info[1], info[2]
+    assert n == G * H * R and G * U == H and R == 4 * U and G <= 132
+    f = np.zeros(n, np.float32)
+    assert L.fac_debug_lstm_pack(P(w), H, 0, P(f), n, info) == n
+    f = f.reshape(G, H, 4, U)                                              # [g][k][gate][u]
+    ref = w.reshape(4, G, U, H).transpose(1, 3, 0, 2)                      # W[gate*H + g*U + u][k] -> [g][k][gate][u]
+    assert np.array_equal(f, ref)
+    b = np.zeros(n, np.float32)
+    assert L.fac_debug_lstm_pack(P(w), H, 1, P(b), n, info) == n
+    words = b.view(np.uint32).reshape(G, H // 16, 2, 8, R)                 # [g][sub][hl][k2][r]
+    def bf(x):
+        return (x.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    lo_half, hi_half = words & 0xFFFF, words >> 16                         # even k in the low half
+    val = np.stack([bf(lo_half), bf(hi_half)], axis=-1)                    # [g][sub][hl][k2][r][parity]
+    rec = val[:, :, 0] + val[:, :, 1]                                      # hi + lo -> [g][sub][k2][r][parity]
+    rec = rec.transpose(0, 1, 2, 4, 3).reshape(G, H, R)                    # k = sub*16 + 2*k2 + parity
+    ref2 = ref.reshape(G, H, R).astype(np.float64)
+    assert np.abs(rec - ref2).max() <= 2.0 ** -16 * np.abs(ref2).max()
