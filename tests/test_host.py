@@ -263,3 +263,40 @@ def test_lstm_recurrent_weight_packing(H, built_lib):
     rec = rec.transpose(0, 1, 2, 4, 3).reshape(G, H, R)                    # k = sub*16 + 2*k2 + parity
     ref2 = ref.reshape(G, H, R).astype(np.float64)
     assert np.abs(rec - ref2).max() <= 2.0 ** -16 * np.abs(ref2).max()
+
+
+def test_header_is_plain_c_and_links_from_c(built_lib, tmp_path):
+    """The boundary is a C ABI: include/facodec_b200.h must compile as C99 and a C program must be able to link the
+    library and call it (host-only entry points, so this runs without a GPU)."""
+    import os
+    import shutil
+    import subprocess
+    from facodec_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = _lib.lib_path()
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "facodec_b200.h"
+int main(void) {
+    int plan[8];
+    int pad[9];
+    if (fac_abi_version() != 1) return 2;
+    if (fac_debug_tc_plan(192, 192, 7, 9, 1, 48000, 4, 256, plan) != FAC_OK) return 3;
+    if (fac_debug_pad_map(3, 6, 0, 1, pad, 9) != FAC_OK) return 4;
+    if (fac_encode_frames(96000) != 320) return 5;
+    printf("%d %d %d %d\n", plan[0], plan[1], plan[4], pad[0]);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), lib,
+           "-Wl,-rpath," + os.path.dirname(lib)]
+    subprocess.check_call(cmd)
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = "/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.check_output([str(exe)], env=env, text=True).split()
+    assert out[:3] == ["192", "1", "512"]        # fused C = 192 unit: N = 192, MT = 1, 512 TMEM columns
