@@ -20,9 +20,11 @@ __global__ void __launch_bounds__(AA_TILE) alias_free_act_kernel(const float* __
     __shared__ float f[12];
     __shared__ float xs[AA_TILE + 16];          // x[t0-8 .. t0+AA_TILE+8)
     __shared__ float us[2 * AA_TILE + 16];      // u[2 t0 - 5 .. 2 t0 + 2 AA_TILE + 6]
-    const int row = blockIdx.y;                 // b * C + c
-    const int c = row % C;
-    const int t0 = blockIdx.x * AA_TILE;
+    const int ntile = (T + AA_TILE - 1) / AA_TILE;
+    const long long blk = blockIdx.x;           // row-major over (b * C + c, time tile): no 65535 limit on B * C
+    const long long row = blk / ntile;          // b * C + c
+    const int c = (int)(row % C);
+    const int t0 = (int)(blk - row * ntile) * AA_TILE;
     const float* xr = x + (size_t)row * T;
     if (threadIdx.x < 12) f[threadIdx.x] = filt[threadIdx.x];
     for (int i = threadIdx.x; i < AA_TILE + 16; i += AA_TILE) {
@@ -67,8 +69,10 @@ __global__ void __launch_bounds__(AA_TILE) alias_free_act_kernel(const float* __
 
 cudaError_t launch_alias_free_act(const float* x, float* y, int B, int C, int T, const float* filt12, const float* alpha,
                                   const float* beta, cudaStream_t st) {
-    dim3 grid((T + AA_TILE - 1) / AA_TILE, B * C);
-    alias_free_act_kernel<<<grid, AA_TILE, 0, st>>>(x, y, C, T, filt12, alpha, beta);
+    const long long nblk = (long long)((T + AA_TILE - 1) / AA_TILE) * B * C;
+    if (nblk <= 0) return cudaSuccess;
+    if (nblk > 0x7fffffffLL) return cudaErrorInvalidValue;
+    alias_free_act_kernel<<<(unsigned)nblk, AA_TILE, 0, st>>>(x, y, C, T, filt12, alpha, beta);
     return cudaGetLastError();
 }
 

@@ -35,6 +35,7 @@
 #include <cuda_fp16.h>
 
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -1314,37 +1315,49 @@ cudaError_t tc_read_phase_clocks(long long* out8) {
     return cudaMemcpyFromSymbol(out8, g_tc_phase_clock, sizeof(long long) * 8);
 }
 
+// Function attributes (the > 48 KB dynamic shared-memory opt-in) and the SM count are PER DEVICE: a process may hold
+// handles on several GPUs (fac_create(out, device)), so both are tracked per device id under a mutex.
+namespace {
+struct DevCfg { bool done = false; int sm_count = 0; };
+DevCfg g_devcfg[64];
+std::mutex g_devcfg_mu;
+cudaError_t ensure_device_config(int& sm_count) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(g_devcfg_mu);
+    DevCfg& d = g_devcfg[dev];
+    if (!d.done) {
+        const int cap = 225 * 1024;
+        e = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e != cudaSuccess) return e;
+        if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sm_count <= 0) d.sm_count = 148;
+        d.done = true;
+    }
+    sm_count = d.sm_count;
+    return cudaSuccess;
+}
+}  // namespace
+
 cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
     if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
-    static size_t configured = 0;
-    if (p.smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-        if (e != cudaSuccess) return e;
-        configured = 225 * 1024;
-    }
+    int sm_count = 148;
+    cudaError_t e0 = ensure_device_config(sm_count);
+    if (e0 != cudaSuccess) return e0;
     dim3 grid((p.Tout + 128 * p.MT - 1) / (128 * p.MT), p.Cout / p.N, p.B);
     if (p.promoted) {
-        static bool configured_p = false;
-        if (!configured_p) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-            if (e != cudaSuccess) return e;
-            configured_p = true;
-        }
-        static int sm_count = 0;
-        if (sm_count == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
-        }
         const long long ntiles = (long long)grid.x * grid.y * grid.z;
         const unsigned nctas = (unsigned)(ntiles < sm_count ? ntiles : sm_count);   // persistent: one CTA per SM
         if (p.f16x2) conv_tcp_kernel<true><<<dim3(nctas), tc::kThreadsP, p.smem_bytes, st>>>(p);
         else conv_tcp_kernel<false><<<dim3(nctas), tc::kThreadsP, p.smem_bytes, st>>>(p);
     } else {
+        if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
         if (p.fused && p.bf16) conv_tc_kernel<true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.fused) conv_tc_kernel<true, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.bf16) conv_tc_kernel<false, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);

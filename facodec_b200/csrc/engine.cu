@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/facodec_b200.h"
+#include "../../include/facodec_b200_debug.h"
 #include "common.cuh"
 #include "kernels.h"
 

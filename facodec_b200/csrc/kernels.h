@@ -131,11 +131,13 @@ cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st);
 
 // elementwise / small ops
 cudaError_t launch_transpose(const float* in, float* out, int B, int R, int C, cudaStream_t st);  // [B][R][C]->[B][C][R]
-cudaError_t launch_wn_gate(const float* xin, float* acts, size_t n_rows, int hidden, cudaStream_t st);  // tanh(a)*sigmoid(b)
+// tanh(a + g_a) * sigmoid(b + g_b); g = null or one [2*hidden] conditioning row per utterance (rows_per_utt rows each, g_stride floats apart)
+cudaError_t launch_wn_gate(const float* xin, float* acts, size_t n_rows, int hidden, cudaStream_t st, const float* g = nullptr,
+                           size_t rows_per_utt = 0, size_t g_stride = 0);
 cudaError_t launch_wn_update(const float* rs, float* x, float* out, size_t n_rows, int hidden, int last, cudaStream_t st);
 cudaError_t launch_glu_res(const float* y, float* x, int B, int T, int C, const int* valid_len, cudaStream_t st);  // x = x + y1*sig(y2) (masked)
 cudaError_t launch_attention(const float* q, const float* k, const float* v, float* o, int B, int T, int heads,
-                             int dk, const int* valid_len, cudaStream_t st);
+                             int dk, const int* valid_len, cudaStream_t st, int force_stream = 0);
 cudaError_t launch_mean_pool(const float* x, float* out, int B, int T, int C, const int* valid_len, cudaStream_t st);
 cudaError_t launch_fill_u32(unsigned int* p, unsigned int v, size_t n, cudaStream_t st);
 

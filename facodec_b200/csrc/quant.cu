@@ -289,25 +289,39 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 }
 cudaError_t launch_transpose(const float* in, float* out, int B, int R, int C, cudaStream_t st) {
     if (B <= 0 || R <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid((C + 31) / 32, (R + 31) / 32, B), block(32, 8);
-    transpose_kernel<<<grid, block, 0, st>>>(in, out, R, C);
+    if ((R + 31) / 32 > 65535) return cudaErrorInvalidValue;
+    dim3 block(32, 8);
+    for (int b0 = 0; b0 < B; b0 += 65535) {     // grid.z is limited to 65535
+        const int nb = B - b0 < 65535 ? B - b0 : 65535;
+        dim3 grid((C + 31) / 32, (R + 31) / 32, nb);
+        transpose_kernel<<<grid, block, 0, st>>>(in + (size_t)b0 * R * C, out + (size_t)b0 * R * C, R, C);
+    }
     return cudaGetLastError();
 }
 
-// fused_add_tanh_sigmoid_multiply (modules/commons.py:113-120) with g = 0
-__global__ void wn_gate_kernel(const float* __restrict__ xin, float* __restrict__ acts, size_t n_rows, int hidden) {
+// fused_add_tanh_sigmoid_multiply (modules/commons.py:113-120): acts = tanh(x_in[:H] + g_l[:H]) * sigmoid(x_in[H:] + g_l[H:]).
+// g (or null = zeros, the codec's own WN call) is the layer's slice of cond_layer(g) (modules/wavenet.py:143-151): one
+// [2H] row per utterance, utterance = row / rows_per_utt, consecutive utterances g_stride floats apart.
+__global__ void wn_gate_kernel(const float* __restrict__ xin, float* __restrict__ acts, size_t n_rows, int hidden,
+                               const float* __restrict__ g, size_t rows_per_utt, size_t g_stride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows * hidden) return;
     size_t row = i / hidden;
     int c = (int)(i - row * hidden);
-    float a = xin[row * 2 * hidden + c] + 0.0f;
-    float s = xin[row * 2 * hidden + hidden + c] + 0.0f;
+    float ga = 0.0f, gs = 0.0f;
+    if (g) {
+        const float* gr = g + (row / rows_per_utt) * g_stride;
+        ga = gr[c]; gs = gr[hidden + c];
+    }
+    float a = xin[row * 2 * hidden + c] + ga;
+    float s = xin[row * 2 * hidden + hidden + c] + gs;
     acts[i] = tanhf(a) * sigmoid_f(s);
 }
-cudaError_t launch_wn_gate(const float* xin, float* acts, size_t n_rows, int hidden, cudaStream_t st) {
+cudaError_t launch_wn_gate(const float* xin, float* acts, size_t n_rows, int hidden, cudaStream_t st, const float* g,
+                           size_t rows_per_utt, size_t g_stride) {
     size_t n = n_rows * hidden;
     if (n == 0) return cudaSuccess;
-    wn_gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xin, acts, n_rows, hidden);
+    wn_gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xin, acts, n_rows, hidden, g, rows_per_utt ? rows_per_utt : 1, g_stride);
     return cudaGetLastError();
 }
 // WN.forward residual/skip split, modules/wavenet.py:159-165
@@ -453,15 +467,119 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
         }
     }
 }
+// Long sequences (the [16][T] score block above no longer fits shared memory, T > ~2700 frames = 34 s): same
+// attention with the scores RECOMPUTED instead of stored.  Pass 1 walks the key tiles keeping a running row maximum and
+// the sum of exp(s - max) (rescaled when the maximum moves); pass 2 recomputes each tile's scores, normalises them and
+// accumulates P V.  Shared memory no longer depends on T; the probabilities differ from the stored-score kernel only by
+// the rescaling round-off (~1e-7 relative).
+__global__ void __launch_bounds__(256) attention_stream_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                               const float* __restrict__ v, float* __restrict__ o, int T,
+                                                               int heads, const int* __restrict__ valid_len) {
+    extern __shared__ __align__(16) float sm[];
+    float* qs = sm;                              // [16][256]
+    float* tile = qs + ATT_Q * ATT_DK;           // [32][257]
+    float* pt = tile + 32 * (ATT_DK + 1);        // [16][32] probabilities of the current key tile
+    const int C = heads * ATT_DK;
+    const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
+    const int q0 = blockIdx.x * ATT_Q;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int vlen = valid_len ? valid_len[b] : T;
+    const float* qb = q + (size_t)b * T * C + h * ATT_DK;
+    const float* kb = k + (size_t)b * T * C + h * ATT_DK;
+    const float* vb = v + (size_t)b * T * C + h * ATT_DK;
+    for (int i = tid; i < ATT_Q * ATT_DK; i += 256) {
+        int qi = i / ATT_DK, d = i % ATT_DK;
+        int t = q0 + qi;
+        qs[i] = (t < T) ? qb[(size_t)t * C + d] * (1.0f / 16.0f) : 0.f;
+    }
+    auto load_tile = [&](const float* base, int s0) {
+        for (int i = tid; i < 32 * ATT_DK; i += 256) {
+            int r = i / ATT_DK, d = i % ATT_DK;
+            tile[r * (ATT_DK + 1) + d] = (s0 + r < T) ? base[(size_t)(s0 + r) * C + d] : 0.f;
+        }
+    };
+    auto score = [&](int qi, int s0) {           // masked score of (query qi, key s0 + lane); -inf beyond T
+        float acc = 0.f;
+        const float* qr = qs + qi * ATT_DK;
+        const float* kr = tile + lane * (ATT_DK + 1);
+#pragma unroll 8
+        for (int d = 0; d < ATT_DK; ++d) acc = fmaf(qr[d], kr[d], acc);
+        const int s = s0 + lane;
+        if (s >= T) return -3.0e38f;
+        return ((q0 + qi < vlen) && (s < vlen)) ? acc : -1e4f;
+    };
+    float mrow[2] = {-3.0e38f, -3.0e38f}, lrow[2] = {0.f, 0.f};
+    for (int s0 = 0; s0 < T; s0 += 32) {
+        __syncthreads();
+        load_tile(kb, s0);
+        __syncthreads();
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+            const float sc = score(warp * 2 + qq, s0);
+            float mx = sc;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float mnew = fmaxf(mrow[qq], mx);
+            const float e = (s0 + lane < T) ? expf(sc - mnew) : 0.f;
+            lrow[qq] = lrow[qq] * expf(mrow[qq] - mnew) + warp_sum(e);
+            mrow[qq] = mnew;
+        }
+    }
+    float acc[2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+    const float inv0 = 1.0f / lrow[0], inv1 = 1.0f / lrow[1];
+    for (int s0 = 0; s0 < T; s0 += 32) {
+        __syncthreads();
+        load_tile(kb, s0);
+        __syncthreads();
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+            const float sc = score(warp * 2 + qq, s0);
+            pt[(warp * 2 + qq) * 32 + lane] = (s0 + lane < T) ? expf(sc - mrow[qq]) * (qq ? inv1 : inv0) : 0.f;
+        }
+        __syncthreads();
+        load_tile(vb, s0);
+        __syncthreads();
+        const int smax = min(32, T - s0);
+        for (int s = 0; s < smax; ++s) {
+            const float* vr = tile + s * (ATT_DK + 1);
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+                const float pw = pt[(warp * 2 + qq) * 32 + s];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[qq][j] = fmaf(pw, vr[lane + 32 * j], acc[qq][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq) {
+        int t = q0 + warp * 2 + qq;
+        if (t < T) {
+            float* ob = o + ((size_t)b * T + t) * C + h * ATT_DK;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ob[lane + 32 * j] = acc[qq][j];
+        }
+    }
+}
 cudaError_t launch_attention(const float* q, const float* k, const float* v, float* o, int B, int T, int heads, int dk,
-                             const int* valid_len, cudaStream_t st) {
+                             const int* valid_len, cudaStream_t st, int force_stream) {
     if (dk != ATT_DK) return cudaErrorInvalidValue;
     if (B <= 0 || T <= 0) return cudaSuccess;
+    if ((long long)B * heads > 65535) return cudaErrorInvalidValue;
     size_t smem = sizeof(float) * ((size_t)ATT_Q * ATT_DK + 32 * (ATT_DK + 1) + (size_t)ATT_Q * T);
-    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    dim3 grid((T + ATT_Q - 1) / ATT_Q, B * heads);
+    if (smem > 200 * 1024 || force_stream) {
+        smem = sizeof(float) * ((size_t)ATT_Q * ATT_DK + 32 * (ATT_DK + 1) + (size_t)ATT_Q * 32);
+        cudaError_t e = cudaFuncSetAttribute(attention_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attention_stream_kernel<<<grid, 256, smem, st>>>(q, k, v, o, T, heads, valid_len);
+        return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((T + ATT_Q - 1) / ATT_Q, B * heads);
     attention_kernel<<<grid, 256, smem, st>>>(q, k, v, o, T, heads, valid_len);
     return cudaGetLastError();
 }

@@ -10,18 +10,26 @@ import torch
 from conftest import ROOT
 
 
-def test_library_exports_every_declared_symbol(built_lib):
-    hdr = open(os.path.join(ROOT, "include", "facodec_b200.h")).read()
+def _declared(header):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = sorted(set(re.findall(r"\b(fac_[a-z_0-9]+)\s*\(", hdr)))
-    assert len(declared) >= 15
+    return sorted(set(re.findall(r"\b(fac_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    """include/facodec_b200.h is the drop-in surface and holds no test hook; the kernel-level hooks and
+    the profiling calls live in include/facodec_b200_debug.h.  Every symbol either header declares is exported."""
+    public, debug = _declared("facodec_b200.h"), _declared("facodec_b200_debug.h")
+    assert len(public) >= 15
+    assert not [n for n in public if n.startswith(("fac_debug_", "fac_profile_"))]
+    assert all(n.startswith(("fac_debug_", "fac_profile_")) for n in debug)
     lib = ctypes.CDLL(built_lib)
-    for name in declared:
-        assert hasattr(lib, name), f"{name} declared in include/facodec_b200.h but not exported"
+    for name in public + debug:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     from facodec_b200 import _lib
-    assert sorted(_lib.EXPORTED) == declared
+    assert sorted(_lib.EXPORTED) == sorted(public + debug)
     L = _lib.load()
-    assert L.fac_abi_version() == 1
+    assert L.fac_abi_version() == 2
 
 
 def test_encode_frames_matches_reference_rule(built_lib):
@@ -281,10 +289,11 @@ def test_header_is_plain_c_and_links_from_c(built_lib, tmp_path):
     src.write_text(r'''
 #include <stdio.h>
 #include "facodec_b200.h"
+#include "facodec_b200_debug.h"
 int main(void) {
     int plan[8];
     int pad[9];
-    if (fac_abi_version() != 1) return 2;
+    if (fac_abi_version() != 2) return 2;
     if (fac_debug_tc_plan(192, 192, 7, 9, 1, 48000, 4, 256, plan) != FAC_OK) return 3;
     if (fac_debug_pad_map(3, 6, 0, 1, pad, 9) != FAC_OK) return 4;
     if (fac_encode_frames(96000) != 320) return 5;
