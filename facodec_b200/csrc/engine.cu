@@ -39,6 +39,7 @@ struct ConvW {
     bool tc = false; size_t tcw = 0; int vf = 1, Kr = 0, tcN = 0;   // tcN: channel tile the blob was laid out for
     bool promoted = false;   // blob built for conv_tcp_kernel (layers upstream of the VQ)
     bool has16 = false; size_t tcw16 = 0;   // 16-bit-operand blob: bf16 hi/lo (non-promoted layers) or fp16 hi / scaled lo (promoted)
+    bool has_tt = false; size_t tcw_tt = 0; // transposed-formulation blob (conv_tt_kernel, promoted layers): [co tile of 128][chunk][tap][hi|lo']
 };
 struct SnakeW { size_t a = 0, ia = 0; int C = 0; };
 struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; size_t whh16[2] = {0, 0}; bool has16 = false; int H = 0, U = 0, G = 0; };
@@ -83,6 +84,9 @@ struct fac_handle {
     int use_tc = 2;
     int fuse_res = 1;               // fused ResidualUnit launches (fac_set_option "fuse_resunit"); 2 = only where the
                                     // fused tile still allows two CTAs per SM (C <= 128)
+    int enc_mufu = 0;               // fac_set_option "encoder_snake_mufu" (experiment)
+    int attn_stream = 0;            // fac_set_option "attention_stream": 1 forces the recomputing attention kernel (test aid)
+    int enc_tt = 1;                 // fac_set_option "encoder_tt": promoted layers run the transposed kernel (conv_tt_kernel)
     int enc_f16 = 0;                // fac_set_option "encoder_f16x2": promoted layers use the fp16 hi + scaled-lo split
     int tc_occ2 = 256;              // fac_set_option "tc_occ2_maxn": conv_tc tiles with N <= this are planned for two CTAs per SM (0 = off)
     bool dec_bf16 = true;           // decoder-side layers use the bf16x3 split (fac_set_option "decoder_bf16")
@@ -156,6 +160,12 @@ void attach_tc(fac_handle* h, ConvW& c, int stride, bool promoted) {
     tc_pack_blob(tp, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw);
     c.tc = true;
     if (promoted) {
+        TcConvParams tt = tp;
+        if (tt_conv_plan(tt)) {
+            c.tcw_tt = pack_alloc(h, tt_blob_floats(tt));
+            tt_pack_blob(tt, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw_tt);
+            c.has_tt = true;
+        }
         TcConvParams t16 = tp;
         t16.f16x2 = 1;
         if (tc_conv_plan(t16) && t16.N == tp.N) {
@@ -534,8 +544,10 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
         tp.f16x2 = (tp.promoted && c.h->enc_f16 && w.has16) ? 1 : 0;
         tp.occ2_maxn = c.h->tc_occ2;
         tp.Tout = Tout;
-        if (tc_conv_plan(tp)) {
-            tp.x = x; tp.y = y; tp.wblob = c.W((tp.bf16 || tp.f16x2) ? w.tcw16 : w.tcw); tp.bias = c.W(w.b);
+        const bool use_tt = tp.promoted && c.h->enc_tt && w.has_tt;
+        tp.snake_mufu = c.h->enc_mufu;
+        if (use_tt ? tt_conv_plan(tp) : tc_conv_plan(tp)) {
+            tp.x = x; tp.y = y; tp.wblob = c.W(use_tt ? w.tcw_tt : ((tp.bf16 || tp.f16x2) ? w.tcw16 : w.tcw)); tp.bias = c.W(w.b);
             if (o.in_snake) { tp.in_alpha = c.W(o.in_snake->a); tp.in_inv_alpha = c.W(o.in_snake->ia); }
             tp.out_act = o.act;
             if (o.out_snake) { tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(o.out_snake->a); tp.out_inv_alpha = c.W(o.out_snake->ia); }
@@ -549,9 +561,9 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
             double bytes = 4.0 * ((double)B * Tin * w.Cin + (double)B * Tout * w.Cout * (o.res ? 2 : 1) + (double)w.K * w.Cin * w.Cout);
             char det[96];
             snprintf(det, sizeof det, "%s Cin%d Cout%d K%d d%d T%d", name, w.Cin, w.Cout, w.K, o.dil, Tout);
-            c.begin(tp.promoted ? "conv_tcp" : "conv_tc", flops, bytes, det);
+            c.begin(use_tt ? "conv_tt" : (tp.promoted ? "conv_tcp" : "conv_tc"), flops, bytes, det);
             (void)short_chain;
-            c.check(launch_conv_tc(tp, c.st), name);
+            c.check(use_tt ? launch_conv_tt(tp, c.st) : launch_conv_tc(tp, c.st), name);
             c.end();
             return;
         }
@@ -804,7 +816,7 @@ void style_encoder(Ctx& c, const float* mel, int B, int Tm, const int* vlen, flo
     run_conv(c, q.cq, x, qb, B, Tm, Tm, p, "se.q");
     run_conv(c, q.ck, x, kb, B, Tm, Tm, p, "se.k");
     run_conv(c, q.cv, x, vb, B, Tm, Tm, p, "se.v");
-    if (!c.dry) c.check(launch_attention(qb, kb, vb, ob, B, Tm, 2, 256, vlen, c.st), "se.attn");
+    if (!c.dry) c.check(launch_attention(qb, kb, vb, ob, B, Tm, 2, 256, vlen, c.st, c.h->attn_stream), "se.attn");
     ConvOpts r;
     r.res = x;
     run_conv(c, q.co, ob, a, B, Tm, Tm, r, "se.o");          // a = x + conv_o(attn)
@@ -952,7 +964,7 @@ int two_pass(fac_handle* h, cudaStream_t st, F body) {
 // ==========================================================================================
 extern "C" {
 
-int fac_abi_version(void) { return 1; }
+int fac_abi_version(void) { return 2; }
 
 int fac_create(fac_handle** out, int device) {
     if (!out) return FAC_ERR_INVALID;
@@ -1277,6 +1289,10 @@ int fac_set_option(fac_handle* h, const char* name, int value) {
     if (std::string(name) == "fuse_resunit") { h->fuse_res = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     if (std::string(name) == "tc_occ2_maxn") { h->tc_occ2 = value < 0 ? 0 : value; return FAC_OK; }
     if (std::string(name) == "encoder_f16x2") { h->enc_f16 = value != 0; return FAC_OK; }
+    if (std::string(name) == "encoder_tt") { h->enc_tt = value != 0; return FAC_OK; }
+    if (std::string(name) == "encoder_snake_mufu") { h->enc_mufu = value != 0; return FAC_OK; }
+    if (std::string(name) == "tt_probe") { g_tt_probe_on = value != 0; return FAC_OK; }
+    if (std::string(name) == "attention_stream") { h->attn_stream = value != 0; return FAC_OK; }
     if (std::string(name) == "decoder_bf16") { h->dec_bf16 = value != 0; return FAC_OK; }
     if (std::string(name) == "tensor_cores") { h->use_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     h->err = std::string("unknown option ") + name;
@@ -1293,22 +1309,24 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
     TcConvParams tp;
     tp.Cin = Cin; tp.Cout = Cout; tp.promoted = (promoted == 1 || promoted == 3) ? 1 : 0; tp.bf16 = promoted == 2 ? 1 : 0;
     tp.f16x2 = promoted == 3 ? 1 : 0;
+    const bool use_tt = promoted == 4;
     tp.occ2_maxn = h->tc_occ2;
     tp.Tout = Tout;
     if (stride == 1) { tp.vf = 1; tp.Kr = K; tp.dil = dil; }
     else if (K == 2 * stride && dil == 1) { tp.vf = stride; tp.Kr = 2; tp.dil = 1; }
     else { h->err = "fac_debug_conv_tc: unsupported stride/kernel"; return FAC_ERR_UNSUPPORTED; }
-    if (!tc_conv_plan(tp)) { h->err = "fac_debug_conv_tc: layer not eligible for the tensor-core path"; return FAC_ERR_UNSUPPORTED; }
+    if (!(use_tt ? tt_conv_plan(tp) : tc_conv_plan(tp))) { h->err = "fac_debug_conv_tc: layer not eligible for the tensor-core path"; return FAC_ERR_UNSUPPORTED; }
     int ldw = (Cout + 3) / 4 * 4;
     std::vector<float> gen((size_t)K * Cin * ldw, 0.f);
     for (int co = 0; co < Cout; ++co)
         for (int ci = 0; ci < Cin; ++ci)
             for (int k = 0; k < K; ++k) gen[((size_t)k * Cin + ci) * ldw + co] = w_host[((size_t)co * Cin + ci) * K + k];
-    size_t nb = tc_blob_floats(tp);
+    size_t nb = use_tt ? tt_blob_floats(tp) : tc_blob_floats(tp);
     auto al4 = [](size_t v) { return (v + 3) / 4 * 4; };
     size_t o_b = al4(nb), o_ia = al4(o_b + Cout), o_iia = al4(o_ia + Cin), o_oa = al4(o_iia + Cin), o_oia = al4(o_oa + Cout);
     std::vector<float> pk(o_oia + Cout + 16, 0.f);
-    tc_pack_blob(tp, gen.data(), ldw, pk.data());
+    if (use_tt) tt_pack_blob(tp, gen.data(), ldw, pk.data());
+    else tc_pack_blob(tp, gen.data(), ldw, pk.data());
     for (int i = 0; i < Cout; ++i) pk[o_b + i] = bias_host ? bias_host[i] : 0.f;
     for (int i = 0; i < Cin; ++i) { pk[o_ia + i] = in_alpha_host ? in_alpha_host[i] : 1.f; pk[o_iia + i] = 1.0f / (pk[o_ia + i] + 1e-9f); }
     for (int i = 0; i < Cout; ++i) { pk[o_oa + i] = out_alpha_host ? out_alpha_host[i] : 1.f; pk[o_oia + i] = 1.0f / (pk[o_oa + i] + 1e-9f); }
@@ -1326,7 +1344,7 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
     tp.pad_left_s = pad_left; tp.pad_right_s = pad_right; tp.reflect = reflect;
     tp.Tout = Tout; tp.ldy = Cout;
     tp.x_bstride = (size_t)Tin * Cin; tp.y_bstride = (size_t)Tout * Cout;
-    e = launch_conv_tc(tp, st);
+    e = use_tt ? launch_conv_tt(tp, st) : launch_conv_tc(tp, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);
     if (e != cudaSuccess) { h->err = std::string("fac_debug_conv_tc: ") + cudaGetErrorString(e); return FAC_ERR_CUDA; }
@@ -1416,7 +1434,7 @@ int fac_debug_pad_map(int L, int pad_left, int pad_right, int reflect, int* out,
 
 // Host-only: the tile plan the tcgen05 conv kernels would use for a layer geometry (no GPU, no handle).
 int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, int mode, int occ2_maxn, int* out8) {
-    if (!out8 || Cin <= 0 || Cout <= 0 || K <= 0 || dil <= 0 || stride <= 0 || mode < 0 || mode > 5) return FAC_ERR_INVALID;
+    if (!out8 || Cin <= 0 || Cout <= 0 || K <= 0 || dil <= 0 || stride <= 0 || mode < 0 || mode > 6) return FAC_ERR_INVALID;
     TcConvParams tp;
     tp.Cin = Cin; tp.Cout = Cout; tp.Tout = Tout; tp.occ2_maxn = occ2_maxn;
     tp.promoted = (mode == 1 || mode == 3) ? 1 : 0;
@@ -1426,6 +1444,13 @@ int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, i
     if (stride == 1) { tp.vf = 1; tp.Kr = K; tp.dil = dil; }
     else if (K == 2 * stride && dil == 1) { tp.vf = stride; tp.Kr = 2; tp.dil = 1; }
     else return FAC_ERR_UNSUPPORTED;
+    if (mode == 6) {
+        tp.promoted = 0; tp.bf16 = 0; tp.f16x2 = 0; tp.fused = 0;
+        if (!tt_conv_plan(tp)) return FAC_ERR_UNSUPPORTED;
+        out8[0] = tp.N; out8[1] = tp.NT; out8[2] = tp.nchunk; out8[3] = tp.stagesB; out8[4] = tp.tmem_cols;
+        out8[5] = (int)tp.smem_bytes; out8[6] = tp.Rpad; out8[7] = tp.promote_every;
+        return FAC_OK;
+    }
     if (!tc_conv_plan(tp)) return FAC_ERR_UNSUPPORTED;
     out8[0] = tp.N; out8[1] = tp.MT; out8[2] = tp.nchunk; out8[3] = tp.stagesB; out8[4] = tp.tmem_cols;
     out8[5] = (int)tp.smem_bytes; out8[6] = tp.Rpad; out8[7] = tp.promote_every;
@@ -1459,7 +1484,7 @@ int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8) {
     if (!h || !out8) return FAC_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    cudaError_t e = tc_read_phase_clocks(out8);
+    cudaError_t e = g_tt_probe_on ? tt_read_probe(out8) : tc_read_phase_clocks(out8);
 
     if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
     return FAC_OK;

@@ -45,6 +45,10 @@ struct TcConvParams {
     int promoted = 0;                  // 1 = conv_tcp_kernel (register-promoted accumulation)
     int bf16 = 0;                      // 1 = bf16 hi/lo split (kind::f16, K = 16) instead of tf32 hi/lo; decoder only
     int f16x2 = 0;                     // promoted only: fp16 hi + 2^11-scaled fp16 lo split (kind::f16, K = 16) instead of tf32 hi/lo
+    int tt = 0;                        // 1 = conv_tt_kernel: transposed formulation (weights = MMA A operand, M = 128 output
+                                       // channels; time = N = NT <= 256), fp16 hi + scaled-lo split, promoted (tt_conv_plan)
+    int NT = 0;                        // tt: time steps per tile
+    int snake_mufu = 0;                // tt, EXPERIMENT: Snake via the SFU sine (abs error ~4e-7 instead of 2.5e-7)
     int fused = 0;                     // 1 = whole ResidualUnit: conv7 -> +b7 -> Snake -> 1x1 conv -> +b1 -> +x
     const float* wblob2 = nullptr;     // 1x1 conv weight blob (same tile N), when fused
     const float* bias2 = nullptr;
@@ -63,6 +67,12 @@ bool tc_conv_plan(TcConvParams& p);
 size_t tc_blob_floats(const TcConvParams& p);
 void tc_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob);
 cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st);
+bool tt_conv_plan(TcConvParams& p);                 // conv_tt.cu
+size_t tt_blob_floats(const TcConvParams& p);
+void tt_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob);
+cudaError_t launch_conv_tt(const TcConvParams& p, cudaStream_t st);
+extern int g_tt_probe_on;                            // 1 = launch the probing variant (process-wide test aid)
+cudaError_t tt_read_probe(long long* out8);
 cudaError_t tc_read_phase_clocks(long long* out8);   // probe-CTA phase timestamps of the last conv_tc_kernel
 
 // ---- LSTM recurrence (lstm.cu) -----------------------------------------------------------
