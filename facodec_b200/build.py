@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libfacodec_b200.so")
-SOURCES = ["engine.cu", "conv_simt.cu", "conv_tc.cu", "conv_tt.cu", "lstm.cu", "frontend.cu", "quant.cu", "altfree.cu"]
+SOURCES = ["engine.cu", "conv_simt.cu", "conv_tc.cu", "conv_tt.cu", "lstm.cu", "lstm2.cu", "frontend.cu", "quant.cu", "altfree.cu"]
 HEADERS = ["common.cuh", "kernels.h", "conv_tc_common.cuh", os.path.join("..", "..", "include", "facodec_b200.h"),
            os.path.join("..", "..", "include", "facodec_b200_debug.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",

@@ -42,7 +42,8 @@ struct ConvW {
     bool has_tt = false; size_t tcw_tt = 0; // transposed-formulation blob (conv_tt_kernel, promoted layers): [co tile of 128][chunk][tap][hi|lo']
 };
 struct SnakeW { size_t a = 0, ia = 0; int C = 0; };
-struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; size_t whh16[2] = {0, 0}; bool has16 = false; int H = 0, U = 0, G = 0; };
+struct LstmW { ConvW ih[2]; size_t whh[2] = {0, 0}; size_t whh16[2] = {0, 0}; bool has16 = false; int H = 0, U = 0, G = 0;
+               size_t whh2[2][2] = {{0, 0}, {0, 0}}; bool has2[2] = {false, false}; };   // lstm2 packs: [layer][pass3]
 struct ResW { SnakeW s1; ConvW c7; SnakeW s2; ConvW c1; int dil = 1; };
 struct VqW { size_t w_in, b_in, cb, cbn, cbn2, w_out, b_out; };
 
@@ -84,6 +85,8 @@ struct fac_handle {
     int use_tc = 2;
     int fuse_res = 1;               // fused ResidualUnit launches (fac_set_option "fuse_resunit"); 2 = only where the
                                     // fused tile still allows two CTAs per SM (C <= 128)
+    int lstm_v2 = 1;                // fac_set_option "lstm_v2": resident-W fp16 recurrence kernel (lstm2.cu); 0 = round-1 kernel
+    int dec_lstm_fp16 = 1;          // fac_set_option "decoder_lstm_fp16": downstream LSTMs run ONE fp16 pass (0 = bf16 hi/lo 3-pass)
     int enc_mufu = 0;               // fac_set_option "encoder_snake_mufu" (experiment)
     int attn_stream = 0;            // fac_set_option "attention_stream": 1 forces the recomputing attention kernel (test aid)
     int enc_tt = 1;                 // fac_set_option "encoder_tt": promoted layers run the transposed kernel (conv_tt_kernel)
@@ -282,6 +285,16 @@ LstmW pack_lstm(fac_handle* h, int m, const std::string& prefix, bool promoted =
                     for (int u = 0; u < U; ++u)
                         h->pack[L.whh[l] + ((size_t)cta * H + k) * R + g * U + u] =
                             whh.data[((size_t)g * H + cta * U + u) * H + k];
+        for (int p3 = 0; p3 < 2; ++p3) {
+            // second-generation kernel: promoted (upstream) layers use the 3-pass pack, the others the one-pass pack; the
+            // 3-pass pack of a downstream layer backs fac_set_option("decoder_bf16", 0)
+            if (p3 == 0 && promoted) continue;
+            if ((H / 16) % 8 != 0 || lstm2_smem_bytes(H, U, p3) > 227 * 1024) continue;
+            const size_t nw = lstm2_pack_words(H, U, p3);
+            L.whh2[l][p3] = pack_alloc(h, nw);
+            lstm2_pack(whh.data.data(), H, U, p3, reinterpret_cast<uint32_t*>(h->pack.data() + L.whh2[l][p3]));
+            L.has2[p3] = true;
+        }
         if (!promoted) {
             // bf16 hi/lo words for the recurrence downstream of the VQ: [cta][H/16][hi|lo][8 k-pairs][R]
             auto bf16_rn = [](float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7FFFu + ((u >> 16) & 1u); return (uint32_t)(u >> 16); };
@@ -657,12 +670,16 @@ void slstm(Ctx& c, const LstmW& L, const float* x, float* y, int B, int T) {
     float* xg = c.alloc<float>((size_t)B * T * 4 * H);
     float* h1 = c.alloc<float>((size_t)B * T * H);
     float* hT = c.alloc<float>((size_t)2 * H * 32);
+    uint32_t* h16 = c.alloc<uint32_t>((size_t)2 * 2 * (H / 2) * 32);
     unsigned int* bar = c.alloc<unsigned int>(64);
     for (int l = 0; l < 2; ++l) {
         const float* in = l == 0 ? x : h1;
         ConvOpts o;
         run_conv(c, L.ih[l], in, xg, 1, B * T, B * T, o, "lstm.ih");
         if (c.dry) continue;
+        // precision class: 3-pass fp32-faithful upstream of the VQ (and when "decoder_bf16" is off), one fp16 pass downstream
+        const int pass3 = (c.vq_critical || !c.h->dec_bf16) ? 1 : 0;
+        const bool v2 = c.h->lstm_v2 && L.has2[pass3] && (pass3 || c.h->dec_lstm_fp16);
         for (int b0 = 0; b0 < B; b0 += 32) {
             int nb = B - b0 < 32 ? B - b0 : 32;
             LstmParams p;
@@ -674,7 +691,13 @@ void slstm(Ctx& c, const LstmW& L, const float* x, float* y, int B, int T) {
             p.hT = hT; p.bar = bar;
             p.B = nb; p.T = T; p.H = H; p.U = L.U; p.G = L.G;
             c.begin("lstm_rec", 2.0 * nb * T * 4.0 * H * H, 4.0 * ((double)nb * T * 5 * H + 4.0 * H * H));
-            c.check(launch_lstm_layer(p, c.st), "lstm.rec");
+            if (v2) {
+                p.whh_p2 = reinterpret_cast<const uint32_t*>(c.W(L.whh2[l][pass3]));
+                p.h16 = h16; p.pass3 = pass3;
+                c.check(launch_lstm2_layer(p, c.st), "lstm.rec2");
+            } else {
+                c.check(launch_lstm_layer(p, c.st), "lstm.rec");
+            }
             c.end();
         }
     }
@@ -1262,6 +1285,7 @@ int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, i
         tmp.host[0][std::string("l.") + names[i]] = std::move(t);
     }
     tmp.dec_bf16 = h->dec_bf16;     // decoder-class precision (bf16 hi/lo) unless the caller switched it off
+    tmp.lstm_v2 = h->lstm_v2; tmp.dec_lstm_fp16 = h->dec_lstm_fp16;
     LstmW L;
     try { L = pack_lstm(&tmp, 0, "l"); } catch (const PackError& e) { h->err = e.msg; return FAC_ERR_UNSUPPORTED; }
     cudaSetDevice(h->device);
@@ -1291,6 +1315,8 @@ int fac_set_option(fac_handle* h, const char* name, int value) {
     if (std::string(name) == "encoder_f16x2") { h->enc_f16 = value != 0; return FAC_OK; }
     if (std::string(name) == "encoder_tt") { h->enc_tt = value != 0; return FAC_OK; }
     if (std::string(name) == "encoder_snake_mufu") { h->enc_mufu = value != 0; return FAC_OK; }
+    if (std::string(name) == "lstm_v2") { h->lstm_v2 = value != 0; return FAC_OK; }
+    if (std::string(name) == "decoder_lstm_fp16") { h->dec_lstm_fp16 = value != 0; return FAC_OK; }
     if (std::string(name) == "tt_probe") { g_tt_probe_on = value != 0; return FAC_OK; }
     if (std::string(name) == "attention_stream") { h->attn_stream = value != 0; return FAC_OK; }
     if (std::string(name) == "decoder_bf16") { h->dec_bf16 = value != 0; return FAC_OK; }
@@ -1494,7 +1520,7 @@ int fac_debug_lstm_phase_clocks(fac_handle* h, long long* out4) {
     if (!h || !out4) return FAC_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    cudaError_t e = lstm_read_phase_clocks(out4);
+    cudaError_t e = h->lstm_v2 ? lstm2_read_phase_clocks(out4) : lstm_read_phase_clocks(out4);
     if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
     return FAC_OK;
 }

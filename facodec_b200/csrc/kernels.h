@@ -82,6 +82,10 @@ struct LstmParams {
     const float* whh_p = nullptr; // packed per CTA: [G][H][4U]  (r = gate*U + u)
     const float* whh_p16 = nullptr; // bf16 split: [G][H/16][hi|lo][8 k-pairs][4U] 32-bit words (k even in the low half)
     int bf16 = 0;                 // 1 = bf16 hi/lo recurrence (downstream of the VQ only)
+    // second-generation kernel (lstm2.cu): W_hh resident in shared memory as fp16 words, h exchanged pre-split
+    const uint32_t* whh_p2 = nullptr;   // lstm2_pack layout
+    uint32_t* h16 = nullptr;            // scratch [2 parities][planes][H/2][32] words
+    int pass3 = 0;                      // 1 = fp16 hi + scaled-lo 3-pass (upstream of the VQ); 0 = one fp16 pass
     const float* skip = nullptr;  // [B][T][H] added to the output (SLSTM skip) or null
     float* y = nullptr;           // [B][T][H]
     float* hT = nullptr;          // scratch [2][H][32]
@@ -89,6 +93,11 @@ struct LstmParams {
     int B = 0, T = 0, H = 0, U = 0, G = 0;
 };
 cudaError_t launch_lstm_layer(const LstmParams& p, cudaStream_t st);
+cudaError_t launch_lstm2_layer(const LstmParams& p, cudaStream_t st);   // lstm2.cu
+size_t lstm2_pack_words(int H, int U, int pass3);
+void lstm2_pack(const float* whh, int H, int U, int pass3, uint32_t* out);
+size_t lstm2_smem_bytes(int H, int U, int pass3);
+cudaError_t lstm2_read_phase_clocks(long long* out4);
 int lstm_units_per_cta(int H);
 cudaError_t lstm_read_phase_clocks(long long* out4);   // CTA-0 accumulated phase clocks of the last launch  // U such that H % U == 0 and H / U <= resident CTAs
 

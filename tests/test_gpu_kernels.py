@@ -91,13 +91,16 @@ def test_conv_kernel_vs_torch(case, built_lib):
     assert err <= 2e-5 * max(scale, 1.0), f"max err {err} (scale {scale})"
 
 
+@pytest.mark.parametrize("v2", [1, 0])
 @pytest.mark.parametrize("bf16", [0, 1])
 @pytest.mark.parametrize("B,T,H", [(2, 5, 1024), (3, 17, 1536), (32, 4, 1024), (5, 40, 1536)])
-def test_slstm_vs_torch(B, T, H, bf16, built_lib):
-    """bf16 = 0: 3xTF32 recurrence + input projections (the class used upstream of the VQ); bf16 = 1: bf16 hi/lo
-    split (16 mantissa bits per operand; decoder only), looser bound."""
+def test_slstm_vs_torch(B, T, H, bf16, v2, built_lib):
+    """v2 = 1 (default, lstm2.cu: W_hh resident in shared memory as fp16 words): bf16 = 0 -> fp16 hi + scaled-lo 3-pass
+    recurrence (the fp32-faithful class used upstream of the VQ), bf16 = 1 -> ONE fp16 pass (decoder class: operands
+    rounded to 11 bits).  v2 = 0 (round-1 kernel): 3xTF32 / bf16 hi+lo."""
     e = _engine()
     e.set_option("decoder_bf16", bf16)
+    e.set_option("lstm_v2", v2)
     g = torch.Generator().manual_seed(H + B)
     lstm = torch.nn.LSTM(H, H, 2)
     with torch.no_grad():
@@ -116,8 +119,9 @@ def test_slstm_vs_torch(B, T, H, bf16, built_lib):
     assert rc == 0, e.L.fac_last_error(e.handle)
     y = yd.cpu().transpose(1, 2)
     err = (y - ref).abs().max().item()
-    print(f"SLSTM bf16={bf16} B={B} T={T} H={H} maxerr={err:.3e}")
-    assert err <= (2e-4 if bf16 else 2e-5)
+    e.set_option("lstm_v2", 1)
+    print(f"SLSTM v2={v2} bf16={bf16} B={B} T={T} H={H} maxerr={err:.3e}")
+    assert err <= ((1e-3 if v2 else 2e-4) if bf16 else 2e-5)
 
 
 TC_CASES = [
