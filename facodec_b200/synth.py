@@ -112,22 +112,72 @@ def synth_encoder(seed):
     return sd
 
 
-def synth_decoder(seed):
-    """Keys of dac/model/dac.py:131-165 Decoder(1024, 1536, [6,5,5,2], lstm=2)."""
+def synth_decoder(seed, lstm=2):
+    """Keys of dac/model/dac.py:131-165 Decoder(1024, 1536, [6,5,5,2], lstm=2); lstm=0 (the redecoder's decoder,
+    configs/config_redecoder.yml) drops the SLSTM and shifts the nn.Sequential indices down by one."""
     g = _Gen(seed)
     sd = {}
     _conv(g, sd, "model.0.conv.conv", DEC_DIM, LATENT, 7)
-    _lstm(g, sd, "model.1.lstm", DEC_DIM)
+    base = 1
+    if lstm:
+        _lstm(g, sd, "model.1.lstm", DEC_DIM, layers=lstm)
+        base = 2
     c = DEC_DIM
     for i, s in enumerate(DEC_RATES):
-        p = f"model.{i + 2}"
+        p = f"model.{i + base}"
         _snake(g, sd, f"{p}.block.0.alpha", c)
         _conv(g, sd, f"{p}.block.1.convtr.convtr", c // 2, c, 2 * s, transposed=True)
         for j in range(3):
             _res_unit(g, sd, f"{p}.block.{j + 2}", c // 2)
         c //= 2
-    _snake(g, sd, "model.6.alpha", c)
-    _conv(g, sd, "model.7.conv.conv", 1, c, 7)
+    _snake(g, sd, f"model.{4 + base}.alpha", c)
+    _conv(g, sd, f"model.{5 + base}.conv.conv", 1, c, 7)
+    return sd
+
+
+def synth_redecoder(seed, embed_dim=512, n_layers=16, gin=1024):
+    """Keys of modules/redecoder.py:5-21 Redecoder(encoder_type='wavenet'): WN(hidden 512, kernel 5, 16 layers,
+    gin_channels 1024) as ``encoder.*`` (modules/wavenet.py:103-136), conv_out Conv1d(512, 1024, 1), one prosody and two
+    content nn.Embedding(1024, 512) (N(0, 1) init)."""
+    g = _Gen(seed)
+    sd = {}
+    _conv(g, sd, "encoder.cond_layer.conv.conv", 2 * embed_dim * n_layers, gin, 1)
+    for i in range(n_layers):
+        _conv(g, sd, f"encoder.in_layers.{i}.conv.conv", 2 * embed_dim, embed_dim, 5)
+    for i in range(n_layers):
+        _conv(g, sd, f"encoder.res_skip_layers.{i}.conv.conv", 2 * embed_dim if i < n_layers - 1 else embed_dim, embed_dim, 1)
+    _conv(g, sd, "conv_out", LATENT, embed_dim, 1, weight_norm=False)
+    sd["prosody_embed.0.weight"] = g.normal((1024, embed_dim))
+    for i in range(2):
+        sd[f"content_embed.{i}.weight"] = g.normal((1024, embed_dim))
+    return sd
+
+
+def synth_redecoder_state_dicts(seed=0):
+    """{'encoder': Redecoder, 'decoder': Decoder(causal=False, lstm=0)} as build_model(stage='redecoder') lays them out
+    (modules/commons.py:385-412)."""
+    return {"encoder": synth_redecoder(seed * 3 + 101), "decoder": synth_decoder(seed * 3 + 102, lstm=0)}
+
+
+def synth_cnnlstm(seed, indim, outdim, heads):
+    """Keys of modules/quantize.py:106-125 CNNLSTM(indim, outdim, head): model.{0,1,2} = ResidualUnit (block.0 / block.2 =
+    Activation1d(SnakeBeta) -> ``act.alpha`` / ``act.beta`` (log scale) plus the registered filter buffers, block.1 /
+    block.3 = weight-normed Conv1d k7 / k1), model.3 = Activation1d(SnakeBeta), heads.{i} = nn.Linear."""
+    g = _Gen(seed)
+    sd = {}
+    for j in range(3):
+        p = f"model.{j}"
+        for blk in (0, 2):
+            sd[f"{p}.block.{blk}.act.alpha"] = g.uniform((indim,), 0.3)
+            sd[f"{p}.block.{blk}.act.beta"] = g.uniform((indim,), 0.3)
+        _conv(g, sd, f"{p}.block.1", indim, indim, 7)
+        _conv(g, sd, f"{p}.block.3", indim, indim, 1)
+    sd["model.3.act.alpha"] = g.uniform((indim,), 0.3)
+    sd["model.3.act.beta"] = g.uniform((indim,), 0.3)
+    b = 1.0 / math.sqrt(indim)
+    for i in range(heads):
+        sd[f"heads.{i}.weight"] = g.uniform((outdim, indim), b)
+        sd[f"heads.{i}.bias"] = g.uniform((outdim,), b)
     return sd
 
 

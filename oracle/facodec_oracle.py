@@ -141,25 +141,30 @@ def encoder_forward(sd, x, rates=(2, 5, 5, 6), taps=None):
     return sconv1d(h, sd, f"block.{n + 3}.conv.conv")
 
 
-def decoder_forward(sd, z, rates=(6, 5, 5, 2), taps=None):
-    """Decoder.forward, dac.py:131-165. z [B,1024,T'] -> y [B,1,300 T']."""
-    h = sconv1d(z, sd, "model.0.conv.conv")
+def decoder_forward(sd, z, rates=(6, 5, 5, 2), taps=None, causal=True, lstm=2):
+    """Decoder.forward, dac.py:131-165. z [B,1024,T'] -> y [B,1,300 T'].  ``causal`` / ``lstm`` are the constructor
+    arguments: the codec uses (True, 2) (configs/config.yml), the redecoder (False, 0) (configs/config_redecoder.yml:
+    decoder_causal / decoder_lstm) -- without the SLSTM the nn.Sequential indices shift down by one."""
+    h = sconv1d(z, sd, "model.0.conv.conv", causal=causal)
     if taps is not None:
         taps["dec_conv0"] = h
-    h = slstm(h, sd, "model.1.lstm")
-    if taps is not None:
-        taps["dec_lstm"] = h
+    base = 1
+    if lstm:
+        h = slstm(h, sd, "model.1.lstm", num_layers=lstm)
+        base = 2
+        if taps is not None:
+            taps["dec_lstm"] = h
     for i, s in enumerate(rates):
-        p = f"model.{i + 2}"
+        p = f"model.{i + base}"
         h = snake(h, sd[f"{p}.block.0.alpha"])
-        h = sconvtr1d(h, sd, f"{p}.block.1.convtr.convtr", s)
+        h = sconvtr1d(h, sd, f"{p}.block.1.convtr.convtr", s, causal=causal)
         for j, d in enumerate((1, 3, 9)):
-            h = residual_unit(h, sd, f"{p}.block.{j + 2}", d)
+            h = residual_unit(h, sd, f"{p}.block.{j + 2}", d, causal=causal)
         if taps is not None:
             taps[f"dec_block{i + 1}"] = h
     n = len(rates)
-    h = snake(h, sd[f"model.{n + 2}.alpha"])
-    h = sconv1d(h, sd, f"model.{n + 3}.conv.conv")
+    h = snake(h, sd[f"model.{n + base}.alpha"])
+    h = sconv1d(h, sd, f"model.{n + base + 1}.conv.conv", causal=causal)
     return torch.tanh(h)
 
 
@@ -233,15 +238,22 @@ def style_encoder(sd, mel, mask, prefix="timbre_encoder"):
 # ----------------------------------------------------------------------------
 # modules/wavenet.py
 # ----------------------------------------------------------------------------
-def wavenet(sd, x, prefix="melspec_encoder", hidden=256, n_layers=8):
-    """WN.forward, wavenet.py:138-166 with g=None, x_mask == 1, eval (dropout off);
-    gate = commons.py:113-120 fused_add_tanh_sigmoid_multiply."""
+def wavenet(sd, x, prefix="melspec_encoder", hidden=256, n_layers=8, g=None, causal=True):
+    """WN.forward, wavenet.py:138-166 with x_mask == 1, eval (dropout off), dilation_rate 1;
+    gate = commons.py:113-120 fused_add_tanh_sigmoid_multiply.  g [B, gin, 1] (or None, the codec's own call) goes
+    through cond_layer once and is sliced per layer (:143-151)."""
     output = torch.zeros_like(x)
+    if g is not None:
+        g = sconv1d(g, sd, f"{prefix}.cond_layer.conv.conv", causal=causal)
     for i in range(n_layers):
-        x_in = sconv1d(x, sd, f"{prefix}.in_layers.{i}.conv.conv")
-        in_act = x_in + torch.zeros_like(x_in)
+        x_in = sconv1d(x, sd, f"{prefix}.in_layers.{i}.conv.conv", causal=causal)
+        if g is not None:
+            g_l = g[:, i * 2 * hidden:(i + 1) * 2 * hidden, :]
+        else:
+            g_l = torch.zeros_like(x_in)
+        in_act = x_in + g_l
         acts = torch.tanh(in_act[:, :hidden]) * torch.sigmoid(in_act[:, hidden:])
-        rs = sconv1d(acts, sd, f"{prefix}.res_skip_layers.{i}.conv.conv")
+        rs = sconv1d(acts, sd, f"{prefix}.res_skip_layers.{i}.conv.conv", causal=causal)
         if i < n_layers - 1:
             x = (x + rs[:, :hidden]) * 1.0
             output = output + rs[:, hidden:]
@@ -426,3 +438,93 @@ def alias_free_act(x, act, ratio=2, kernel_size=12):
     pr = kernel_size // 2
     d = F.pad(u, (pl, pr), mode="replicate")
     return F.conv1d(d, filt.expand(C, -1, -1), stride=ratio, groups=C)
+
+
+# ----------------------------------------------------------------------------
+# modules/redecoder.py (voice conversion: reconstruct_redecoder.py:108-122), encoder_type == "wavenet"
+# ----------------------------------------------------------------------------
+def redecoder_forward(sd, p_code, c_code, timbre_vec, use_p_code=True, use_c_code=True, n_c=2, embed_dim=512,
+                      n_p_codebooks=1, causal=False):
+    """Redecoder.forward, modules/redecoder.py:35-48: sum of code embeddings -> WN(hidden 512, kernel 5, 16 layers,
+    gin 1024, causal = args.decoder_causal) conditioned on the timbre vector -> Conv1d(512, 1024, 1).
+    p_code [B, n_p, T], c_code [B, >= n_c, T] int64, timbre_vec [B, 1024] -> [B, 1024, T]."""
+    B, _, T = p_code.shape
+    p_embed = torch.zeros(B, T, embed_dim)
+    c_embed = torch.zeros(B, T, embed_dim)
+    if use_p_code:
+        for i in range(n_p_codebooks):
+            p_embed += F.embedding(p_code[:, i, :], sd[f"prosody_embed.{i}.weight"])
+    if use_c_code:
+        for i in range(n_c):
+            c_embed += F.embedding(c_code[:, i, :], sd[f"content_embed.{i}.weight"])
+    x = p_embed + c_embed
+    x = wavenet(sd, x.transpose(1, 2), prefix="encoder", hidden=embed_dim, n_layers=16, g=timbre_vec.unsqueeze(2),
+                causal=causal) * torch.ones(B, 1, T)
+    return F.conv1d(x, sd["conv_out.weight"], sd["conv_out.bias"])
+
+
+def voice_convert(sds_re, codes, timbre):
+    """reconstruct_redecoder.py:118-121: z = model.encoder(codes[0], codes[1], timbre, use_p_code=False, n_c=1);
+    wave = model.decoder(z) with the redecoder's own non-causal, LSTM-free decoder."""
+    with torch.no_grad():
+        z = redecoder_forward(sds_re["encoder"], codes[0], codes[1], timbre, use_p_code=False, n_c=1)
+        y = decoder_forward(sds_re["decoder"], z, causal=False, lstm=0)
+    return z, y
+
+
+# ----------------------------------------------------------------------------
+# modules/quantize.py:29-125 predictor heads (training-only in the reference; SURVEY.md 8f rank 1)
+# ----------------------------------------------------------------------------
+def snake_beta(x, alpha, beta, alpha_logscale=True):
+    """SnakeBeta.forward, modules/quantize.py:78-88."""
+    a = alpha.unsqueeze(0).unsqueeze(-1)
+    b = beta.unsqueeze(0).unsqueeze(-1)
+    if alpha_logscale:
+        a = torch.exp(a)
+        b = torch.exp(b)
+    return x + (1.0 / (b + 0.000000001)) * torch.pow(torch.sin(x * a), 2)
+
+
+def _head_act(x, sd, prefix):
+    """Activation1d(activation=SnakeBeta(dim, alpha_logscale=True)), modules/quantize.py:97."""
+    return alias_free_act(x, lambda u: snake_beta(u, sd[prefix + ".act.alpha"], sd[prefix + ".act.beta"]))
+
+
+def head_residual_unit(x, sd, prefix, dilation):
+    """modules/quantize.py:90-104 ResidualUnit: plain weight-normed nn.Conv1d (zero padding ((7-1)*d)//2), NOT SConv1d."""
+    y = _head_act(x, sd, prefix + ".block.0")
+    y = F.conv1d(y, _wn_weight(sd, prefix + ".block.1"), sd[prefix + ".block.1.bias"], dilation=dilation,
+                 padding=((7 - 1) * dilation) // 2)
+    y = _head_act(y, sd, prefix + ".block.2")
+    y = F.conv1d(y, _wn_weight(sd, prefix + ".block.3"), sd[prefix + ".block.3.bias"])
+    return x + y
+
+
+def cnnlstm_forward(sd, x, n_heads, global_pred=False):
+    """CNNLSTM.forward, modules/quantize.py:106-125 (despite the name: 3 ResidualUnits (dilation 1, 2, 3), an alias-free
+    SnakeBeta, then ``n_heads`` nn.Linear heads; no LSTM in the reference class).  x [B, C, T] -> list of [B, T, out]
+    (or [B, out] when global_pred)."""
+    h = x
+    for j, d in enumerate((1, 2, 3)):
+        h = head_residual_unit(h, sd, f"model.{j}", d)
+    h = _head_act(h, sd, "model.3")
+    h = h.transpose(1, 2)
+    if global_pred:
+        h = torch.mean(h, dim=1, keepdim=False)
+    return [F.linear(h, sd[f"heads.{i}.weight"], sd[f"heads.{i}.bias"]) for i in range(n_heads)]
+
+
+# ----------------------------------------------------------------------------
+# meldataset.py:29-47 dataset-side mel (PseudoDataset training targets)
+# ----------------------------------------------------------------------------
+def dataset_mel(wave, window, fb, n_fft=2048, hop=HOP, win_length=1200):
+    """meldataset.py:37-47 preprocess: to_mel = torchaudio MelSpectrogram(n_mels=80, n_fft=2048, win_length=1200,
+    hop_length=300) with its DEFAULT sample_rate=16000 (the filterbank differs from the quantizer's 24 kHz one),
+    then (log(1e-5 + mel) + 4) / 4.  wave [T] or [B, T] -> [B, 80, T // 300 + 1] (no frame slicing here)."""
+    if wave.dim() == 1:
+        wave = wave.unsqueeze(0)
+    spec = torch.stft(wave, n_fft, hop_length=hop, win_length=win_length, window=window, center=True, pad_mode="reflect",
+                      normalized=False, onesided=True, return_complex=True)
+    spec = spec.abs().pow(2.0)
+    mel = torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2)
+    return (torch.log(1e-5 + mel) - (-4)) / 4

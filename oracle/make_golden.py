@@ -48,9 +48,37 @@ def run_case(model, c):
     return {k: v.numpy() for k, v in out.items()}
 
 
-def vq_margin_report(model, c, out):
-    """top1-top2 distance gap of every VQ decision (for choosing robust fixtures)."""
-    return None
+# Voice-conversion fixtures (reconstruct_redecoder.py:108-122): codes + timbre of a codec fixture -> redecoder.encoder ->
+# redecoder.decoder.  name -> (source codec fixture, redecoder weight seed, use_p_code, n_c)
+REDEC_CASES = {
+    "redec_b2_t7200_vc": dict(src="b2_t7200", wseed=0, use_p=False, n_c=1),      # the call reconstruct_redecoder.py makes
+    "redec_b2_t7200_full": dict(src="b2_t7200", wseed=0, use_p=True, n_c=2),      # every embedding table
+    "redec_b3_t1500_short": dict(src="b3_t1500_short", wseed=1, use_p=True, n_c=1),   # 5 frames: non-causal short-input pads
+}
+
+
+def run_redec_case(model, c):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, c["src"] + ".npz")))
+    cp, cc, timbre = (torch.from_numpy(g[k]) for k in ("codes_p", "codes_c", "timbre"))
+    with torch.no_grad():
+        z = model.encoder(cp, cc, timbre, use_p_code=c["use_p"], n_c=c["n_c"])
+        y = model.decoder(z)
+    return dict(z=z.numpy(), y=y.numpy())
+
+
+def vq_margin_report(sd, prefix, latents):
+    """top-1 / top-2 gap of every decision of one VectorQuantize (dac/nn/quantize.py:78-94): returns the per-frame margin
+    dist[2nd] - dist[1st] of the reference's own distance matrix (fp32).  Used by scripts/vq_margins.py to report how
+    far the benchmark batch's decisions are from a tie."""
+    import torch.nn.functional as F
+    w_in = torch._weight_norm(sd[prefix + ".in_proj.weight_v"], sd[prefix + ".in_proj.weight_g"], 0)
+    z_e = F.conv1d(latents, w_in, sd[prefix + ".in_proj.bias"])
+    b, d, t = z_e.shape
+    enc = F.normalize(z_e.permute(0, 2, 1).reshape(b * t, d))
+    cb = F.normalize(sd[prefix + ".codebook.weight"])
+    dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cb.t() + cb.pow(2).sum(1, keepdim=True).t()
+    top2 = torch.topk(-dist, 2, dim=1).values
+    return (top2[:, 0] - top2[:, 1]).reshape(b, t)
 
 
 def main():
@@ -71,7 +99,26 @@ def main():
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **out)
         print(name, {k: v.shape for k, v in out.items()}, os.path.getsize(path) // 1024, "KiB")
+    main_redecoder()
+
+
+def main_redecoder():
+    model = ref_import.build_reference_redecoder(0)
+    loaded = None
+    for name, c in REDEC_CASES.items():
+        if loaded != c["wseed"]:
+            sds = synth.synth_redecoder_state_dicts(c["wseed"])
+            for k in ("encoder", "decoder"):
+                model[k].load_state_dict(sds[k])
+            loaded = c["wseed"]
+        out = run_redec_case(model, c)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, {k: v.shape for k, v in out.items()}, os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "redecoder":
+        main_redecoder()
+    else:
+        main()

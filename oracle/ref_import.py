@@ -90,6 +90,9 @@ def _install_stubs():
         m = types.ModuleType("munch")
         m.Munch = Munch
         sys.modules["munch"] = m
+    for name in ("soundfile", "librosa"):      # meldataset.py:8-9 (file I/O only; PseudoDataset never calls them)
+        if name not in sys.modules:
+            sys.modules[name] = _Anything(name)
     if "argbind" not in sys.modules:
         ab = _Anything("argbind")
         ab.bind = lambda *a, **k: (a[0] if (len(a) == 1 and callable(a[0]) and not k) else (lambda f: f))
@@ -118,6 +121,21 @@ def import_reference():
         sys.path.insert(0, REFERENCE_ROOT)
     import modules.commons as commons  # noqa
     return commons
+
+
+def build_reference_redecoder(seed=0):
+    """build_model(config_redecoder.yml model_params, stage='redecoder') as reconstruct_redecoder.py:43-61 does:
+    Munch(encoder=Redecoder (wavenet), decoder=Decoder(causal=False, lstm=0)), eval mode, CPU fp32."""
+    import yaml
+    commons = import_reference()
+    cfg = yaml.safe_load(open(os.path.join(REFERENCE_ROOT, "configs", "config_redecoder.yml")))
+    params = recursive_munch(cfg["model_params"])
+    torch.manual_seed(seed)
+    model = commons.build_model(params, stage="redecoder")
+    out = Munch(encoder=model.encoder, decoder=model.decoder)
+    for k in out:
+        out[k].eval()
+    return out
 
 
 def build_reference_model(seed=0):

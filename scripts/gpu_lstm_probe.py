@@ -5,7 +5,8 @@ sys.path.insert(0, ROOT)
 from facodec_b200.modules import Engine
 e = Engine(); e._ensure(torch.device("cuda:0"))
 P = lambda t: ctypes.c_void_p(t.data_ptr())
-for (B, T, H) in ((32, 320, 1024), (32, 320, 1536)):
+for (B, T, H, bf) in ((32, 320, 1024, 0), (32, 320, 1536, 1)):
+    e.set_option('decoder_bf16', bf)   # 0 -> 3-pass (encoder class), 1 -> one fp16 pass (decoder class)
     g = torch.Generator().manual_seed(1)
     lstm = torch.nn.LSTM(H, H, 2)
     ws = [getattr(lstm, f"{n}_l{l}").detach().contiguous() for l in range(2) for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]

@@ -42,6 +42,14 @@ GOLDEN_CASES = {
 }
 
 
+# voice-conversion fixtures (kept in sync with oracle/make_golden.py by test_oracle.py::test_redecoder_case_table)
+REDEC_CASES = {
+    "redec_b2_t7200_vc": dict(src="b2_t7200", wseed=0, use_p=False, n_c=1),
+    "redec_b2_t7200_full": dict(src="b2_t7200", wseed=0, use_p=True, n_c=2),
+    "redec_b3_t1500_short": dict(src="b3_t1500_short", wseed=1, use_p=True, n_c=1),
+}
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
 

@@ -125,3 +125,112 @@ def test_reflect_pad_short_branch():
     y = O._pad1d_reflect(x, 5, 0)
     assert y.shape[-1] == 8
     assert y.flatten().tolist() == [0.0, 0.0, 0.0, 3.0, 2.0, 1.0, 2.0, 3.0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: voice-conversion path (modules/redecoder.py), predictor heads (modules/quantize.py:29-125), dataset mel
+# ---------------------------------------------------------------------------------------------------------------
+from conftest import REDEC_CASES  # noqa: E402
+
+
+def test_redecoder_case_table():
+    from oracle import make_golden
+    assert make_golden.REDEC_CASES == REDEC_CASES
+    for name in REDEC_CASES:
+        assert os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+
+
+@pytest.mark.parametrize("name", list(REDEC_CASES))
+def test_redecoder_oracle_matches_golden(name):
+    from facodec_b200 import synth
+    c = REDEC_CASES[name]
+    g = load_golden(name)
+    src = load_golden(c["src"])
+    sds = synth.synth_redecoder_state_dicts(c["wseed"])
+    cp, cc, timbre = (torch.from_numpy(src[k]) for k in ("codes_p", "codes_c", "timbre"))
+    with torch.no_grad():
+        z = O.redecoder_forward(sds["encoder"], cp, cc, timbre, use_p_code=c["use_p"], n_c=c["n_c"])
+        y = O.decoder_forward(sds["decoder"], z, causal=False, lstm=0)
+    _close(z, g["z"], "z")
+    _close(y, g["y"], "y")
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+def test_redecoder_oracle_matches_imported_reference():
+    """modules/redecoder.py:35-48 + the non-causal, LSTM-free Decoder of build_model(stage='redecoder'): bit-identical."""
+    import warnings
+    warnings.simplefilter("ignore")
+    from facodec_b200 import synth
+    model = ref_import.build_reference_redecoder(0)
+    sds = synth.synth_redecoder_state_dicts(2)
+    for k in ("encoder", "decoder"):
+        model[k].load_state_dict(sds[k])
+    g = torch.Generator().manual_seed(5)
+    cp = torch.randint(0, 1024, (2, 1, 13), generator=g)
+    cc = torch.randint(0, 1024, (2, 2, 13), generator=g)
+    timbre = torch.randn(2, 1024, generator=g)
+    for use_p, n_c in ((False, 1), (True, 2)):
+        with torch.no_grad():
+            z = model.encoder(cp, cc, timbre, use_p_code=use_p, n_c=n_c)
+            y = model.decoder(z)
+            z2 = O.redecoder_forward(sds["encoder"], cp, cc, timbre, use_p_code=use_p, n_c=n_c)
+            y2 = O.decoder_forward(sds["decoder"], z2, causal=False, lstm=0)
+        assert torch.equal(z, z2) and torch.equal(y, y2)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+def test_predictor_heads_and_snakebeta_match_imported_reference():
+    """SnakeBeta (modules/quantize.py:29-88) inside Activation1d, the heads' ResidualUnit (:90-104) and CNNLSTM (:106-125),
+    imported unmodified: the restatement is bit-identical (round 1 pinned the alias-free activation with Identity only)."""
+    import warnings
+    warnings.simplefilter("ignore")
+    from facodec_b200 import synth
+    ref_import.import_reference()
+    from modules.quantize import CNNLSTM, SnakeBeta
+    from alias_free_torch import Activation1d as RefAct
+    g = torch.Generator().manual_seed(9)
+    sb = SnakeBeta(6, alpha_logscale=True)
+    with torch.no_grad():
+        sb.alpha.copy_(torch.randn(6, generator=g) * 0.3)
+        sb.beta.copy_(torch.randn(6, generator=g) * 0.3)
+    x = torch.randn(2, 6, 40, generator=g)
+    with torch.no_grad():
+        assert torch.equal(sb(x), O.snake_beta(x, sb.alpha, sb.beta))
+        act = RefAct(activation=sb)
+        assert torch.equal(act(x), O.alias_free_act(x, lambda u: O.snake_beta(u, sb.alpha, sb.beta)))
+    for (indim, outdim, heads, glob) in ((64, 10, 2, False), (32, 7, 1, True)):
+        m = CNNLSTM(indim, outdim, heads, global_pred=glob).eval()
+        sd = synth.synth_cnnlstm(3, indim, outdim, heads)
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.endswith("filter") for k in missing)      # only the registered filter buffers
+        xx = torch.randn(2, indim, 33, generator=g)
+        with torch.no_grad():
+            a = m(xx)
+            b = O.cnnlstm_forward(sd, xx, heads, global_pred=glob)
+        assert len(a) == len(b) == heads
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+def test_dataset_mel_matches_imported_meldataset():
+    """meldataset.py:37-47 preprocess (torchaudio MelSpectrogram with its default sample_rate = 16000) imported unmodified
+    (soundfile / librosa stubbed: file I/O only), against the restatement fed with synth's host-independent window and
+    16 kHz filterbank."""
+    import warnings
+    warnings.simplefilter("ignore")
+    from facodec_b200 import synth
+    ref_import.import_reference()
+    import meldataset
+    w = synth.synth_waves(1, 5000, seed=3)[0, 0]
+    with torch.no_grad():
+        ref = meldataset.preprocess(w.numpy())
+        fb_ref = meldataset.to_mel.mel_scale.fb
+        win_ref = meldataset.to_mel.spectrogram.window
+        got_same = O.dataset_mel(w, win_ref, fb_ref)
+        assert torch.equal(ref, got_same)
+        fb = synth.melscale_fbanks_htk(sample_rate=16000, f_max=8000.0)
+        assert float((fb - fb_ref).abs().max()) <= 1e-5      # fp64-then-round vs torchaudio fp32 evaluation
+        got = O.dataset_mel(w, synth.hann_window_periodic(1200), fb)
+    assert tuple(ref.shape) == (1, 80, 5000 // 300 + 1)
+    assert float((got - ref).abs().max()) <= 2e-5
