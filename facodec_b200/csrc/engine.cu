@@ -56,6 +56,13 @@ struct DecW {
     ConvW conv0; LstmW lstm;
     struct Block { SnakeW snake; ConvW up; int stride; int cout; ResW res[3]; } blk[4];
     SnakeW snake; ConvW conv_out;
+    bool causal = true, has_lstm = true;   // the redecoder's decoder: causal = false, no SLSTM (config_redecoder.yml)
+};
+// modules/redecoder.py Redecoder(encoder_type = "wavenet"): embeddings + WN(512, k5, 16 layers, gin 1024) + conv_out
+struct RedW {
+    size_t emb_p = 0, emb_c[2] = {0, 0};
+    ConvW cond, wn_in[16], wn_rs[16], conv_out;
+    int hidden = 512, layers = 16;
 };
 struct QuantW {
     VqW vq[6];
@@ -71,12 +78,13 @@ struct RvqSet { int nq; VqW vq[8]; };
 struct fac_handle {
     int device = 0;
     std::string err;
-    std::map<std::string, HostTensor> host[3];
-    bool have[3] = {false, false, false};
+    std::map<std::string, HostTensor> host[FAC_NUM_MODULES];
+    bool have[FAC_NUM_MODULES] = {false, false, false, false, false};
     bool finalized = false;
     std::vector<float> pack;        // host staging of the weight arena
     float* warena = nullptr; size_t wfloats = 0;
     EncW enc; DecW dec; QuantW qw;
+    RedW red; DecW dec2;            // voice-conversion model: Redecoder + its non-causal, LSTM-free decoder
     std::vector<RvqSet> rvqs; std::vector<float*> rvq_arenas;
     char* ws = nullptr; size_t ws_bytes = 0;
     int launches = 0;
@@ -223,6 +231,35 @@ ConvW pack_convtr(fac_handle* h, int m, const std::string& prefix, int stride) {
             for (int r = 0; r < stride; ++r) {
                 h->pack[c.w + ((size_t)0 * Cin + ci) * c.ldw + r * Cout + co] = w[((size_t)ci * Cout + co) * K + r + stride];
                 h->pack[c.w + ((size_t)1 * Cin + ci) * c.ldw + r * Cout + co] = w[((size_t)ci * Cout + co) * K + r];
+            }
+    const HostTensor& b = need(h, m, prefix + ".bias");
+    c.b = pack_alloc(h, c.Cout);
+    for (int r = 0; r < stride; ++r)
+        for (int co = 0; co < Cout; ++co) h->pack[c.b + r * Cout + co] = b.data[co];
+    attach_tc(h, c, 1, false);
+    return c;
+}
+
+// Non-causal variant (encodec.py:264-269: trim padding_total - padding_total/2 on the left, padding_total/2 on the right):
+// output sample n = t*s + r reads full[n + pl], pl = s - s/2, i.e. x[t-1]*w[a+s] (a < s) + x[t]*w[a] + x[t+1]*w[a-s] (a >= s)
+// with a = r + pl: a 3-tap conv over (x[t-1], x[t], x[t+1]), zero padding 1 | 1, s*Cout phase-major channels.
+ConvW pack_convtr_noncausal(fac_handle* h, int m, const std::string& prefix, int stride) {
+    std::vector<int64_t> shp;
+    std::vector<float> w = folded_weight(h, m, prefix, shp);
+    if (shp.size() != 3 || shp[2] != 2 * stride) throw PackError{"convtr kernel != 2*stride at " + prefix};
+    int Cin = (int)shp[0], Cout = (int)shp[1], K = (int)shp[2];
+    const int pl = stride - stride / 2;
+    ConvW c;
+    c.Cin = Cin; c.Cout = Cout * stride; c.K = 3; c.ldw = (c.Cout + 3) / 4 * 4;
+    c.w = pack_alloc(h, (size_t)3 * Cin * c.ldw);
+    for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+            for (int r = 0; r < stride; ++r) {
+                const int a = r + pl;
+                const float* wk = &w[((size_t)ci * Cout + co) * K];
+                h->pack[c.w + ((size_t)0 * Cin + ci) * c.ldw + r * Cout + co] = a < stride ? wk[a + stride] : 0.f;
+                h->pack[c.w + ((size_t)1 * Cin + ci) * c.ldw + r * Cout + co] = wk[a];
+                h->pack[c.w + ((size_t)2 * Cin + ci) * c.ldw + r * Cout + co] = a >= stride ? wk[a - stride] : 0.f;
             }
     const HostTensor& b = need(h, m, prefix + ".bias");
     c.b = pack_alloc(h, c.Cout);
@@ -387,23 +424,50 @@ void pack_encoder(fac_handle* h) {
     e.conv_out = pack_conv(h, m, "block.7.conv.conv", 1, true);
 }
 
-void pack_decoder(fac_handle* h) {
-    DecW& d = h->dec;
-    const int m = FAC_DECODER;
+void pack_decoder_into(fac_handle* h, int m, DecW& d, bool lstm, bool causal) {
     const int rates[4] = {6, 5, 5, 2};
+    d.causal = causal; d.has_lstm = lstm;
     d.conv0 = pack_conv(h, m, "model.0.conv.conv");
-    d.lstm = pack_lstm(h, m, "model.1.lstm");
+    int base = 1;
+    if (lstm) { d.lstm = pack_lstm(h, m, "model.1.lstm"); base = 2; }
     for (int i = 0; i < 4; ++i) {
-        std::string p = "model." + std::to_string(i + 2);
+        std::string p = "model." + std::to_string(i + base);
         d.blk[i].snake = pack_snake(h, m, p + ".block.0.alpha");
-        d.blk[i].up = pack_convtr(h, m, p + ".block.1.convtr.convtr", rates[i]);
+        d.blk[i].up = causal ? pack_convtr(h, m, p + ".block.1.convtr.convtr", rates[i])
+                             : pack_convtr_noncausal(h, m, p + ".block.1.convtr.convtr", rates[i]);
         d.blk[i].stride = rates[i];
         d.blk[i].cout = d.blk[i].up.Cout / rates[i];
         const int dils[3] = {1, 3, 9};
         for (int j = 0; j < 3; ++j) d.blk[i].res[j] = pack_res(h, m, p + ".block." + std::to_string(j + 2), dils[j]);
     }
-    d.snake = pack_snake(h, m, "model.6.alpha");
-    d.conv_out = pack_conv(h, m, "model.7.conv.conv");
+    d.snake = pack_snake(h, m, "model." + std::to_string(4 + base) + ".alpha");
+    d.conv_out = pack_conv(h, m, "model." + std::to_string(5 + base) + ".conv.conv");
+}
+
+void pack_decoder(fac_handle* h) { pack_decoder_into(h, FAC_DECODER, h->dec, true, true); }
+
+// modules/redecoder.py:5-21 (encoder_type "wavenet"); key names of modules/wavenet.py:103-136 under "encoder."
+void pack_redecoder(fac_handle* h) {
+    RedW& r = h->red;
+    const int m = FAC_REDECODER;
+    auto emb = [&](const std::string& key) {
+        const HostTensor& t = need(h, m, key);
+        if (t.shape.size() != 2 || t.shape[0] != 1024 || t.shape[1] != r.hidden) throw PackError{"embedding shape at " + key};
+        size_t off = pack_alloc(h, t.numel());
+        for (size_t i = 0; i < t.numel(); ++i) h->pack[off + i] = t.data[i];
+        return off;
+    };
+    r.emb_p = emb("prosody_embed.0.weight");
+    r.emb_c[0] = emb("content_embed.0.weight");
+    r.emb_c[1] = emb("content_embed.1.weight");
+    r.cond = pack_conv(h, m, "encoder.cond_layer.conv.conv");
+    for (int i = 0; i < r.layers; ++i) {
+        r.wn_in[i] = pack_conv(h, m, "encoder.in_layers." + std::to_string(i) + ".conv.conv");
+        r.wn_rs[i] = pack_conv(h, m, "encoder.res_skip_layers." + std::to_string(i) + ".conv.conv");
+    }
+    r.conv_out = pack_conv(h, m, "conv_out");
+    if (r.cond.Cin != LATENT || r.cond.Cout != 2 * r.hidden * r.layers || r.wn_in[0].K != 5 || r.conv_out.Cout != LATENT)
+        throw PackError{"redecoder geometry (expects WN(512, kernel 5, 16 layers, gin 1024))"};
 }
 
 void pack_quantizer(fac_handle* h) {
@@ -606,13 +670,15 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
     c.end();
 }
 
-// causal SConv1d with reflect padding; returns output length
+// SConv1d with reflect padding (encodec.py:212-228): causal = everything on the left, else padding_total - padding_total/2
+// on the left and padding_total/2 (+ extra) on the right; returns output length
 int sconv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int T, int dil, int stride, ConvOpts o,
-          const char* name) {
+          const char* name, bool causal = true) {
     int k_eff = (w.K - 1) * dil + 1;
     o.dil = dil; o.stride = stride;
-    o.pad_left = k_eff - stride;
-    o.pad_right = conv_extra_pad(T, k_eff, stride);
+    const int total = k_eff - stride, extra = conv_extra_pad(T, k_eff, stride);
+    o.pad_left = causal ? total : total - total / 2;
+    o.pad_right = (causal ? 0 : total / 2) + extra;
     o.reflect = 1;
     int Tout = conv_out_len(T, k_eff, stride);
     run_conv(c, w, x, y, B, T, Tout, o, name);
@@ -620,7 +686,7 @@ int sconv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int T, int di
 }
 
 // Whole ResidualUnit in one tcgen05 launch (conv_tc_kernel<true>) when every channel fits one CTA tile.
-bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B, int T) {
+bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B, int T, bool causal) {
     if (c.h->use_tc < 1 || !c.h->fuse_res || c.vq_critical || !r.c7.tc || !r.c1.tc || r.c7.promoted || r.c1.promoted ||
         r.c7.Cin != r.c7.Cout || r.c1.K != 1 || r.c7.vf != 1)
         return false;
@@ -639,7 +705,8 @@ bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B,
     tp.in_alpha = c.W(r.s1.a); tp.in_inv_alpha = c.W(r.s1.ia);
     tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(r.s2.a); tp.out_inv_alpha = c.W(r.s2.ia);
     tp.B = B; tp.Tin = T; tp.ldx = r.c7.Cin;
-    tp.PLr = k_eff - 1; tp.pad_left_s = k_eff - 1; tp.pad_right_s = 0; tp.reflect = 1;
+    const int pl = causal ? k_eff - 1 : (k_eff - 1) - (k_eff - 1) / 2;
+    tp.PLr = pl; tp.pad_left_s = pl; tp.pad_right_s = k_eff - 1 - pl; tp.reflect = 1;
     tp.Tout = T; tp.ldy = r.c7.Cout;
     tp.x_bstride = (size_t)T * r.c7.Cin; tp.y_bstride = (size_t)T * r.c7.Cout;
     double flops = 2.0 * B * T * (double)r.c7.Cout * r.c7.Cin * (r.c7.K + 1);
@@ -653,15 +720,15 @@ bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B,
 }
 
 // ResidualUnit (dac.py:25-42): y = x + conv1(snake2(conv7_d(snake1(x))))
-void residual_unit(Ctx& c, const ResW& r, const float* x, float* tmp, float* y, int B, int T) {
-    if (residual_unit_fused(c, r, x, y, B, T)) return;
+void residual_unit(Ctx& c, const ResW& r, const float* x, float* tmp, float* y, int B, int T, bool causal = true) {
+    if (residual_unit_fused(c, r, x, y, B, T, causal)) return;
     ConvOpts o1;
     o1.in_snake = &r.s1;
     o1.out_snake = &r.s2;
-    sconv(c, r.c7, x, tmp, B, T, r.dil, 1, o1, "res.conv7");
+    sconv(c, r.c7, x, tmp, B, T, r.dil, 1, o1, "res.conv7", causal);
     ConvOpts o2;
     o2.res = x;
-    sconv(c, r.c1, tmp, y, B, T, 1, 1, o2, "res.conv1");
+    sconv(c, r.c1, tmp, y, B, T, 1, 1, o2, "res.conv1", causal);
 }
 
 // SLSTM (encodec.py:272-288) on channels-last x [B][T][H]; y = lstm2(lstm1(x)) + x
@@ -749,32 +816,35 @@ int encoder_forward(Ctx& c, const float* x, int B, int T, float* z_out, bool z_n
     return t;
 }
 
-// Decoder.forward (dac.py:131-165): z channels-last [B][Tf][1024] -> y [B][300 Tf][1]
-void decoder_forward(Ctx& c, const float* z, int B, int Tf, float* y) {
-    const DecW& d = c.h->dec;
+// Decoder.forward (dac.py:131-165): z channels-last [B][Tf][1024] -> y [B][300 Tf][1].  d = the codec's decoder (causal,
+// SLSTM) or the redecoder's (non-causal, no SLSTM).
+void decoder_forward(Ctx& c, const DecW& d, const float* z, int B, int Tf, float* y) {
     size_t stage = (size_t)B * (size_t)Tf * 28800 + 1024;   // largest: [B][Tf*150][192] == [B][Tf*300][96]
     size_t first = (size_t)B * Tf * 1536;
     if (first > stage) stage = first;
     float* buf[3] = {c.alloc<float>(stage), c.alloc<float>(stage), c.alloc<float>(stage)};
     int cur = 0;
-    int t = sconv(c, d.conv0, z, buf[0], B, Tf, 1, 1, ConvOpts(), "dec.conv0");
+    int t = sconv(c, d.conv0, z, buf[0], B, Tf, 1, 1, ConvOpts(), "dec.conv0", d.causal);
     c.tap("dec_conv0", buf[0], (size_t)B * t * 1536);
-    slstm(c, d.lstm, buf[0], buf[1], B, t);
-    cur = 1;
-    c.tap("dec_lstm", buf[1], (size_t)B * t * 1536);
+    if (d.has_lstm) {
+        slstm(c, d.lstm, buf[0], buf[1], B, t);
+        cur = 1;
+        c.tap("dec_lstm", buf[1], (size_t)B * t * 1536);
+    }
     static const char* dblk_names[4] = {"dec_block1", "dec_block2", "dec_block3", "dec_block4"};
     for (int i = 0; i < 4; ++i) {
-        // Snake -> SConvTranspose1d(k=2s, stride s) as a K=2 zero-left-padded conv with s*Cout channels
+        // Snake -> SConvTranspose1d(k=2s, stride s) as a zero-padded conv with s*Cout phase-major channels:
+        // causal = 2 taps (x[t-1], x[t]), non-causal = 3 taps (x[t-1], x[t], x[t+1])
         ConvOpts o;
         o.in_snake = &d.blk[i].snake;
-        o.pad_left = 1; o.reflect = 0;
+        o.pad_left = 1; o.pad_right = d.causal ? 0 : 1; o.reflect = 0;
         int nxt = (cur + 1) % 3;
         run_conv(c, d.blk[i].up, buf[cur], buf[nxt], B, t, t, o, "dec.up");
         cur = nxt;
         t *= d.blk[i].stride;
         for (int j = 0; j < 3; ++j) {
             int tmp = (cur + 1) % 3, nx2 = (cur + 2) % 3;
-            residual_unit(c, d.blk[i].res[j], buf[cur], buf[tmp], buf[nx2], B, t);
+            residual_unit(c, d.blk[i].res[j], buf[cur], buf[tmp], buf[nx2], B, t, d.causal);
             cur = nx2;
         }
         c.tap(dblk_names[i], buf[cur], (size_t)B * t * d.blk[i].cout);
@@ -782,7 +852,54 @@ void decoder_forward(Ctx& c, const float* z, int B, int Tf, float* y) {
     ConvOpts o;
     o.in_snake = &d.snake;
     o.act = ACT_TANH;
-    sconv(c, d.conv_out, buf[cur], y, B, t, 1, 1, o, "dec.conv_out");
+    sconv(c, d.conv_out, buf[cur], y, B, t, 1, 1, o, "dec.conv_out", d.causal);
+}
+
+__global__ void embed_sum_kernel(const int64_t* __restrict__ codes_p, const int64_t* __restrict__ codes_c, int cc_stride,
+                                 const float* __restrict__ ep, const float* __restrict__ ec0, const float* __restrict__ ec1,
+                                 float* __restrict__ out, int T, int hidden, int use_p, int n_c) {
+    // one CTA per (b, t): out[b][t][:] = [use_p] E_p[codes_p[b,0,t]] + sum_{i < n_c} E_c[i][codes_c[b,i,t]]  (redecoder.py:36-46)
+    const int bt = blockIdx.x, b = bt / T, t = bt - b * T;
+    const long long ip = use_p ? codes_p[(size_t)b * T + t] : -1;
+    const long long i0 = n_c > 0 ? codes_c[(size_t)b * cc_stride + t] : -1;
+    const long long i1 = n_c > 1 ? codes_c[(size_t)b * cc_stride + T + t] : -1;
+    for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
+        float pe = 0.f, ce = 0.f;                 // the reference sums the prosody and the content embeddings apart
+        if (ip >= 0) pe += ep[(size_t)ip * hidden + c];
+        if (i0 >= 0) ce += ec0[(size_t)i0 * hidden + c];
+        if (i1 >= 0) ce += ec1[(size_t)i1 * hidden + c];
+        out[(size_t)bt * hidden + c] = pe + ce;
+    }
+}
+
+// Redecoder.forward (modules/redecoder.py:35-48): codes -> embeddings -> WN conditioned on the timbre -> conv_out.
+// codes_p [B][1][T], codes_c [B][ncc][T] int64 (device), timbre [B][1024]; returns channels-last z [B][T][1024] in workspace.
+float* redecoder_forward(Ctx& c, const int64_t* codes_p, const int64_t* codes_c, int ncc, const float* timbre, int B, int T,
+                         int use_p, int use_c, int n_c) {
+    const RedW& r = c.h->red;
+    const int Hd = r.hidden;
+    float* x = c.alloc<float>((size_t)B * T * Hd);
+    float* pin = c.alloc<float>((size_t)B * T * 2 * Hd);
+    float* acts = c.alloc<float>((size_t)B * T * Hd);
+    float* rs = c.alloc<float>((size_t)B * T * 2 * Hd);
+    float* skip = c.alloc<float>((size_t)B * T * Hd);
+    float* g = c.alloc<float>((size_t)B * 2 * Hd * r.layers);
+    float* z = c.alloc<float>((size_t)B * T * LATENT);
+    if (!c.dry) {
+        embed_sum_kernel<<<B * T, 128, 0, c.st>>>(codes_p, codes_c, ncc * T, c.W(r.emb_p), c.W(r.emb_c[0]), c.W(r.emb_c[1]), x, T, Hd,
+                                                  use_p, use_c ? n_c : 0);
+        c.check(cudaGetLastError(), "red.embed");
+    }
+    run_conv(c, r.cond, timbre, g, 1, B, B, ConvOpts(), "red.cond");        // cond_layer on g [B,1024,1]: a Linear per utterance
+    if (!c.dry) c.check_nk(cudaMemsetAsync(skip, 0, sizeof(float) * (size_t)B * T * Hd, c.st), "red.zero");
+    for (int i = 0; i < r.layers; ++i) {
+        sconv(c, r.wn_in[i], x, pin, B, T, 1, 1, ConvOpts(), "red.in", false);
+        if (!c.dry) c.check(launch_wn_gate(pin, acts, (size_t)B * T, Hd, c.st, g + (size_t)i * 2 * Hd, (size_t)T, (size_t)2 * Hd * r.layers), "red.gate");
+        sconv(c, r.wn_rs[i], acts, rs, B, T, 1, 1, ConvOpts(), "red.rs", false);
+        if (!c.dry) c.check(launch_wn_update(rs, x, skip, (size_t)B * T, Hd, i == r.layers - 1, c.st), "red.upd");
+    }
+    run_conv(c, r.conv_out, skip, z, B, T, T, ConvOpts(), "red.conv_out");
+    return z;
 }
 
 // mel [B][Tm][80] from wave [B][T] (Tm = T/300), preprocess modules/quantize.py:239-242
@@ -1014,7 +1131,7 @@ int fac_destroy(fac_handle* h) {
 const char* fac_last_error(const fac_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 int fac_load_tensor(fac_handle* h, int module, const char* key, const float* data_host, const int64_t* shape, int ndim) {
-    if (!h || !key || !data_host || module < 0 || module > 2 || ndim < 0 || ndim > 4) return FAC_ERR_INVALID;
+    if (!h || !key || !data_host || module < 0 || module >= FAC_NUM_MODULES || ndim < 0 || ndim > 4) return FAC_ERR_INVALID;
     HostTensor t;
     size_t n = 1;
     for (int i = 0; i < ndim; ++i) { if (shape[i] < 0) return FAC_ERR_INVALID; t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
@@ -1033,6 +1150,8 @@ int fac_finalize(fac_handle* h) {
         if (h->have[FAC_ENCODER]) pack_encoder(h);
         if (h->have[FAC_QUANTIZER]) pack_quantizer(h);
         if (h->have[FAC_DECODER]) pack_decoder(h);
+        if (h->have[FAC_REDECODER]) pack_redecoder(h);
+        if (h->have[FAC_REDECODER_DECODER]) pack_decoder_into(h, FAC_REDECODER_DECODER, h->dec2, false, false);
     } catch (const PackError& e) {
         h->err = e.msg;
         return FAC_ERR_STATE;
@@ -1045,7 +1164,7 @@ int fac_finalize(fac_handle* h) {
     if (e != cudaSuccess) { h->err = std::string("weight upload: ") + cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
     h->wfloats = n;
     h->pack.clear(); h->pack.shrink_to_fit();
-    for (int m = 0; m < 3; ++m) h->host[m].clear();
+    for (int m = 0; m < FAC_NUM_MODULES; ++m) h->host[m].clear();
     h->finalized = true;
     return FAC_OK;
 }
@@ -1077,7 +1196,7 @@ int fac_decode(fac_handle* h, const float* z, int B, int Tf, float* y, void* str
     return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
         float* zcl = c.alloc<float>((size_t)B * Tf * LATENT);
         if (!c.dry) c.check(launch_transpose(z, zcl, B, LATENT, Tf, c.st), "dec.z_transpose");
-        decoder_forward(c, zcl, B, Tf, y);
+        decoder_forward(c, h->dec, zcl, B, Tf, y);
     });
 }
 
@@ -1115,7 +1234,7 @@ int fac_codec_forward(fac_handle* h, const float* x, int B, int T, int n_c, floa
         encoder_forward(c, x, B, T, zcl, false);
         QuantOut o = quantizer_forward(c, zcl, x, B, T, Tz, n_c, nullptr, 0, nullptr, nullptr, timbre, codes_p,
                                        codes_c, codes_r, false);
-        decoder_forward(c, o.outs_cl, B, o.Tq, y);
+        decoder_forward(c, h->dec, o.outs_cl, B, o.Tq, y);
     });
 }
 
@@ -1138,7 +1257,7 @@ int fac_codec_forward_host(fac_handle* h, const float* x_host, int B, int T, int
         if (!c.dry) c.check_nk(cudaMemcpyAsync(xd, x_host, sizeof(float) * (size_t)B * T, cudaMemcpyHostToDevice, c.st), "h2d");
         encoder_forward(c, xd, B, T, zcl, false);
         QuantOut o = quantizer_forward(c, zcl, xd, B, T, Tz, n_c, nullptr, 0, nullptr, nullptr, nullptr, cp, cc, cr, false);
-        decoder_forward(c, o.outs_cl, B, o.Tq, yd);
+        decoder_forward(c, h->dec, o.outs_cl, B, o.Tq, yd);
         if (c.dry) return;
         c.check_nk(cudaMemcpyAsync(y_host, yd, sizeof(float) * (size_t)B * Tq * HOP, cudaMemcpyDeviceToHost, c.st), "d2h.y");
         if (codes_p_host) c.check_nk(cudaMemcpyAsync(codes_p_host, cp, sizeof(int64_t) * (size_t)B * Tq, cudaMemcpyDeviceToHost, c.st), "d2h.cp");
@@ -1149,6 +1268,46 @@ int fac_codec_forward_host(fac_handle* h, const float* x_host, int B, int T, int
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { h->err = std::string("stream sync: ") + cudaGetErrorString(e); return FAC_ERR_CUDA; }
     return FAC_OK;
+}
+
+int fac_redecode(fac_handle* h, const int64_t* codes_p, const int64_t* codes_c, int n_c_rows, const float* timbre, int B, int T,
+                 int use_p_code, int use_c_code, int n_c, float* z, void* stream) {
+    int rc = check_ready(h, FAC_REDECODER);
+    if (rc) return rc;
+    if (!codes_p || !codes_c || !timbre || !z || B <= 0 || T <= 0 || n_c < 0 || n_c > 2 || n_c > n_c_rows) {
+        h->err = "fac_redecode: bad arguments (n_c <= rows of codes_c <= 2)";
+        return FAC_ERR_INVALID;
+    }
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        float* zcl = redecoder_forward(c, codes_p, codes_c, n_c_rows, timbre, B, T, use_p_code, use_c_code, n_c);
+        if (!c.dry) c.check(launch_transpose(zcl, z, B, T, LATENT, c.st), "red.z_T");
+    });
+}
+
+int fac_redecoder_decode(fac_handle* h, const float* z, int B, int Tf, float* y, void* stream) {
+    int rc = check_ready(h, FAC_REDECODER_DECODER);
+    if (rc) return rc;
+    if (!z || !y || B <= 0 || Tf <= 0) { h->err = "fac_redecoder_decode: bad arguments"; return FAC_ERR_INVALID; }
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        float* zcl = c.alloc<float>((size_t)B * Tf * LATENT);
+        if (!c.dry) c.check(launch_transpose(z, zcl, B, LATENT, Tf, c.st), "red.dec.z_transpose");
+        decoder_forward(c, h->dec2, zcl, B, Tf, y);
+    });
+}
+
+int fac_voice_convert(fac_handle* h, const int64_t* codes_p, const int64_t* codes_c, int n_c_rows, const float* timbre, int B,
+                      int T, int use_p_code, int use_c_code, int n_c, float* y, void* stream) {
+    int rc = check_ready(h, FAC_REDECODER);
+    if (!rc) rc = check_ready(h, FAC_REDECODER_DECODER);
+    if (rc) return rc;
+    if (!codes_p || !codes_c || !timbre || !y || B <= 0 || T <= 0 || n_c < 0 || n_c > 2 || n_c > n_c_rows) {
+        h->err = "fac_voice_convert: bad arguments";
+        return FAC_ERR_INVALID;
+    }
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        float* zcl = redecoder_forward(c, codes_p, codes_c, n_c_rows, timbre, B, T, use_p_code, use_c_code, n_c);
+        decoder_forward(c, h->dec2, zcl, B, T, y);
+    });
 }
 
 int fac_rvq_create(fac_handle* h, int nq, const float* const* in_w, const float* const* in_b, const float* const* out_w,

@@ -21,15 +21,16 @@ from torch import nn
 
 from . import _lib, synth
 
-MOD_ENCODER, MOD_QUANTIZER, MOD_DECODER = 0, 1, 2
+MOD_ENCODER, MOD_QUANTIZER, MOD_DECODER, MOD_REDECODER, MOD_REDEC_DECODER = 0, 1, 2, 3, 4
 
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The current CUDA stream OF THE TENSORS' DEVICE (not of whatever device happens to be current)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class Engine:
@@ -99,8 +100,10 @@ class _RefKeyModule(nn.Module):
     _module_id = None
     _buffer_keys = ()
 
-    def __init__(self, init_sd, engine=None):
+    def __init__(self, init_sd, engine=None, module_id=None):
         super().__init__()
+        if module_id is not None:
+            self._module_id = module_id
         self._keys = list(init_sd.keys())
         self._p = nn.ParameterDict()
         for k, v in init_sd.items():
@@ -148,10 +151,18 @@ class _RefKeyModule(nn.Module):
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def _prep(self, *tensors):
+        """Every tensor argument must live on the engine's CUDA device: a CPU tensor or one on another GPU would hand the
+        kernels a foreign pointer (illegal address, sticky context error) instead of the promised FacError."""
         if self.training:
             raise NotImplementedError("facodec_b200 implements the eval-mode forward only; call .eval()")
         dev = tensors[0].device
         self._engine.sync_weights(dev)
+        for t in tensors[1:]:
+            if t is None:
+                continue
+            if t.device.type != "cuda" or (t.device.index if t.device.index is not None else torch.cuda.current_device()) != self._engine.device_index:
+                raise _lib.FacError("all inputs must be on cuda:%d (no CPU fallback, no cross-device copies); got %s"
+                                    % (self._engine.device_index, t.device))
         return self._engine.L, self._engine.handle
 
 
@@ -175,18 +186,22 @@ class Encoder(_RefKeyModule):
         B, C, T = x.shape
         assert C == 1, "encoder expects [B,1,T]"
         z = torch.empty(B, 1024, L.fac_encode_frames(T), device=x.device, dtype=torch.float32)
-        _lib.check(h, L.fac_encode(h, _ptr(x), B, T, _ptr(z), _stream()), "fac_encode")
+        _lib.check(h, L.fac_encode(h, _ptr(x), B, T, _ptr(z), _stream(x.device)), "fac_encode")
         return z
 
 
 class Decoder(_RefKeyModule):
-    """dac/model/dac.py:131-165 Decoder(1024, 1536, [6,5,5,2], causal=True, lstm=2)."""
+    """dac/model/dac.py:131-165 Decoder(1024, 1536, [6,5,5,2], causal, lstm): the codec's decoder (causal=True, lstm=2,
+    configs/config.yml) or the redecoder model's (causal=False, lstm=0, configs/config_redecoder.yml)."""
     _module_id = MOD_DECODER
 
     def __init__(self, input_channel=1024, channels=1536, rates=(6, 5, 5, 2), d_out=1, causal=True, lstm=2, engine=None):
-        if (input_channel, channels, tuple(rates), d_out, bool(causal), lstm) != (1024, 1536, (6, 5, 5, 2), 1, True, 2):
-            raise NotImplementedError("only the configs/config.yml decoder geometry is built")
-        super().__init__(synth.synth_decoder(3), engine)
+        if (input_channel, channels, tuple(rates), d_out) != (1024, 1536, (6, 5, 5, 2), 1) or \
+                (bool(causal), int(lstm)) not in ((True, 2), (False, 0)):
+            raise NotImplementedError("built: the config.yml decoder (causal, lstm=2) and the config_redecoder.yml one "
+                                      "(non-causal, lstm=0)")
+        super().__init__(synth.synth_decoder(3, lstm=int(lstm)), engine, module_id=MOD_DECODER if causal else MOD_REDEC_DECODER)
+        self.causal = bool(causal)
 
     def forward(self, z):
         L, h = self._prep(z)
@@ -194,8 +209,41 @@ class Decoder(_RefKeyModule):
         B, C, Tf = z.shape
         assert C == 1024
         y = torch.empty(B, 1, Tf * 300, device=z.device, dtype=torch.float32)
-        _lib.check(h, L.fac_decode(h, _ptr(z), B, Tf, _ptr(y), _stream()), "fac_decode")
+        fn = L.fac_decode if self.causal else L.fac_redecoder_decode
+        _lib.check(h, fn(h, _ptr(z), B, Tf, _ptr(y), _stream(z.device)), "fac_decode")
         return y
+
+
+class Redecoder(_RefKeyModule):
+    """modules/redecoder.py:5-48 Redecoder(args) with args.encoder_type == 'wavenet' (wavenet_embed_dim 512, 1 prosody + 2
+    content codebooks): forward(p_code, c_code, timbre_vec, use_p_code=True, use_c_code=True, n_c=2) -> [B, 1024, T]."""
+    _module_id = MOD_REDECODER
+
+    def __init__(self, args=None, engine=None):
+        def g(name, default):
+            if args is None:
+                return default
+            return args[name] if isinstance(args, dict) and name in args else getattr(args, name, default)
+        if (g("encoder_type", "wavenet"), g("wavenet_embed_dim", 512), g("n_p_codebooks", 1), g("n_c_codebooks", 2),
+                bool(g("decoder_causal", False))) != ("wavenet", 512, 1, 2, False):
+            raise NotImplementedError("only the configs/config_redecoder.yml geometry (wavenet, 512, 1 + 2 codebooks, non-causal)")
+        super().__init__(synth.synth_redecoder(7), engine)
+        self.n_p_codebooks, self.n_c_codebooks, self.codebook_size, self.embed_dim = 1, 2, 1024, 512
+        self.encoder_type = "wavenet"
+
+    def forward(self, p_code, c_code, timbre_vec, use_p_code=True, use_c_code=True, n_c=2):
+        L, h = self._prep(p_code, c_code, timbre_vec)
+        cp = p_code.detach().to(torch.int64).contiguous()
+        cc = c_code.detach().to(torch.int64).contiguous()
+        tv = _f32c(timbre_vec)
+        B, _, T = cp.shape
+        if cc.shape[1] < n_c:
+            raise IndexError("c_code has %d codebooks, n_c = %d" % (cc.shape[1], n_c))
+        z = torch.empty(B, 1024, T, device=cp.device, dtype=torch.float32)
+        rc = L.fac_redecode(h, _ptr(cp), _ptr(cc), cc.shape[1], _ptr(tv), B, T, int(bool(use_p_code)), int(bool(use_c_code)),
+                            int(n_c), _ptr(z), _stream(cp.device))
+        _lib.check(h, rc, "fac_redecode")
+        return z
 
 
 class FAquantizer(_RefKeyModule):
@@ -216,7 +264,9 @@ class FAquantizer(_RefKeyModule):
         self.is_timbre_norm = True
 
     def forward(self, x, wave_segments, n_c=1, n_t=2, full_waves=None, wave_lens=None, return_codes=False):
-        L, h = self._prep(x)
+        L, h = self._prep(x, wave_segments, full_waves)
+        if not (1 <= int(n_c) <= 2):
+            raise ValueError("n_c must be 1 or 2 (content codebooks)")
         x = _f32c(x)
         wave = _f32c(wave_segments)
         B, C, Tz = x.shape
@@ -237,7 +287,7 @@ class FAquantizer(_RefKeyModule):
             wl = wave_lens.detach().to(dev, torch.int64).contiguous()
             tfull = fw.shape[-1]
         rc = L.fac_quantize(h, _ptr(x), _ptr(wave), B, T, Tz, int(n_c), _ptr(fw), tfull, _ptr(wl), _ptr(outs), _ptr(zp),
-                            _ptr(zc), _ptr(zr), _ptr(losses), _ptr(timbre), _ptr(cp), _ptr(cc), _ptr(cr), _stream())
+                            _ptr(zc), _ptr(zr), _ptr(losses), _ptr(timbre), _ptr(cp), _ptr(cc), _ptr(cr), _stream(dev))
         _lib.check(h, rc, "fac_quantize")
         quantized = [zp, zc, zr]
         if return_codes:
@@ -276,7 +326,7 @@ class Codec:
         cc = torch.empty(B, n_c, Tq, device=dev, dtype=torch.int64)
         cr = torch.empty(B, 3, Tq, device=dev, dtype=torch.int64)
         timbre = torch.empty(B, 1024, device=dev)
-        rc = e.L.fac_codec_forward(e.handle, _ptr(x), B, T, n_c, _ptr(y), _ptr(cp), _ptr(cc), _ptr(cr), _ptr(timbre), _stream())
+        rc = e.L.fac_codec_forward(e.handle, _ptr(x), B, T, n_c, _ptr(y), _ptr(cp), _ptr(cc), _ptr(cr), _ptr(timbre), _stream(dev))
         _lib.check(e.handle, rc, "fac_codec_forward")
         return y, [cp, cc, cr], timbre
 
@@ -297,7 +347,7 @@ class Codec:
                    torch.empty(B, 3, Tq, dtype=torch.int64, pin_memory=pin))
         y, cp, cc, cr = out
         with torch.cuda.device(dev):
-            rc = e.L.fac_codec_forward_host(e.handle, _ptr(x_host), B, T, n_c, _ptr(y), _ptr(cp), _ptr(cc), _ptr(cr), _stream())
+            rc = e.L.fac_codec_forward_host(e.handle, _ptr(x_host), B, T, n_c, _ptr(y), _ptr(cp), _ptr(cc), _ptr(cr), _stream(dev))
         _lib.check(e.handle, rc, "fac_codec_forward_host")
         return y, [cp, cc, cr]
 
@@ -305,12 +355,47 @@ class Codec:
         return self.engine.L.fac_last_launch_count(self.engine.handle)
 
 
+class VoiceConverter:
+    """reconstruct_redecoder.py:118-121 as one C call: z = model.encoder(codes[0], codes[1], timbre, use_p_code, n_c);
+    wave = model.decoder(z) on a build_model(stage='redecoder') Munch, latents resident."""
+
+    def __init__(self, model):
+        self.model = model
+        self.engine = model.encoder._engine
+
+    def convert(self, codes, timbre, use_p_code=False, use_c_code=True, n_c=1):
+        e = self.engine
+        dev = codes[0].device
+        e.sync_weights(dev)
+        cp = codes[0].detach().to(torch.int64).contiguous()
+        cc = codes[1].detach().to(torch.int64).contiguous()
+        tv = _f32c(timbre)
+        B, _, T = cp.shape
+        y = torch.empty(B, 1, T * 300, device=dev)
+        rc = e.L.fac_voice_convert(e.handle, _ptr(cp), _ptr(cc), cc.shape[1], _ptr(tv), B, T, int(bool(use_p_code)),
+                                   int(bool(use_c_code)), int(n_c), _ptr(y), _stream(dev))
+        _lib.check(e.handle, rc, "fac_voice_convert")
+        return y
+
+
 def build_model(args=None, stage="codec"):
     """Mirror of modules/commons.py:283-348 build_model(args, stage='codec') for the hot-path
     modules: returns Munch(encoder, quantizer, decoder) (discriminator / fa_predictors are training-only
-    and out of scope).  ``args`` may be the reference's recursive_munch(config['model_params']) or None."""
+    and out of scope).  ``args`` may be the reference's recursive_munch(config['model_params']) or None.
+    stage='redecoder' returns the voice-conversion model Munch(encoder=Redecoder, decoder=Decoder(non-causal, no LSTM))."""
+    if stage == "redecoder":
+        # modules/commons.py:385-412: Munch(encoder=Redecoder(args), decoder=Decoder(causal=args.decoder_causal, lstm=args.decoder_lstm))
+        eng = Engine()
+
+        def ga(name, default):
+            if args is None:
+                return default
+            return args[name] if isinstance(args, dict) and name in args else getattr(args, name, default)
+        return Munch(encoder=Redecoder(args, engine=eng),
+                     decoder=Decoder(input_channel=1024, channels=1536, rates=(6, 5, 5, 2), causal=ga("decoder_causal", False),
+                                     lstm=ga("decoder_lstm", 0), engine=eng))
     if stage != "codec":
-        raise NotImplementedError("only stage='codec' is built")
+        raise NotImplementedError("built stages: 'codec' and 'redecoder'")
 
     def g(obj, name, default):
         if obj is None:

@@ -33,7 +33,10 @@ enum fac_status {
     FAC_ERR_UNSUPPORTED = -4
 };
 
-enum fac_module { FAC_ENCODER = 0, FAC_QUANTIZER = 1, FAC_DECODER = 2 };
+/* FAC_REDECODER / FAC_REDECODER_DECODER: the voice-conversion model of build_model(args, stage='redecoder')
+ * (modules/commons.py:385-412): modules/redecoder.py Redecoder (wavenet) and its Decoder(causal=False, lstm=0). */
+enum fac_module { FAC_ENCODER = 0, FAC_QUANTIZER = 1, FAC_DECODER = 2, FAC_REDECODER = 3, FAC_REDECODER_DECODER = 4,
+                  FAC_NUM_MODULES = 5 };
 
 /* Library/ABI version (bumped on any signature change). */
 int fac_abi_version(void);
@@ -87,6 +90,18 @@ int fac_codec_forward(fac_handle* h, const float* x, int B, int T, int n_c, floa
 /* Same, HOST buffers (pinned recommended): H2D of x, forward, D2H of y + codes, stream sync. */
 int fac_codec_forward_host(fac_handle* h, const float* x_host, int B, int T, int n_c, float* y_host,
                            int64_t* codes_p_host, int64_t* codes_c_host, int64_t* codes_r_host, void* stream);
+
+/* Voice conversion (reconstruct_redecoder.py:108-122, webui.py:68-81).
+ * fac_redecode = model.encoder(p_code, c_code, timbre, use_p_code, use_c_code, n_c) of the redecoder model,
+ * modules/redecoder.py:35-48: codes_p [B,1,T], codes_c [B,n_c_rows,T] int64 (device; the codec's codes[0], codes[1]),
+ * timbre [B,1024] -> z [B,1024,T].  n_c <= n_c_rows <= 2 content codebooks are summed.
+ * fac_redecoder_decode = that model's decoder (non-causal, no SLSTM: config_redecoder.yml decoder_causal / decoder_lstm),
+ * z [B,1024,Tf] -> y [B,1,300*Tf].  fac_voice_convert runs both with the latents kept channels-last on the device. */
+int fac_redecode(fac_handle* h, const int64_t* codes_p, const int64_t* codes_c, int n_c_rows, const float* timbre,
+                 int B, int T, int use_p_code, int use_c_code, int n_c, float* z, void* stream);
+int fac_redecoder_decode(fac_handle* h, const float* z, int B, int Tf, float* y, void* stream);
+int fac_voice_convert(fac_handle* h, const int64_t* codes_p, const int64_t* codes_c, int n_c_rows, const float* timbre,
+                      int B, int T, int use_p_code, int use_c_code, int n_c, float* y, void* stream);
 
 /* quantize/rvq.py:27-75 ResidualVQ.forward (eval) over quantize/fvq.py FactorizedVectorQuantize,
  * dim=1024, codebook_dim=8, 2^10 entries (BASELINE configs[3]).  Parameters are passed directly

@@ -247,3 +247,78 @@ def test_encoder_f16x2_option_keeps_parity(built_lib):
             assert np.array_equal(t.cpu().numpy(), g[k]), k
         assert np.abs(z.cpu().numpy() - g["z"]).max() <= Z_RTOL * np.abs(g["z"]).max()
         assert rms(y, g["y"]) <= RMS_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: voice conversion (modules/redecoder.py + the non-causal, LSTM-free decoder; reconstruct_redecoder.py:108-122)
+# ---------------------------------------------------------------------------------------------------------------
+_REDEC = {}
+
+
+def redec_model_for(seed):
+    import facodec_b200 as fb
+    from facodec_b200 import synth
+    if seed not in _REDEC:
+        _REDEC.clear()
+        m = fb.build_model(stage="redecoder")
+        sds = synth.synth_redecoder_state_dicts(seed)
+        for k in ("encoder", "decoder"):
+            m[k].load_state_dict(sds[k])
+            m[k].eval()
+        _REDEC[seed] = m
+    return _REDEC[seed]
+
+
+@pytest.mark.parametrize("name", ["redec_b2_t7200_vc", "redec_b2_t7200_full", "redec_b3_t1500_short"])
+def test_redecoder_golden(name, built_lib):
+    """Fixtures made from the imported reference (oracle/make_golden.py redecoder): codes + timbre of a codec fixture ->
+    redecoder.encoder -> redecoder.decoder.  z within fp32-class tolerance, waveform RMS <= 1e-4; the fused
+    fac_voice_convert call gives the same bits as the two-call surface."""
+    import facodec_b200 as fb
+    from conftest import REDEC_CASES
+    c = REDEC_CASES[name]
+    g = load_golden(name)
+    src = load_golden(c["src"])
+    m = redec_model_for(c["wseed"])
+    dev = torch.device("cuda:0")
+    cp, cc, timbre = (torch.from_numpy(src[k]).to(dev) for k in ("codes_p", "codes_c", "timbre"))
+    z = m.encoder(cp, cc, timbre, use_p_code=c["use_p"], n_c=c["n_c"])
+    y = m.decoder(z)
+    torch.cuda.synchronize()
+    assert tuple(z.shape) == g["z"].shape and tuple(y.shape) == g["y"].shape
+    zerr = np.abs(z.cpu().numpy() - g["z"]).max()
+    assert zerr <= 2e-4 * max(1.0, np.abs(g["z"]).max()), f"z max err {zerr}"          # bf16 hi/lo class (16 mantissa bits)
+    assert rms(y, g["y"]) <= RMS_TOL
+    # teacher-forced decoder on the reference's own z
+    assert rms(m.decoder(torch.from_numpy(g["z"]).to(dev)), g["y"]) <= RMS_TOL
+    y2 = fb.VoiceConverter(m).convert([cp, cc], timbre, use_p_code=c["use_p"], n_c=c["n_c"])
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y)
+
+
+def test_voice_conversion_flow_vs_live_oracle(built_lib):
+    """reconstruct_redecoder.py:108-122 end to end on this box: codec encode of a source and a reference utterance, then
+    model.encoder(codes[0], codes[1], timbre_of_reference, use_p_code=False, n_c=1) -> model.decoder, against the oracle."""
+    from facodec_b200 import synth
+    from oracle import facodec_oracle as O
+    codec = model_for(0)
+    sds = state_dicts(0)
+    rm = redec_model_for(0)
+    rsds = synth.synth_redecoder_state_dicts(0)
+    src = synth.synth_waves(1, 9000, seed=41)
+    ref = synth.synth_waves(1, 6000, seed=42)
+    dev = torch.device("cuda:0")
+    _, q, _ = run_model(codec, src, 2, {})
+    _, q2, _ = run_model(codec, ref, 2, {})
+    y = rm.decoder(rm.encoder(q[5][0], q[5][1], q2[4], use_p_code=False, n_c=1))
+    torch.cuda.synchronize()
+    _, qo, _ = O.codec_forward(sds, src, n_c=2)
+    _, qo2, _ = O.codec_forward(sds, ref, n_c=2)
+    zo, yo = O.voice_convert(rsds, qo[5], qo2[4])
+    assert torch.equal(q[5][0].cpu(), qo[5][0]) and torch.equal(q[5][1].cpu(), qo[5][1])
+    assert rms(y, yo) <= RMS_TOL
+    with pytest.raises(IndexError):
+        rm.encoder(q[5][0], q[5][1][:, :1], q2[4], n_c=2)
+    import facodec_b200 as fb
+    with pytest.raises(fb.FacError):
+        rm.encoder(q[5][0], q[5][1].cpu(), q2[4])                    # input on another device: no silent foreign pointer
