@@ -86,6 +86,8 @@ struct fac_handle {
     EncW enc; DecW dec; QuantW qw;
     RedW red; DecW dec2;            // voice-conversion model: Redecoder + its non-causal, LSTM-free decoder
     std::vector<RvqSet> rvqs; std::vector<float*> rvq_arenas;
+    struct HeadSet;                 // modules/quantize.py:106-125 CNNLSTM instances (fac_head_*)
+    std::vector<HeadSet*> heads;
     char* ws = nullptr; size_t ws_bytes = 0;
     int launches = 0;
     // tcgen05 3xTF32 path (fac_set_option "tensor_cores"): 0 = never, 1 = layers downstream of the VQ only
@@ -102,6 +104,8 @@ struct fac_handle {
     int tc_occ2 = 256;              // fac_set_option "tc_occ2_maxn": conv_tc tiles with N <= this are planned for two CTAs per SM (0 = off)
     bool dec_bf16 = true;           // decoder-side layers use the bf16x3 split (fac_set_option "decoder_bf16")
     float* aa_filter = nullptr;
+    // dataset-side mel (meldataset.py:29-47: MelSpectrogram with its default sample_rate 16000): own constants, built lazily
+    float* mel16_arena = nullptr; ConvW mel16_dft, mel16_dft_tc; size_t mel16_fb = 0;
     // optional per-kernel-family timing (fac_profile_*): CUDA events around every launch
     bool profiling = false;
     struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
@@ -110,6 +114,19 @@ struct fac_handle {
     std::map<std::string, ProfAgg> prof_agg;
     // debug taps: named intermediates copied out during a forward (fac_debug_tap)
     std::map<std::string, std::pair<float*, size_t>> taps;
+};
+
+// One CNNLSTM predictor head (modules/quantize.py:106-125): 3 ResidualUnits (alias-free SnakeBeta, k7 conv dilation
+// 1/2/3 with zero padding, alias-free SnakeBeta, 1x1 conv, +x), a final alias-free SnakeBeta, nheads Linear layers.
+// Built through a private staging handle so that the conv packing code is shared; weights live in their own arena.
+struct fac_handle::HeadSet {
+    int indim = 0, outdim = 0, nheads = 0, global_pred = 0;
+    struct Unit { size_t a1, b1, a2, b2; ConvW c7, c1; int dil; } unit[3];
+    size_t af, bf;                  // final activation exp(alpha), exp(beta)
+    ConvW lin[8];
+    std::map<std::string, HostTensor> staged;
+    float* arena = nullptr;
+    bool ready = false;
 };
 
 namespace {
@@ -470,6 +487,31 @@ void pack_redecoder(fac_handle* h) {
         throw PackError{"redecoder geometry (expects WN(512, kernel 5, 16 layers, gin 1024))"};
 }
 
+// The mel front-end's constants: [1200][2*1025] windowed DFT basis (fp64 -> fp32), its tensor-core variant, the filterbank.
+void pack_mel_frontend(fac_handle* h, ConvW& dft, ConvW& dft_tc, size_t& fb_off, const float* win, const float* fb) {
+    dft.Cin = 1; dft.Cout = 2 * N_BINS; dft.K = WIN; dft.ldw = SPEC_LD;
+    dft.w = pack_alloc(h, (size_t)WIN * SPEC_LD);
+    dft.b = 0;
+    const int left = (N_FFT - WIN) / 2;
+    for (int n = 0; n < WIN; ++n)
+        for (int k = 0; k < N_BINS; ++k) {
+            // reduce the phase index mod N_FFT in integers so the fp64 angle stays small
+            long long ph = ((long long)k * (n + left)) % N_FFT;
+            double ang = 2.0 * M_PI * (double)ph / (double)N_FFT;
+            h->pack[dft.w + (size_t)n * SPEC_LD + 2 * k] = (float)((double)win[n] * std::cos(ang));
+            h->pack[dft.w + (size_t)n * SPEC_LD + 2 * k + 1] = (float)(-(double)win[n] * std::sin(ang));
+        }
+    // tensor-core variant: [1200][2176] with zero columns beyond 2*1025, zero bias
+    dft_tc.Cin = WIN; dft_tc.Cout = SPEC_TC_LD; dft_tc.K = 1; dft_tc.ldw = SPEC_TC_LD;
+    dft_tc.w = pack_alloc(h, (size_t)WIN * SPEC_TC_LD);
+    for (int n = 0; n < WIN; ++n)
+        for (int k = 0; k < 2 * N_BINS; ++k) h->pack[dft_tc.w + (size_t)n * SPEC_TC_LD + k] = h->pack[dft.w + (size_t)n * SPEC_LD + k];
+    dft_tc.b = pack_alloc(h, SPEC_TC_LD);
+    attach_tc(h, dft_tc, 1, true);
+    fb_off = pack_alloc(h, (size_t)N_BINS * N_MELS);
+    for (size_t i = 0; i < (size_t)N_BINS * N_MELS; ++i) h->pack[fb_off + i] = fb[i];
+}
+
 void pack_quantizer(fac_handle* h) {
     QuantW& q = h->qw;
     const int m = FAC_QUANTIZER;
@@ -497,27 +539,7 @@ void pack_quantizer(fac_handle* h) {
     const HostTensor& win = need(h, m, "to_mel.spectrogram.window");
     const HostTensor& fb = need(h, m, "to_mel.mel_scale.fb");
     if ((int)win.numel() != WIN || fb.shape[0] != N_BINS || fb.shape[1] != N_MELS) throw PackError{"mel buffers shape"};
-    q.dft.Cin = 1; q.dft.Cout = 2 * N_BINS; q.dft.K = WIN; q.dft.ldw = SPEC_LD;
-    q.dft.w = pack_alloc(h, (size_t)WIN * SPEC_LD);
-    q.dft.b = 0;
-    const int left = (N_FFT - WIN) / 2;
-    for (int n = 0; n < WIN; ++n)
-        for (int k = 0; k < N_BINS; ++k) {
-            // reduce the phase index mod N_FFT in integers so the fp64 angle stays small
-            long long ph = ((long long)k * (n + left)) % N_FFT;
-            double ang = 2.0 * M_PI * (double)ph / (double)N_FFT;
-            h->pack[q.dft.w + (size_t)n * SPEC_LD + 2 * k] = (float)((double)win.data[n] * std::cos(ang));
-            h->pack[q.dft.w + (size_t)n * SPEC_LD + 2 * k + 1] = (float)(-(double)win.data[n] * std::sin(ang));
-        }
-    // tensor-core variant: [1200][2176] with zero columns beyond 2*1025, zero bias
-    q.dft_tc.Cin = WIN; q.dft_tc.Cout = SPEC_TC_LD; q.dft_tc.K = 1; q.dft_tc.ldw = SPEC_TC_LD;
-    q.dft_tc.w = pack_alloc(h, (size_t)WIN * SPEC_TC_LD);
-    for (int n = 0; n < WIN; ++n)
-        for (int k = 0; k < 2 * N_BINS; ++k) h->pack[q.dft_tc.w + (size_t)n * SPEC_TC_LD + k] = h->pack[q.dft.w + (size_t)n * SPEC_LD + k];
-    q.dft_tc.b = pack_alloc(h, SPEC_TC_LD);
-    attach_tc(h, q.dft_tc, 1, true);
-    q.fb = pack_alloc(h, (size_t)N_BINS * N_MELS);
-    for (size_t i = 0; i < (size_t)N_BINS * N_MELS; ++i) h->pack[q.fb + i] = fb.data[i];
+    pack_mel_frontend(h, q.dft, q.dft_tc, q.fb, win.data.data(), fb.data.data());
 }
 
 // ------------------------------------------------------------------------------------------
@@ -903,15 +925,17 @@ float* redecoder_forward(Ctx& c, const int64_t* codes_p, const int64_t* codes_c,
 }
 
 // mel [B][Tm][80] from wave [B][T] (Tm = T/300), preprocess modules/quantize.py:239-242
-float* mel_forward(Ctx& c, const float* wave, int B, int T, int Tm) {
-    const QuantW& q = c.h->qw;
-    if (c.h->use_tc >= 2 && q.dft_tc.tc) {
+struct MelW { const ConvW* dft; const ConvW* dft_tc; size_t fb; };
+float* mel_forward(Ctx& c, const float* wave, int B, int T, int Tm, const MelW* mw = nullptr) {
+    MelW q;
+    if (mw) q = *mw; else { q.dft = &c.h->qw.dft; q.dft_tc = &c.h->qw.dft_tc; q.fb = c.h->qw.fb; }
+    if (c.h->use_tc >= 2 && q.dft_tc->tc) {
         // frames gather + K=1 GEMM on the promoted tcgen05 kernel (the mel feeds the prosody VQ: fp32-grade sums)
         float* frames = c.alloc<float>((size_t)B * Tm * WIN);
         float* spec = c.alloc<float>((size_t)B * Tm * SPEC_TC_LD);
         float* mel = c.alloc<float>((size_t)B * Tm * N_MELS);
         if (!c.dry) c.check(launch_stft_frames(wave, frames, B, T, Tm, HOP, WIN, N_FFT / 2 - (N_FFT - WIN) / 2, c.st), "mel.frames");
-        run_conv(c, q.dft_tc, frames, spec, 1, B * Tm, B * Tm, ConvOpts(), "mel.dft");
+        run_conv(c, *q.dft_tc, frames, spec, 1, B * Tm, B * Tm, ConvOpts(), "mel.dft");
         if (!c.dry) c.check(launch_mel_from_spec(spec, SPEC_TC_LD, c.W(q.fb), mel, B, Tm, Tm, c.st), "mel.fb");
         c.tap("mel80", mel, (size_t)B * Tm * N_MELS);
         return mel;
@@ -925,7 +949,7 @@ float* mel_forward(Ctx& c, const float* wave, int B, int T, int Tm) {
     o.reflect = 1;
     o.no_bias = true;
     o.ldy = SPEC_LD;
-    run_conv(c, q.dft, wave, spec, B, T, Tm, o, "mel.dft");
+    run_conv(c, *q.dft, wave, spec, B, T, Tm, o, "mel.dft");
     if (!c.dry) c.check(launch_mel_from_spec(spec, SPEC_LD, c.W(q.fb), mel, B, Tm, Tm, c.st), "mel.fb");
     c.tap("mel80", mel, (size_t)B * Tm * N_MELS);
     return mel;
@@ -1123,7 +1147,9 @@ int fac_destroy(fac_handle* h) {
     if (h->warena) cudaFree(h->warena);
     if (h->ws) cudaFree(h->ws);
     if (h->aa_filter) cudaFree(h->aa_filter);
+    if (h->mel16_arena) cudaFree(h->mel16_arena);
     for (float* p : h->rvq_arenas) cudaFree(p);
+    for (auto* hs : h->heads) { if (hs->arena) cudaFree(hs->arena); delete hs; }
     delete h;
     return FAC_OK;
 }
@@ -1310,6 +1336,177 @@ int fac_voice_convert(fac_handle* h, const int64_t* codes_p, const int64_t* code
     });
 }
 
+// meldataset.py:37-47 preprocess: torchaudio MelSpectrogram(n_mels=80, n_fft=2048, win_length=1200, hop_length=300) with
+// its DEFAULT sample_rate = 16000 (HTK filterbank over [0, 8000] Hz -- not the quantizer's 24 kHz one), centre = True
+// (T/300 + 1 frames), then (log(1e-5 + mel) + 4) / 4.
+int fac_dataset_mel(fac_handle* h, const float* wave, int B, int T, float* mel, void* stream) {
+    if (!h || !wave || !mel || B <= 0) return FAC_ERR_INVALID;
+    if (T <= N_FFT / 2) { h->err = "fac_dataset_mel: wave shorter than the STFT reflect padding (1024), as torch.stft"; return FAC_ERR_INVALID; }
+    cudaSetDevice(h->device);
+    if (!h->mel16_arena) {
+        fac_handle tmp;
+        tmp.device = h->device;
+        std::vector<float> win(WIN), fb((size_t)N_BINS * N_MELS);
+        for (int i = 0; i < WIN; ++i) win[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)WIN));   // periodic Hann
+        // torchaudio.functional.melscale_fbanks(n_freqs=1025, f_min=0, f_max=8000, n_mels=80, sample_rate=16000, norm=None, "htk")
+        const double sr = 16000.0, f_max = 8000.0;
+        auto hz2mel = [](double f) { return 2595.0 * std::log10(1.0 + f / 700.0); };
+        auto mel2hz = [](double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); };
+        std::vector<double> fpts(N_MELS + 2);
+        for (int i = 0; i < N_MELS + 2; ++i) fpts[i] = mel2hz(hz2mel(0.0) + (hz2mel(f_max) - hz2mel(0.0)) * i / (N_MELS + 1));
+        for (int k = 0; k < N_BINS; ++k) {
+            const double f = (sr / 2.0) * k / (N_BINS - 1);
+            for (int m = 0; m < N_MELS; ++m) {
+                const double down = (f - fpts[m]) / (fpts[m + 1] - fpts[m]), up = (fpts[m + 2] - f) / (fpts[m + 2] - fpts[m + 1]);
+                fb[(size_t)k * N_MELS + m] = (float)std::max(0.0, std::min(down, up));
+            }
+        }
+        try { pack_mel_frontend(&tmp, h->mel16_dft, h->mel16_dft_tc, h->mel16_fb, win.data(), fb.data()); }
+        catch (const PackError& e) { h->err = e.msg; return FAC_ERR_STATE; }
+        cudaError_t e = cudaMalloc(&h->mel16_arena, (tmp.pack.size() + 64) * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->mel16_arena, tmp.pack.data(), tmp.pack.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); h->mel16_arena = nullptr; return FAC_ERR_CUDA; }
+    }
+    float* saved = h->warena;
+    h->warena = h->mel16_arena;
+    const int F = T / HOP + 1;
+    int rc = two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        MelW mw{&h->mel16_dft, &h->mel16_dft_tc, h->mel16_fb};
+        c.vq_critical = true;                        // fp32-faithful DFT (the promoted tensor-core kernel)
+        float* mel_cl = mel_forward(c, wave, B, T, F, &mw);
+        c.vq_critical = false;
+        if (!c.dry) c.check(launch_transpose(mel_cl, mel, B, F, N_MELS, c.st), "mel16.T");
+    });
+    h->warena = saved;
+    return rc;
+}
+
+// ---- predictor heads (training-side in the reference, forward only here) ----
+int fac_head_begin(fac_handle* h) {
+    if (!h) return FAC_ERR_INVALID;
+    h->heads.push_back(new fac_handle::HeadSet());
+    return (int)h->heads.size() - 1;
+}
+
+int fac_head_tensor(fac_handle* h, int head_id, const char* key, const float* data_host, const int64_t* shape, int ndim) {
+    if (!h || head_id < 0 || head_id >= (int)h->heads.size() || !key || !data_host || ndim < 0 || ndim > 4) return FAC_ERR_INVALID;
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) { if (shape[i] < 0) return FAC_ERR_INVALID; t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+    t.data.assign(data_host, data_host + n);
+    h->heads[head_id]->staged[key] = std::move(t);
+    h->heads[head_id]->ready = false;
+    return FAC_OK;
+}
+
+int fac_head_finalize(fac_handle* h, int head_id, int indim, int outdim, int nheads, int global_pred) {
+    if (!h || head_id < 0 || head_id >= (int)h->heads.size() || indim <= 0 || outdim <= 0 || nheads < 1 || nheads > 8) return FAC_ERR_INVALID;
+    if (indim % 16 != 0) { h->err = "fac_head_finalize: indim must be a multiple of 16"; return FAC_ERR_UNSUPPORTED; }
+    fac_handle::HeadSet& hs = *h->heads[head_id];
+    fac_handle tmp;                          // staging handle: reuses pack_conv / folded_weight on hs.staged
+    tmp.device = h->device;
+    tmp.host[0] = hs.staged;
+    hs.indim = indim; hs.outdim = outdim; hs.nheads = nheads; hs.global_pred = global_pred;
+    try {
+        auto expv = [&](const std::string& key) {
+            const HostTensor& t = need(&tmp, 0, key);
+            if ((int)t.numel() != indim) throw PackError{"shape of " + key};
+            size_t off = pack_alloc(&tmp, indim);
+            for (int i = 0; i < indim; ++i) tmp.pack[off + i] = expf(t.data[i]);     // alpha_logscale=True: exp() of the parameter
+            return off;
+        };
+        const int dils[3] = {1, 2, 3};
+        for (int j = 0; j < 3; ++j) {
+            const std::string p = "model." + std::to_string(j);
+            auto& u = hs.unit[j];
+            u.dil = dils[j];
+            u.a1 = expv(p + ".block.0.act.alpha"); u.b1 = expv(p + ".block.0.act.beta");
+            u.c7 = pack_conv(&tmp, 0, p + ".block.1");
+            u.a2 = expv(p + ".block.2.act.alpha"); u.b2 = expv(p + ".block.2.act.beta");
+            u.c1 = pack_conv(&tmp, 0, p + ".block.3");
+            if (u.c7.Cin != indim || u.c7.Cout != indim || u.c7.K != 7 || u.c1.K != 1) throw PackError{"head ResidualUnit geometry"};
+        }
+        hs.af = expv("model.3.act.alpha"); hs.bf = expv("model.3.act.beta");
+        for (int i = 0; i < nheads; ++i) {
+            hs.lin[i] = pack_conv(&tmp, 0, "heads." + std::to_string(i));
+            if (hs.lin[i].Cin != indim || hs.lin[i].Cout != outdim) throw PackError{"head Linear geometry"};
+        }
+    } catch (const PackError& e) {
+        h->err = e.msg;
+        return FAC_ERR_STATE;
+    }
+    cudaSetDevice(h->device);
+    if (hs.arena) { cudaDeviceSynchronize(); cudaFree(hs.arena); hs.arena = nullptr; }
+    cudaError_t e = cudaMalloc(&hs.arena, (tmp.pack.size() + 64) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(hs.arena, tmp.pack.data(), tmp.pack.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
+    hs.staged.clear();
+    hs.ready = true;
+    return FAC_OK;
+}
+
+static int ensure_aa_filter(fac_handle* h);
+
+int fac_head_forward(fac_handle* h, int head_id, const float* x, int B, int T, float* const* outs, void* stream) {
+    if (!h || head_id < 0 || head_id >= (int)h->heads.size() || !x || !outs || B <= 0 || T <= 0) return FAC_ERR_INVALID;
+    fac_handle::HeadSet& hs = *h->heads[head_id];
+    if (!hs.ready) { h->err = "fac_head_forward: head not finalized"; return FAC_ERR_STATE; }
+    int rc = ensure_aa_filter(h);
+    if (rc) return rc;
+    // the conv launch helpers read weights through h->warena: point it at this head's arena for the duration of the call
+    float* saved = h->warena;
+    h->warena = hs.arena;
+    const int C = hs.indim;
+    rc = two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        const size_t n = (size_t)B * T * C;
+        float* a_nct = c.alloc<float>(n);
+        float* a_cl = c.alloc<float>(n);
+        float* c7_cl = c.alloc<float>(n);
+        float* c7_nct = c.alloc<float>(n);
+        float* x_cl[2] = {c.alloc<float>(n), c.alloc<float>(n)};
+        float* x_nct = c.alloc<float>(n);
+        float* pooled = c.alloc<float>((size_t)B * C);
+        auto act = [&](const float* src, float* dst, size_t al, size_t be, const char* nm) {
+            if (!c.dry) c.check(launch_alias_free_act(src, dst, B, C, T, h->aa_filter, c.W(al), c.W(be), c.st), nm);
+        };
+        auto tr = [&](const float* src, float* dst, int R, int Cc, const char* nm) {     // [B][R][Cc] -> [B][Cc][R]
+            if (!c.dry) c.check(launch_transpose(src, dst, B, R, Cc, c.st), nm);
+        };
+        tr(x, x_cl[0], C, T, "head.x_T");                                              // NCT -> channels-last
+        const float* cur_nct = x;
+        int cur = 0;
+        for (int j = 0; j < 3; ++j) {
+            const auto& u = hs.unit[j];
+            act(cur_nct, a_nct, u.a1, u.b1, "head.act1");
+            tr(a_nct, a_cl, C, T, "head.a_T");
+            ConvOpts o7;
+            o7.dil = u.dil; o7.pad_left = 3 * u.dil; o7.pad_right = 3 * u.dil; o7.reflect = 0;     // padding = ((7-1)*d)//2, zeros
+            run_conv(c, u.c7, a_cl, c7_cl, B, T, T, o7, "head.conv7");
+            tr(c7_cl, c7_nct, T, C, "head.c7_T");
+            act(c7_nct, a_nct, u.a2, u.b2, "head.act2");
+            tr(a_nct, a_cl, C, T, "head.b_T");
+            ConvOpts o1;
+            o1.res = x_cl[cur];
+            run_conv(c, u.c1, a_cl, x_cl[cur ^ 1], B, T, T, o1, "head.conv1");
+            cur ^= 1;
+            tr(x_cl[cur], x_nct, T, C, "head.y_T");
+            cur_nct = x_nct;
+        }
+        act(cur_nct, a_nct, hs.af, hs.bf, "head.act_final");
+        tr(a_nct, a_cl, C, T, "head.f_T");                                             // Rearrange("b c t -> b t c")
+        for (int i = 0; i < hs.nheads; ++i) {
+            if (hs.global_pred) {
+                if (!c.dry) c.check(launch_mean_pool(a_cl, pooled, B, T, C, nullptr, c.st), "head.mean");
+                run_conv(c, hs.lin[i], pooled, outs[i], 1, B, B, ConvOpts(), "head.linear");
+            } else {
+                run_conv(c, hs.lin[i], a_cl, outs[i], 1, B * T, B * T, ConvOpts(), "head.linear");
+            }
+        }
+    });
+    h->warena = saved;
+    return rc;
+}
+
 int fac_rvq_create(fac_handle* h, int nq, const float* const* in_w, const float* const* in_b, const float* const* out_w,
                    const float* const* out_b, const float* const* codebook) {
     if (!h || nq < 1 || nq > 8) return FAC_ERR_INVALID;
@@ -1357,9 +1554,7 @@ int fac_rvq_forward(fac_handle* h, int rvq_id, const float* x, int B, int T, int
     });
 }
 
-int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int act, const float* alpha,
-                       const float* beta, float* y, void* stream) {
-    if (!h || !x || !y || B <= 0 || C <= 0 || T <= 0 || (act == 1 && (!alpha || !beta))) return FAC_ERR_INVALID;
+static int ensure_aa_filter(fac_handle* h) {
     cudaSetDevice(h->device);
     if (!h->aa_filter) {
         // kaiser_sinc_filter1d(cutoff=0.25, half_width=0.3, kernel_size=12), alias_free_torch/filter.py:27-58
@@ -1386,6 +1581,14 @@ int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int a
         if (e == cudaSuccess) e = cudaMemcpy(h->aa_filter, f, sizeof(f), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); return FAC_ERR_CUDA; }
     }
+    return FAC_OK;
+}
+
+int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int act, const float* alpha,
+                       const float* beta, float* y, void* stream) {
+    if (!h || !x || !y || B <= 0 || C <= 0 || T <= 0 || (act == 1 && (!alpha || !beta))) return FAC_ERR_INVALID;
+    int rc0 = ensure_aa_filter(h);
+    if (rc0) return rc0;
     cudaError_t e = launch_alias_free_act(x, y, B, C, T, h->aa_filter, act == 1 ? alpha : nullptr, act == 1 ? beta : nullptr,
                                           (cudaStream_t)stream);
     if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }

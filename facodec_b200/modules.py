@@ -530,3 +530,84 @@ class Activation1d(nn.Module):
         rc = e.L.fac_alias_free_act(e.handle, _ptr(x), B, C, T, 0 if self.identity else 1, _ptr(a), _ptr(b), _ptr(y), _stream())
         _lib.check(e.handle, rc, "fac_alias_free_act")
         return y
+
+
+
+class CNNLSTM(nn.Module):
+    """modules/quantize.py:106-125 CNNLSTM(indim, outdim, head, global_pred=False), forward only (the FApredictors heads are
+    training-side in the reference: SURVEY.md 8f rank 1).  state_dict keys follow the reference, including the registered
+    Kaiser-sinc filter buffers of every Activation1d (accepted on load, regenerated on save).  forward(x [B, indim, T]) ->
+    list of ``head`` tensors [B, T, outdim] ([B, outdim] when global_pred)."""
+
+    def __init__(self, indim, outdim, head, global_pred=False, seed=0):
+        super().__init__()
+        self.indim, self.outdim, self.nheads, self.global_pred = int(indim), int(outdim), int(head), bool(global_pred)
+        sd = synth.synth_cnnlstm(500 + seed, self.indim, self.outdim, self.nheads)
+        self._keys = list(sd.keys())
+        self._p = nn.ParameterDict({k.replace(".", "/"): nn.Parameter(v, requires_grad=False) for k, v in sd.items()})
+        self._engine = Engine()
+        self._head_id = None
+        self._tag = None
+
+    @staticmethod
+    def _filter():
+        from math import pi
+        ks, half = 12, 6
+        A = 2.285 * (half - 1) * pi * (4 * 0.3) + 7.95
+        beta = 0.1102 * (A - 8.7) if A > 50.0 else (0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21.0) if A >= 21.0 else 0.0)
+        win = torch.kaiser_window(ks, beta=beta, periodic=False)
+        time = torch.arange(-half, half) + 0.5
+        f = 2 * 0.25 * win * torch.sinc(2 * 0.25 * time)
+        return (f / f.sum()).view(1, 1, ks)
+
+    def state_dict(self, *a, prefix="", **kw):
+        out = OrderedDict()
+        for k in self._keys:
+            out[prefix + k] = self._p[k.replace(".", "/")].detach()
+            if k.endswith("act.beta"):
+                base = k[:-len("act.beta")]
+                out[prefix + base + "upsample.filter"] = self._filter()
+                out[prefix + base + "downsample.lowpass.filter"] = self._filter()
+        return out
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        missing = [k for k in self._keys if k not in sd]
+        if strict and missing:
+            raise RuntimeError("missing keys: %s" % missing[:5])
+        with torch.no_grad():
+            for k in self._keys:
+                if k in sd:
+                    self._p[k.replace(".", "/")].copy_(sd[k])
+        self._tag = None
+
+    def _sync(self, device):
+        e = self._engine
+        e._ensure(device)
+        tag = tuple(p._version for p in self._p.values())
+        if self._tag == tag:
+            return
+        L, h = e.L, e.handle
+        if self._head_id is None:
+            self._head_id = _lib.check(h, L.fac_head_begin(h), "fac_head_begin")
+        for k in self._keys:
+            t = self._p[k.replace(".", "/")].detach().to("cpu", torch.float32).contiguous()
+            shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+            _lib.check(h, L.fac_head_tensor(h, self._head_id, k.encode(), _ptr(t), shape, t.dim()), "fac_head_tensor(%s)" % k)
+        _lib.check(h, L.fac_head_finalize(h, self._head_id, self.indim, self.outdim, self.nheads, int(self.global_pred)),
+                   "fac_head_finalize")
+        self._tag = tag
+
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError("eval mode only")
+        self._sync(x.device)
+        e = self._engine
+        x = _f32c(x)
+        B, C, T = x.shape
+        assert C == self.indim
+        shape = (B, self.outdim) if self.global_pred else (B, T, self.outdim)
+        outs = [torch.empty(shape, device=x.device) for _ in range(self.nheads)]
+        arr = (ctypes.c_void_p * self.nheads)(*[o.data_ptr() for o in outs])
+        rc = e.L.fac_head_forward(e.handle, self._head_id, _ptr(x), B, T, arr, _stream(x.device))
+        _lib.check(e.handle, rc, "fac_head_forward")
+        return outs

@@ -120,6 +120,22 @@ int fac_rvq_forward(fac_handle* h, int rvq_id, const float* x, int B, int T, int
 int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int act,
                        const float* alpha, const float* beta, float* y, void* stream);
 
+/* Dataset-side mel: meldataset.py:37-47 preprocess (PseudoDataset.__getitem__ :64-71) -- torchaudio MelSpectrogram(n_mels=80,
+ * n_fft=2048, win_length=1200, hop_length=300) with its default sample_rate=16000 filterbank, centre=True, then
+ * (log(1e-5 + mel) + 4) / 4.  wave [B,T] (device, T > 1024) -> mel [B,80,T/300+1]. */
+int fac_dataset_mel(fac_handle* h, const float* wave, int B, int T, float* mel, void* stream);
+
+/* Predictor heads: modules/quantize.py:106-125 CNNLSTM(indim, outdim, head, global_pred) forward (3 ResidualUnits of
+ * alias-free SnakeBeta + weight-normed Conv1d k7 (dilation 1, 2, 3, zero padding) / k1, a final alias-free SnakeBeta,
+ * `nheads` nn.Linear layers; mean over time first when global_pred).  fac_head_begin returns a head id; feed the reference
+ * state_dict tensors (keys "model.0.block.0.act.alpha", "model.0.block.1.weight_g", ..., "heads.0.weight"; the registered
+ * filter buffers are ignored) with fac_head_tensor, then fac_head_finalize.  fac_head_forward: x [B,indim,T] (device) ->
+ * outs[i] [B,T,outdim] (or [B,outdim] when global_pred), i < nheads, caller-allocated device buffers. */
+int fac_head_begin(fac_handle* h);
+int fac_head_tensor(fac_handle* h, int head_id, const char* key, const float* data_host, const int64_t* shape, int ndim);
+int fac_head_finalize(fac_handle* h, int head_id, int indim, int outdim, int nheads, int global_pred);
+int fac_head_forward(fac_handle* h, int head_id, const float* x, int B, int T, float* const* outs, void* stream);
+
 /* Engine options.  "tensor_cores": 0 = fp32 FMA kernels everywhere; 1 = tcgen05 3xTF32
  * kernel for every eligible layer downstream of the VQ (decoder, timbre branch), fp32 FMA upstream
  * (encoder, prosody branch); 2 (default) = tcgen05 everywhere, with the register-promoted accumulation

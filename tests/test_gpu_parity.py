@@ -322,3 +322,48 @@ def test_voice_conversion_flow_vs_live_oracle(built_lib):
     import facodec_b200 as fb
     with pytest.raises(fb.FacError):
         rm.encoder(q[5][0], q[5][1].cpu(), q2[4])                    # input on another device: no silent foreign pointer
+
+
+@pytest.mark.parametrize("indim,outdim,heads,glob,T", [(1024, 1, 2, False, 320), (64, 1024, 1, False, 77), (256, 400, 1, True, 50)])
+def test_cnnlstm_predictor_heads_vs_oracle(indim, outdim, heads, glob, T, built_lib):
+    """modules/quantize.py:106-125 CNNLSTM forward (FApredictors f0 / phone / timbre head geometries, scaled): alias-free
+    SnakeBeta + conv stacks + Linear heads against the oracle (pinned bit-for-bit to the imported class in test_oracle.py).
+    Tolerance: decoder-class precision (bf16 hi/lo operands), 2e-3 of the output scale."""
+    import facodec_b200 as fb
+    from facodec_b200 import synth
+    from oracle import facodec_oracle as O
+    m = fb.CNNLSTM(indim, outdim, heads, global_pred=glob).eval()
+    sd = synth.synth_cnnlstm(11, indim, outdim, heads)
+    m.load_state_dict(sd)
+    assert set(sd) <= set(m.state_dict()) and any(k.endswith("upsample.filter") for k in m.state_dict())
+    g = torch.Generator().manual_seed(indim + T)
+    x = torch.randn(3, indim, T, generator=g)
+    with torch.no_grad():
+        ref = O.cnnlstm_forward(sd, x, heads, global_pred=glob)
+    out = m(x.cuda())
+    torch.cuda.synchronize()
+    assert len(out) == heads
+    for a, b in zip(out, ref):
+        assert tuple(a.shape) == tuple(b.shape)
+        err = float((a.cpu() - b).abs().max())
+        assert err <= 2e-3 * max(1.0, float(b.abs().max())), f"max err {err}"
+
+
+def test_dataset_mel_vs_oracle(built_lib):
+    """meldataset.py:37-47 (16 kHz-default filterbank, centre=True frames) through fac_dataset_mel against the oracle
+    restatement (pinned to the imported meldataset module in test_oracle.py).  Log-mel values are O(1): 2e-4 absolute."""
+    from facodec_b200 import meldataset as MD
+    from facodec_b200 import synth
+    from oracle import facodec_oracle as O
+    fb = synth.melscale_fbanks_htk(sample_rate=16000, f_max=8000.0)
+    win = synth.hann_window_periodic(1200)
+    for (B, T) in ((2, 7200), (1, 24001), (3, 1500)):
+        w = synth.synth_waves(B, T, seed=T)[:, 0]
+        ref = O.dataset_mel(w, win, fb)
+        got = MD.to_mel_batch(w.cuda()).cpu()
+        assert tuple(got.shape) == tuple(ref.shape) == (B, 80, T // 300 + 1)
+        assert float((got - ref).abs().max()) <= 2e-4
+    one = MD.preprocess(synth.synth_waves(1, 3000, seed=1)[0, 0].numpy())
+    assert tuple(one.shape) == (1, 80, 11)
+    wave, mel = MD.PseudoDataset(range=(1, 2))[0]
+    assert mel.shape[0] == 80 and mel.shape[1] == wave.shape[0] // 300 + 1
