@@ -103,6 +103,8 @@ struct fac_handle {
     int enc_f16 = 0;                // fac_set_option "encoder_f16x2": promoted layers use the fp16 hi + scaled-lo split
     int tc_occ2 = 256;              // fac_set_option "tc_occ2_maxn": conv_tc tiles with N <= this are planned for two CTAs per SM (0 = off)
     bool dec_bf16 = true;           // decoder-side layers use the bf16x3 split (fac_set_option "decoder_bf16")
+    // second stream for the waveform-only half of the quantizer (fac_set_option "overlap_front")
+    int overlap_front = 1; cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* aa_filter = nullptr;
     // dataset-side mel (meldataset.py:29-47: MelSpectrogram with its default sample_rate 16000): own constants, built lazily
     float* mel16_arena = nullptr; ConvW mel16_dft, mel16_dft_tc; size_t mel16_fb = 0;
@@ -1000,13 +1002,15 @@ struct QuantOut {
     float* outs_cl; float* zp_cl; float* zc_cl; float* zr_cl; int Tq;
 };
 
-// FAquantizer.forward_v2 on channels-last z; returns channels-last outputs in workspace
-QuantOut quantizer_forward(Ctx& c, const float* z_cl, const float* wave, int B, int T, int Tz, int n_c,
-                           const float* full_waves, int T_full, const int64_t* wave_lens, float* losses2,
-                           float* timbre, int64_t* codes_p, int64_t* codes_c, int64_t* codes_r, bool want_parts) {
+// FAquantizer.forward_v2, the part that depends on the waveform only (modules/quantize.py:378-404): timbre (mel ->
+// StyleEncoder -> timbre_linear) and the prosody features (mel[:, :20] -> melspec_linear -> WN -> melspec_linear2).  Nothing
+// here reads the encoder's latents, so fac_codec_forward runs it on a second stream beside the encoder.
+struct QuantFront { float* gb; float* f0; int Tm; };
+QuantFront quantizer_front(Ctx& c, const float* wave, int B, int T, const float* full_waves, int T_full, const int64_t* wave_lens,
+                           float* timbre) {
     const QuantW& q = c.h->qw;
     const int Tm = T / HOP;
-    const int Tq = Tm < Tz ? Tm : Tz;
+    const bool was_critical = c.vq_critical;
     c.vq_critical = true;      // quantizer-side layers are tiny: all of them use the promoted kernel
     // --- timbre ---
     float* mel = mel_forward(c, wave, B, T, Tm);
@@ -1049,6 +1053,24 @@ QuantOut quantizer_forward(Ctx& c, const float* z_cl, const float* wave, int B, 
         sconv(c, q.mel_lin2, skip, f0, B, Tm, 1, 1, ConvOpts(), "melspec_linear2");
         c.tap("f0_input", f0, (size_t)B * Tm * 1024);
     }
+    c.vq_critical = was_critical;
+    QuantFront fr;
+    fr.gb = gb; fr.f0 = f0; fr.Tm = Tm;
+    return fr;
+}
+
+// FAquantizer.forward_v2 on channels-last z; returns channels-last outputs in workspace
+QuantOut quantizer_forward(Ctx& c, const float* z_cl, const float* wave, int B, int T, int Tz, int n_c,
+                           const float* full_waves, int T_full, const int64_t* wave_lens, float* losses2,
+                           float* timbre, int64_t* codes_p, int64_t* codes_c, int64_t* codes_r, bool want_parts,
+                           const QuantFront* pre = nullptr) {
+    const QuantW& q = c.h->qw;
+    const int Tm = T / HOP;
+    const int Tq = Tm < Tz ? Tm : Tz;
+    c.vq_critical = true;
+    QuantFront fr = pre ? *pre : quantizer_front(c, wave, B, T, full_waves, T_full, wave_lens, timbre);
+    float* gb = fr.gb;
+    float* f0 = fr.f0;
     // --- fused per-frame VQ + AdaLN ---
     QuantOut out;
     out.Tq = Tq;
@@ -1082,6 +1104,34 @@ QuantOut quantizer_forward(Ctx& c, const float* z_cl, const float* wave, int B, 
     c.end();
     c.check(launch_vq_loss_reduce(sqerr, 6, B, Tq, losses2 ? losses2 : loss_ws, c.st), "vq_loss");
     return out;
+}
+
+// Runs the waveform-only half of the quantizer on the handle's side stream, forked after whatever the main stream has
+// queued so far (the input copy) and joined by the caller with join_front() before fa_quantize.
+bool fork_front(Ctx& c, QuantFront& fr, const float* wave, int B, int T, float* timbre) {
+    fac_handle* h = c.h;
+    if (!h->overlap_front || h->profiling) { return false; }
+    if (c.dry) { fr = quantizer_front(c, wave, B, T, nullptr, 0, nullptr, timbre); return true; }
+    if (!h->side) {
+        if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            h->overlap_front = 0;
+            return false;
+        }
+    }
+    cudaStream_t main_st = c.st;
+    c.check_nk(cudaEventRecord(h->ev_fork, main_st), "front.fork");
+    c.check_nk(cudaStreamWaitEvent(h->side, h->ev_fork, 0), "front.fork_wait");
+    c.st = h->side;
+    fr = quantizer_front(c, wave, B, T, nullptr, 0, nullptr, timbre);
+    c.check_nk(cudaEventRecord(h->ev_join, h->side), "front.join");
+    c.st = main_st;
+    return true;
+}
+void join_front(Ctx& c) {
+    if (!c.dry) c.check_nk(cudaStreamWaitEvent(c.st, c.h->ev_join, 0), "front.join_wait");
 }
 
 int ensure_ws(fac_handle* h, size_t bytes) {
@@ -1146,6 +1196,9 @@ int fac_destroy(fac_handle* h) {
     cudaSetDevice(h->device);
     if (h->warena) cudaFree(h->warena);
     if (h->ws) cudaFree(h->ws);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->aa_filter) cudaFree(h->aa_filter);
     if (h->mel16_arena) cudaFree(h->mel16_arena);
     for (float* p : h->rvq_arenas) cudaFree(p);
@@ -1257,9 +1310,13 @@ int fac_codec_forward(fac_handle* h, const float* x, int B, int T, int n_c, floa
     return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
         int Tz = fac_encode_frames(T);
         float* zcl = c.alloc<float>((size_t)B * Tz * LATENT);
+        float* timbre_buf = timbre ? timbre : c.alloc<float>((size_t)B * 1024);
+        QuantFront fr;
+        const bool forked = fork_front(c, fr, x, B, T, timbre_buf);
         encoder_forward(c, x, B, T, zcl, false);
-        QuantOut o = quantizer_forward(c, zcl, x, B, T, Tz, n_c, nullptr, 0, nullptr, nullptr, timbre, codes_p,
-                                       codes_c, codes_r, false);
+        if (forked) join_front(c);
+        QuantOut o = quantizer_forward(c, zcl, x, B, T, Tz, n_c, nullptr, 0, nullptr, nullptr, timbre_buf, codes_p,
+                                       codes_c, codes_r, false, forked ? &fr : nullptr);
         decoder_forward(c, h->dec, o.outs_cl, B, o.Tq, y);
     });
 }
@@ -1281,8 +1338,13 @@ int fac_codec_forward_host(fac_handle* h, const float* x_host, int B, int T, int
         int64_t* cr = c.alloc<int64_t>((size_t)B * 3 * Tq);
         float* zcl = c.alloc<float>((size_t)B * Tz * LATENT);
         if (!c.dry) c.check_nk(cudaMemcpyAsync(xd, x_host, sizeof(float) * (size_t)B * T, cudaMemcpyHostToDevice, c.st), "h2d");
+        float* timbre_buf = c.alloc<float>((size_t)B * 1024);
+        QuantFront fr;
+        const bool forked = fork_front(c, fr, xd, B, T, timbre_buf);
         encoder_forward(c, xd, B, T, zcl, false);
-        QuantOut o = quantizer_forward(c, zcl, xd, B, T, Tz, n_c, nullptr, 0, nullptr, nullptr, nullptr, cp, cc, cr, false);
+        if (forked) join_front(c);
+        QuantOut o = quantizer_forward(c, zcl, xd, B, T, Tz, n_c, nullptr, 0, nullptr, nullptr, timbre_buf, cp, cc, cr, false,
+                                       forked ? &fr : nullptr);
         decoder_forward(c, h->dec, o.outs_cl, B, o.Tq, yd);
         if (c.dry) return;
         c.check_nk(cudaMemcpyAsync(y_host, yd, sizeof(float) * (size_t)B * Tq * HOP, cudaMemcpyDeviceToHost, c.st), "d2h.y");
@@ -1677,6 +1739,7 @@ int fac_set_option(fac_handle* h, const char* name, int value) {
     if (std::string(name) == "encoder_f16x2") { h->enc_f16 = value != 0; return FAC_OK; }
     if (std::string(name) == "encoder_tt") { h->enc_tt = value != 0; return FAC_OK; }
     if (std::string(name) == "encoder_snake_mufu") { h->enc_mufu = value != 0; return FAC_OK; }
+    if (std::string(name) == "overlap_front") { h->overlap_front = value != 0; return FAC_OK; }
     if (std::string(name) == "lstm_v2") { h->lstm_v2 = value != 0; return FAC_OK; }
     if (std::string(name) == "decoder_lstm_fp16") { h->dec_lstm_fp16 = value != 0; return FAC_OK; }
     if (std::string(name) == "tt_probe") { g_tt_probe_on = value != 0; return FAC_OK; }
