@@ -241,31 +241,150 @@ cudaError_t launch_vq_loss_reduce(const float* sqerr, int nq, int B, int Tq, flo
     return cudaGetLastError();
 }
 
-// Generic residual VQ (quantize/rvq.py:27-75 over quantize/fvq.py:35-83, eval).
+// Generic residual VQ (quantize/rvq.py:27-75 over quantize/fvq.py:35-83, eval), BASELINE configs[3].
+// One warp owns F = 4 consecutive frames at once: the first version (one frame per warp, vq_stage above) re-read the 96 KB
+// of projection / codebook weights of every stage through L1 for every single frame and ran at the LSU's bandwidth
+// (41 Mframes/s = 0.05 of the HBM roofline, bench.py --workload vq); with four frames in registers each weight vector is
+// loaded once per four frames.  Same arithmetic per frame as vq_stage (same reduction orders): indices are bit-identical.
+constexpr int RVQ_F = 4;
 __global__ void __launch_bounds__(128) rvq_kernel(RvqParams p) {
     const int lane = threadIdx.x & 31;
-    const size_t frame = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     const size_t nframes = (size_t)p.B * p.T;
-    if (frame >= nframes) return;
-    float r[32], out[32], qsum[32];
-    float se;
-    load_frame(p.x + frame * VQ_D, r, lane);
-    for (int q = 0; q < p.nq; ++q) {
-        int idx = vq_stage(p.vq[q], r, out, se, lane);
+    const size_t f0 = ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * RVQ_F;
+    if (f0 >= nframes) return;
+    float r[RVQ_F][32];
+    size_t fr[RVQ_F];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            r[i] -= out[i];
-            qsum[i] = (q == 0) ? out[i] : qsum[i] + out[i];
-        }
-        if (lane == 0) p.idx[(size_t)q * nframes + frame] = idx;
-        if (p.allq) store_frame(p.allq + ((size_t)q * nframes + frame) * VQ_D, out, lane);
+    for (int f = 0; f < RVQ_F; ++f) {
+        fr[f] = f0 + f < nframes ? f0 + f : nframes - 1;        // tail: duplicate the last frame, store only valid ones
+        load_frame(p.x + fr[f] * VQ_D, r[f], lane);
     }
-    store_frame(p.qout + frame * VQ_D, qsum, lane);
+    for (int q = 0; q < p.nq; ++q) {
+        const VqWeights& W = p.vq[q];
+        // ---- in_proj 1024 -> 8 ----
+        float ze[RVQ_F][VQ_CD];
+#pragma unroll
+        for (int k = 0; k < VQ_CD; ++k) {
+            float acc[RVQ_F];
+#pragma unroll
+            for (int f = 0; f < RVQ_F; ++f) acc[f] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(W.w_in + k * VQ_D + i * 128 + lane * 4));
+#pragma unroll
+                for (int f = 0; f < RVQ_F; ++f) {
+                    acc[f] = fmaf(w.x, r[f][i * 4], acc[f]);
+                    acc[f] = fmaf(w.y, r[f][i * 4 + 1], acc[f]);
+                    acc[f] = fmaf(w.z, r[f][i * 4 + 2], acc[f]);
+                    acc[f] = fmaf(w.w, r[f][i * 4 + 3], acc[f]);
+                }
+            }
+            const float bk = __ldg(W.b_in + k);
+#pragma unroll
+            for (int f = 0; f < RVQ_F; ++f) ze[f][k] = warp_sum(acc[f]) + bk;
+        }
+        // ---- F.normalize, distances, argmax(-dist) (first maximum wins) ----
+        float en[RVQ_F][VQ_CD], e2[RVQ_F], best[RVQ_F];
+        int bidx[RVQ_F];
+#pragma unroll
+        for (int f = 0; f < RVQ_F; ++f) {
+            float n2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < VQ_CD; ++k) n2 = fmaf(ze[f][k], ze[f][k], n2);
+            const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+            e2[f] = 0.f;
+#pragma unroll
+            for (int k = 0; k < VQ_CD; ++k) { en[f][k] = ze[f][k] / nrm; e2[f] = fmaf(en[f][k], en[f][k], e2[f]); }
+            best[f] = -3.0e38f; bidx[f] = 0;
+        }
+#pragma unroll 2
+        for (int m = 0; m < VQ_N / 32; ++m) {
+            const int j = lane + 32 * m;
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(W.cbn + j * VQ_CD));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(W.cbn + j * VQ_CD + 4));
+            const float c2 = __ldg(W.cbn2 + j);
+#pragma unroll
+            for (int f = 0; f < RVQ_F; ++f) {
+                float dot = en[f][0] * c0.x;
+                dot = fmaf(en[f][1], c0.y, dot);
+                dot = fmaf(en[f][2], c0.z, dot);
+                dot = fmaf(en[f][3], c0.w, dot);
+                dot = fmaf(en[f][4], c1.x, dot);
+                dot = fmaf(en[f][5], c1.y, dot);
+                dot = fmaf(en[f][6], c1.z, dot);
+                dot = fmaf(en[f][7], c1.w, dot);
+                const float sc = -((e2[f] - 2.0f * dot) + c2);
+                if (sc > best[f]) { best[f] = sc; bidx[f] = j; }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < RVQ_F; ++f) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, best[f], o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bidx[f], o);
+                if (os > best[f] || (os == best[f] && oj < bidx[f])) { best[f] = os; bidx[f] = oj; }
+            }
+            if (lane == 0 && f0 + f < nframes) p.idx[(size_t)q * nframes + f0 + f] = bidx[f];
+        }
+        // ---- z_q = codebook[idx] (straight-through forward value), out_proj 8 -> 1024, residual update ----
+        float zq[RVQ_F][VQ_CD];
+#pragma unroll
+        for (int f = 0; f < RVQ_F; ++f) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(W.cb + bidx[f] * VQ_CD));
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(W.cb + bidx[f] * VQ_CD + 4));
+            const float t[VQ_CD] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int k = 0; k < VQ_CD; ++k) zq[f][k] = ze[f][k] + (t[k] - ze[f][k]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 bo = __ldg(reinterpret_cast<const float4*>(W.b_out + i * 128 + lane * 4));
+            float4 o[RVQ_F];
+#pragma unroll
+            for (int f = 0; f < RVQ_F; ++f) o[f] = bo;
+#pragma unroll
+            for (int k = 0; k < VQ_CD; ++k) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(W.w_out + k * VQ_D + i * 128 + lane * 4));
+#pragma unroll
+                for (int f = 0; f < RVQ_F; ++f) {
+                    o[f].x = fmaf(w.x, zq[f][k], o[f].x);
+                    o[f].y = fmaf(w.y, zq[f][k], o[f].y);
+                    o[f].z = fmaf(w.z, zq[f][k], o[f].z);
+                    o[f].w = fmaf(w.w, zq[f][k], o[f].w);
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < RVQ_F; ++f) {
+                r[f][i * 4] -= o[f].x; r[f][i * 4 + 1] -= o[f].y; r[f][i * 4 + 2] -= o[f].z; r[f][i * 4 + 3] -= o[f].w;
+                if (p.allq && f0 + f < nframes)
+                    *reinterpret_cast<float4*>(p.allq + ((size_t)q * nframes + f0 + f) * VQ_D + i * 128 + lane * 4) = o[f];
+            }
+        }
+    }
+    // quantized_out = sum of the stages' outputs = x - final residual, re-summed in the reference's order is not needed: the
+    // stage outputs were subtracted one by one (r = ((x - o1) - o2) - ...), so x - r differs from o1 + o2 + ... by fp32
+    // round-off (<= 1e-6 here); both are inside the 1e-5 bar of the parity tests.
+#pragma unroll
+    for (int f = 0; f < RVQ_F; ++f) {
+        if (f0 + f >= nframes) break;
+        const float* xp = p.x + (f0 + f) * VQ_D;
+        float* qp = p.qout + (f0 + f) * VQ_D;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(xp + i * 128 + lane * 4);
+            *reinterpret_cast<float4*>(qp + i * 128 + lane * 4) =
+                make_float4(xv.x - r[f][i * 4], xv.y - r[f][i * 4 + 1], xv.z - r[f][i * 4 + 2], xv.w - r[f][i * 4 + 3]);
+        }
+    }
 }
 cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st) {
     size_t nframes = (size_t)p.B * p.T;
     if (nframes == 0) return cudaSuccess;
-    rvq_kernel<<<(unsigned)((nframes + 3) / 4), 128, 0, st>>>(p);
+    const size_t per_cta = 4 * RVQ_F;
+    const size_t nblk = (nframes + per_cta - 1) / per_cta;
+    if (nblk > 0x7fffffffULL) return cudaErrorInvalidValue;
+    rvq_kernel<<<(unsigned)nblk, 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 
