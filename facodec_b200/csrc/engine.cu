@@ -1866,11 +1866,43 @@ long long fac_debug_lstm_pack(const float* whh_host, int H, int bf16, float* out
     }
     LstmW L;
     try { L = pack_lstm(&tmp, 0, "l"); } catch (const PackError&) { return FAC_ERR_UNSUPPORTED; }
-    const long long n = (long long)L.G * H * 4 * L.U;
     if (info3) { info3[0] = L.U; info3[1] = L.G; info3[2] = 4 * L.U; }
+    if (bf16 == 2 || bf16 == 3) {
+        // lstm2.cu layouts: 2 = one fp16 pass [G][H/16][8][4U] words, 3 = fp16 hi + scaled lo [G][H/16][hi|lo][8][4U]
+        const int p3 = bf16 == 3;
+        const long long n2 = (long long)lstm2_pack_words(H, L.U, p3);
+        if (!out || capacity_floats < n2) return n2;
+        lstm2_pack(whh_host, H, L.U, p3, reinterpret_cast<uint32_t*>(out));
+        return n2;
+    }
+    const long long n = (long long)L.G * H * 4 * L.U;
     if (bf16 && !L.has16) return FAC_ERR_UNSUPPORTED;
     if (!out || capacity_floats < n) return n;
     memcpy(out, tmp.pack.data() + (bf16 ? L.whh16[0] : L.whh[0]), sizeof(float) * (size_t)n);
+    return n;
+}
+
+// Host-only: the conv form of nn.ConvTranspose1d(k = 2s, stride s) weights [Cin][Cout][2s] (HOST, already weight-normed):
+// causal != 0 -> 2 taps (x[t-1], x[t]); causal == 0 -> 3 taps (x[t-1], x[t], x[t+1]) (encodec.py:248-270 trims).  out is
+// [taps][Cin][s*Cout] (phase-major output channels r*Cout + co); returns the number of floats.
+long long fac_debug_convtr_pack(const float* w_host, int Cin, int Cout, int stride, int causal, float* out, long long capacity_floats) {
+    if (!w_host || Cin <= 0 || Cout <= 0 || stride <= 0) return FAC_ERR_INVALID;
+    fac_handle tmp;
+    HostTensor t, b;
+    t.shape = {Cin, Cout, 2 * stride};
+    t.data.assign(w_host, w_host + (size_t)Cin * Cout * 2 * stride);
+    b.shape = {Cout};
+    b.data.assign(Cout, 0.f);
+    tmp.host[0]["c.weight"] = std::move(t);
+    tmp.host[0]["c.bias"] = std::move(b);
+    ConvW c;
+    try { c = causal ? pack_convtr(&tmp, 0, "c", stride) : pack_convtr_noncausal(&tmp, 0, "c", stride); }
+    catch (const PackError&) { return FAC_ERR_UNSUPPORTED; }
+    const long long n = (long long)c.K * Cin * c.Cout;
+    if (!out || capacity_floats < n) return n;
+    for (int k = 0; k < c.K; ++k)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int co = 0; co < c.Cout; ++co) out[((size_t)k * Cin + ci) * c.Cout + co] = tmp.pack[c.w + ((size_t)k * Cin + ci) * c.ldw + co];
     return n;
 }
 
@@ -1912,22 +1944,25 @@ int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, i
 // floats (32-bit words) of the blob, writes it when blob_out has room.
 long long fac_debug_tc_pack(const float* w_host, int Cin, int Cout, int K, int stride, int mode, float* blob_out,
                             long long capacity_floats) {
-    if (!w_host || Cin <= 0 || Cout <= 0 || K <= 0 || stride <= 0 || mode < 0 || mode > 3) return FAC_ERR_INVALID;
+    if (!w_host || Cin <= 0 || Cout <= 0 || K <= 0 || stride <= 0 || mode < 0 || mode > 4) return FAC_ERR_INVALID;
     TcConvParams tp;
     tp.Cin = Cin; tp.Cout = Cout; tp.dil = 1;
     tp.promoted = (mode == 1 || mode == 3) ? 1 : 0; tp.bf16 = mode == 2 ? 1 : 0; tp.f16x2 = mode == 3 ? 1 : 0;
     if (stride == 1) { tp.vf = 1; tp.Kr = K; }
     else if (K == 2 * stride) { tp.vf = stride; tp.Kr = 2; }
     else return FAC_ERR_UNSUPPORTED;
-    if (!tc_conv_plan(tp)) return FAC_ERR_UNSUPPORTED;
-    const long long n = (long long)tc_blob_floats(tp);
+    const bool use_tt = mode == 4;
+    if (use_tt) { tp.promoted = 0; tp.bf16 = 0; tp.f16x2 = 0; }
+    if (!(use_tt ? tt_conv_plan(tp) : tc_conv_plan(tp))) return FAC_ERR_UNSUPPORTED;
+    const long long n = (long long)(use_tt ? tt_blob_floats(tp) : tc_blob_floats(tp));
     if (!blob_out || capacity_floats < n) return n;
     const int ldw = (Cout + 3) / 4 * 4;
     std::vector<float> gen((size_t)K * Cin * ldw, 0.f);      // generic packed layout [K*Cin][ldw]
     for (int co = 0; co < Cout; ++co)
         for (int ci = 0; ci < Cin; ++ci)
             for (int k = 0; k < K; ++k) gen[((size_t)k * Cin + ci) * ldw + co] = w_host[((size_t)co * Cin + ci) * K + k];
-    tc_pack_blob(tp, gen.data(), ldw, blob_out);
+    if (use_tt) tt_pack_blob(tp, gen.data(), ldw, blob_out);
+    else tc_pack_blob(tp, gen.data(), ldw, blob_out);
     return n;
 }
 

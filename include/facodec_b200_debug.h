@@ -48,6 +48,8 @@ int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8);
 /* Host-only: the recurrent-weight packing of lstm_rec_kernel for one nn.LSTM weight_hh [4H][H] (HOST, gate order
  * i,f,g,o): bf16 = 0 -> fp32 [G][H][4U] (row r = gate*U + u of the CTA owning hidden units g*U..g*U+U-1);
  * bf16 = 1 -> [G][H/16][hi|lo][8 k-pairs][4U] words of two bf16 (even k in the low half), lo = rn_bf16(w - hi).
+ * bf16 = 2 / 3 -> the resident-W kernel's layouts (lstm2.cu): one fp16 plane [G][H/16][8][4U] / fp16 hi + 2^11-scaled lo planes
+ * [G][H/16][hi|lo][8][4U], column of row r of k pair k2 = r ^ swizzle(k2) (conflict-free fragment loads).
  * Returns the number of 32-bit words (G*H*4U) also when out is NULL/too small; info3 = {U, G, 4U}. */
 long long fac_debug_lstm_pack(const float* whh_host, int H, int bf16, float* out, long long capacity_floats, int* info3);
 /* Host-only: the padding index map every conv kernel applies instead of materialising a padded copy
@@ -55,7 +57,8 @@ long long fac_debug_lstm_pack(const float* whh_host, int H, int bf16, float* out
  * i - pad_left, or -1 where the padded value is zero; n must be pad_left + L + pad_right. */
 int fac_debug_pad_map(int L, int pad_left, int pad_right, int reflect, int* out, int n);
 /* Host-only (no GPU, no handle): the tile plan of the tcgen05 conv kernels for one layer geometry.  mode: 0 conv_tc TF32,
- * 1 conv_tcp (promoted) TF32, 2 conv_tc bf16, 3 conv_tcp fp16 hi + scaled lo, 4 fused ResidualUnit bf16, 5 fused TF32.
+ * 1 conv_tcp (promoted) TF32, 2 conv_tc bf16, 3 conv_tcp fp16 hi + scaled lo, 4 fused ResidualUnit bf16, 5 fused TF32,
+ * 6 conv_tt (transposed: out8[0] = 128 output channels per tile, out8[1] = time steps per tile).
  * Tout may be 0 (unknown).  out8 = {N, MT, K chunks, weight-ring stages, TMEM columns, dynamic shared-memory bytes,
  * padded rows of the operand buffer, chunks per promotion}.  FAC_ERR_UNSUPPORTED when the layer is not eligible. */
 int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, int mode, int occ2_maxn, int* out8);
@@ -68,6 +71,10 @@ long long fac_debug_tc_pack(const float* w_host, int Cin, int Cout, int K, int s
 /* clock64() totals of CTA 0 of the most recent lstm_rec_kernel launch, summed over all steps:
  * [0] grid-barrier wait, [1] W_hh/h streaming + MMAs, [2] cross-warp reduce + gate math, [3] publish. */
 int fac_debug_lstm_phase_clocks(fac_handle* h, long long* out4);
+/* Host-only: see engine.cu -- the conv form of a ConvTranspose1d(k = 2s, stride s) weight [Cin][Cout][2s]: causal -> 2 taps,
+ * non-causal -> 3 taps, out [taps][Cin][s*Cout] (phase-major channels); returns the float count. */
+long long fac_debug_convtr_pack(const float* w_host, int Cin, int Cout, int stride, int causal, float* out,
+                                long long capacity_floats);
 int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, int B, int T, int H, float* y,
                     void* stream);
 /* Registers (dst != NULL) or clears a named tap: the next forward copies that channels-last

@@ -309,3 +309,116 @@ int main(void) {
     env["LD_LIBRARY_PATH"] = "/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
     out = subprocess.check_output([str(exe)], env=env, text=True).split()
     assert out[:3] == ["192", "1", "512"]        # fused C = 192 unit: N = 192, MT = 1, 512 TMEM columns
+
+
+@pytest.mark.parametrize("geom", [(64, 64, 7, 1), (128, 256, 10, 5), (96, 200, 3, 1), (512, 2176, 1, 1)])
+def test_transposed_kernel_weight_blob(geom, built_lib):
+    """Host logic (no GPU): conv_tt_kernel's A-operand blob [co tile of 128][chunk][tap][hi|lo'][k8][128 rows][8 fp16]
+    decodes back to W (fp16 hi + lo'/2^11 to 2^-20), rows beyond Cout are zero, and the plan puts time on MMA N."""
+    import ctypes
+    import numpy as np
+    from facodec_b200 import _lib
+    L = _lib.load()
+    Cin, Cout, K, stride = geom
+    rng = np.random.RandomState(Cin + Cout)
+    w = (rng.randn(Cout, Cin, K) / np.sqrt(Cin * K)).astype(np.float32)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    n = L.fac_debug_tc_pack(P(w), Cin, Cout, K, stride, 4, None, 0)
+    assert n > 0
+    blob = np.zeros(n, np.float32)
+    assert L.fac_debug_tc_pack(P(w), Cin, Cout, K, stride, 4, P(blob), n) == n
+    out = (ctypes.c_int * 8)()
+    assert L.fac_debug_tc_plan(Cin, Cout, K, 1, stride, 96000, 6, 0, out) == 0
+    assert out[0] == 128 and out[1] == 256 and out[4] == 512 and out[5] <= 225 * 1024 and out[7] * (K if stride == 1 else 2) <= 48
+    assert L.fac_debug_tc_plan(Cin, Cout, K, 1, stride, 320, 6, 0, out) == 0 and out[1] == 160      # T' = 320: two full tiles
+    nchunk = out[2]
+    Kr, vf = (K, 1) if stride == 1 else (2, stride)
+    Wg = np.zeros((Kr, vf * Cin, Cout), np.float32)
+    for k in range(K):
+        Wg[k // vf, (k % vf) * Cin:(k % vf + 1) * Cin, :] = w[:, :, k].T
+    nt = (Cout + 127) // 128
+    h16 = blob.view(np.float16).reshape(nt, nchunk, Kr, 2, 2, 128, 8)          # [..][hl][k8][row][e]
+    dec = lambda a: a.transpose(0, 1, 2, 4, 3, 5).reshape(nt, nchunk, Kr, 128, 16).astype(np.float64)
+    rec = dec(h16[:, :, :, 0]) + dec(h16[:, :, :, 1]) / 2048.0                    # [nt][chunk][tap][row][kk]
+    ref = np.zeros((nt, nchunk, Kr, 128, 16))
+    for t in range(nt):
+        rows = min(128, Cout - t * 128)
+        ref[t, :, :, :rows] = Wg[:, :, t * 128:t * 128 + rows].reshape(Kr, nchunk, 16, rows).transpose(1, 0, 3, 2)
+    assert np.abs(rec - ref).max() <= 2.0 ** -20 * np.abs(ref).max()
+    if Cout % 128:
+        assert not rec[-1, :, :, Cout % 128:].any()
+
+
+@pytest.mark.parametrize("H,mode", [(1024, 3), (1024, 2), (1536, 2)])
+def test_lstm2_resident_weight_words(H, mode, built_lib):
+    """Host logic (no GPU): lstm2.cu's resident W_hh layout -- fp16 pairs of consecutive k per 32-bit word, XOR-swizzled
+    columns -- decodes back to W_hh (one pass: fp16 rounding 2^-11; three-pass: hi + lo'/2^11 to 2^-20), and every
+    mma.sync fragment load (4 k pairs x 8 rows per instruction) touches 32 distinct shared-memory banks."""
+    import ctypes
+    import numpy as np
+    from facodec_b200 import _lib
+    L = _lib.load()
+    rng = np.random.RandomState(H + mode)
+    w = (rng.uniform(-1, 1, size=(4 * H, H)) / np.sqrt(H)).astype(np.float32)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    info = (ctypes.c_int * 3)()
+    n = L.fac_debug_lstm_pack(P(w), H, mode, None, 0, info)
+    U, G, R = info[0], info[1], info[2]
+    PL = 2 if mode == 3 else 1
+    assert n == G * (H // 16) * PL * 8 * R
+    words = np.zeros(n, np.float32)
+    assert L.fac_debug_lstm_pack(P(w), H, mode, P(words), n, info) == n
+    wv = words.view(np.uint32).reshape(G, H // 16, PL, 8, R)
+    swz = (lambda k2: (k2 & 3) << 3) if R == 32 else (lambda k2: ((k2 >> 1) & 1) << 3)
+    ref = w.reshape(4, G, U, H).transpose(1, 0, 2, 3).reshape(G, R, H).astype(np.float64)      # [g][r = gate*U + u][k]
+    rec = np.zeros((G, R, H))
+    for k2 in range(8):
+        cols = np.arange(R) ^ swz(k2)
+        for pl in range(PL):
+            wd = wv[:, :, pl, k2, :][:, :, cols]                                               # [g][sub][r]
+            lo16 = (wd & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+            hi16 = (wd >> 16).astype(np.uint16).view(np.float16).astype(np.float64)
+            sc = 1.0 if pl == 0 else 1.0 / 2048.0
+            rec[:, :, 2 * k2::16] += sc * lo16.transpose(0, 2, 1)
+            rec[:, :, 2 * k2 + 1::16] += sc * hi16.transpose(0, 2, 1)
+    tol = 2.0 ** -20 if mode == 3 else 2.0 ** -11
+    assert np.abs(rec - ref).max() <= tol * np.abs(ref).max()
+    # bank check of one A-fragment load instruction: lanes (fg = row 0..7, ft = k pair 0..3) -> word address ft*R + (row ^ swz)
+    for i in range(R // 16):
+        for half in (0, 8):
+            banks = {((ft * R) + ((i * 16 + fg + half) ^ swz(ft))) % 32 for fg in range(8) for ft in range(4)}
+            assert len(banks) == 32
+
+
+@pytest.mark.parametrize("stride", [2, 5, 6])
+def test_transposed_conv_as_conv_causal_and_noncausal(stride, built_lib):
+    """Host logic (no GPU): ConvTranspose1d(k = 2s, stride s) + the reference's trims (encodec.py:248-270) == a 2-tap
+    (causal) / 3-tap (non-causal) zero-padded conv with s*Cout phase-major channels, checked against the oracle's
+    sconvtr1d (pinned to the imported reference)."""
+    import ctypes
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from facodec_b200 import _lib
+    from oracle import facodec_oracle as O
+    L = _lib.load()
+    Cin, Cout, T = 6, 4, 9
+    g = torch.Generator().manual_seed(stride)
+    w = torch.randn(Cin, Cout, 2 * stride, generator=g)
+    x = torch.randn(2, Cin, T, generator=g)
+    sd = {"c.weight": w, "c.bias": torch.zeros(Cout)}
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    wn = np.ascontiguousarray(w.numpy())
+    for causal in (1, 0):
+        n = L.fac_debug_convtr_pack(P(wn), Cin, Cout, stride, causal, None, 0)
+        taps = 2 if causal else 3
+        assert n == taps * Cin * stride * Cout
+        pk = np.zeros(n, np.float32)
+        assert L.fac_debug_convtr_pack(P(wn), Cin, Cout, stride, causal, P(pk), n) == n
+        wk = torch.from_numpy(pk.reshape(taps, Cin, stride * Cout)).permute(2, 1, 0).contiguous()   # conv1d weight [s*Cout][Cin][taps]
+        xp = F.pad(x, (1, 0 if causal else 1))
+        y = F.conv1d(xp, wk)                                                    # [B][s*Cout][T], channel r*Cout + co
+        y = y.view(2, stride, Cout, T).permute(0, 2, 3, 1).reshape(2, Cout, T * stride)
+        ref = O.sconvtr1d(x, sd, "c", stride, causal=bool(causal))
+        assert ref.shape == y.shape
+        assert float((y - ref).abs().max()) <= 1e-5
