@@ -12,7 +12,7 @@ Prints ONE JSON line on rank 0 (contract in the task statement):
   roofline   = dominant kernel family (the two tcgen05 conv kernels conv_tc_kernel + conv_tcp_kernel, ~80 % of a step):
                algorithmic FLOPs / device time, from CUDA events recorded around every launch in a separate
                instrumented pass (fac_profile_*); traffic = DRAM bytes per launch of that family from the committed
-               ncu launch list (profiles/roofline_r01.json)
+               ncu launch list (profiles/roofline_r02.json)
   cpu_baseline = the oracle port (oracle/facodec_oracle.py = the reference's own ATen call sequence)
                timed on this box's host cores on a bounded sample
 --impl reference times that CPU path alone (the reference is 100% Python/PyTorch; /root/reference is
@@ -365,7 +365,7 @@ def main():
     conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
     traffic, traffic_src = None, None
     try:
-        rj = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))
+        rj = json.load(open(os.path.join(ROOT, "profiles", "roofline_r02.json")))
         traffic = rj["conv_family"]["dram_bytes_per_launch"]
         traffic_src = rj["conv_family"]["source"]
     except Exception:
