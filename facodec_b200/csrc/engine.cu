@@ -1201,7 +1201,7 @@ int fac_destroy(fac_handle* h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->aa_filter) cudaFree(h->aa_filter);
     if (h->mel16_arena) cudaFree(h->mel16_arena);
-    for (float* p : h->rvq_arenas) cudaFree(p);
+    for (float* p : h->rvq_arenas) if (p) cudaFree(p);
     for (auto* hs : h->heads) { if (hs->arena) cudaFree(hs->arena); delete hs; }
     delete h;
     return FAC_OK;
@@ -1586,11 +1586,25 @@ int fac_rvq_create(fac_handle* h, int nq, const float* const* in_w, const float*
     return (int)h->rvqs.size() - 1;
 }
 
+// Frees the device arena of one fac_rvq_create set (ids of other sets stay valid; the id is not reused).
+int fac_rvq_destroy(fac_handle* h, int rvq_id) {
+    if (!h || rvq_id < 0 || rvq_id >= (int)h->rvqs.size()) return FAC_ERR_INVALID;
+    if (h->rvq_arenas[rvq_id]) {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        cudaFree(h->rvq_arenas[rvq_id]);
+        h->rvq_arenas[rvq_id] = nullptr;
+        h->rvqs[rvq_id].nq = 0;
+    }
+    return FAC_OK;
+}
+
 int fac_rvq_forward(fac_handle* h, int rvq_id, const float* x, int B, int T, int x_channels_last, float* quantized_out,
                     int64_t* indices, float* all_quantized, void* stream) {
     if (!h || rvq_id < 0 || rvq_id >= (int)h->rvqs.size() || !x || !quantized_out || !indices || B <= 0 || T <= 0) return FAC_ERR_INVALID;
     const RvqSet& s = h->rvqs[rvq_id];
     const float* base = h->rvq_arenas[rvq_id];
+    if (!base || s.nq < 1) { h->err = "fac_rvq_forward: set was destroyed"; return FAC_ERR_STATE; }
     return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
         size_t n = (size_t)B * T * 1024;
         float* xcl = x_channels_last ? nullptr : c.alloc<float>(n);

@@ -476,6 +476,8 @@ class ResidualVQ(nn.Module):
         out_w = arr([self._folded(i, "out_proj") for i in range(n)])
         out_b = arr([self._p[f"layers/{i}/out_proj/bias"].detach().cpu().contiguous() for i in range(n)])
         cb = arr([self._p[f"layers/{i}/_codebook/weight"].detach().cpu().contiguous() for i in range(n)])
+        if self._rvq_id is not None:
+            e.L.fac_rvq_destroy(e.handle, self._rvq_id)      # weights changed: release the previous device arena
         rid = e.L.fac_rvq_create(e.handle, n, in_w, in_b, out_w, out_b, cb)
         _lib.check(e.handle, rid, "fac_rvq_create")
         self._rvq_id, self._tag = rid, tag

@@ -111,6 +111,7 @@ int fac_voice_convert(fac_handle* h, const int64_t* codes_p, const int64_t* code
  * (may be NULL).  x_channels_last != 0 means x / outputs are [B,T,1024] (no transposes). */
 int fac_rvq_create(fac_handle* h, int nq, const float* const* in_w, const float* const* in_b,
                    const float* const* out_w, const float* const* out_b, const float* const* codebook);
+int fac_rvq_destroy(fac_handle* h, int rvq_id);   /* frees that set's device arena (e.g. before re-creating it with new weights) */
 int fac_rvq_forward(fac_handle* h, int rvq_id, const float* x, int B, int T, int x_channels_last,
                     float* quantized_out, int64_t* indices, float* all_quantized, void* stream);
 
