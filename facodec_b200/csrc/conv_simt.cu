@@ -357,12 +357,10 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t st) {
         (p.out_act == ACT_NONE || p.out_act == ACT_TANH)) {
         size_t smem = sizeof(float) * ((size_t)(C1_TILE + (p.K - 1) * p.dil) * c1_pitch(p.Cin) + (size_t)p.K * p.Cin + C1_TILE);
         if (smem <= 200 * 1024) {
-            static bool configured = false;
-            if (!configured) {
-                cudaError_t e = cudaFuncSetAttribute(conv_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-                if (e != cudaSuccess) return e;
-                configured = true;
-            }
+            // function attributes are per device (a process may hold handles on several GPUs): set it on every launch of this
+            // once-per-forward kernel instead of caching a process-wide flag
+            cudaError_t e = cudaFuncSetAttribute(conv_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
             dim3 grid((p.Tout + C1_TILE - 1) / C1_TILE, p.B);
             conv_cout1_kernel<<<grid, 256, smem, st>>>(p);
             return cudaGetLastError();

@@ -367,3 +367,32 @@ def test_dataset_mel_vs_oracle(built_lib):
     assert tuple(one.shape) == (1, 80, 11)
     wave, mel = MD.PseudoDataset(range=(1, 2))[0]
     assert mel.shape[0] == 80 and mel.shape[1] == wave.shape[0] // 300 + 1
+
+
+def test_two_handles_on_two_devices_in_one_process(built_lib):
+    """Launch configuration (> 48 KB dynamic shared-memory opt-in, SM count) is per device: a second engine on cuda:1 in the
+    same process must work and give the same bits as cuda:0 (round-1 ADVICE: process-wide statics broke this)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import facodec_b200 as fb
+    from facodec_b200 import synth
+    sds = state_dicts(0)
+    x = synth.synth_waves(2, 9000, seed=8)
+    outs = []
+    for d in (0, 1):
+        m = fb.build_model()
+        for k in ("encoder", "quantizer", "decoder"):
+            m[k].load_state_dict(sds[k])
+            m[k].eval()
+        dev = torch.device("cuda", d)
+        xd = x.to(dev)
+        z = m.encoder(xd)
+        q = m.quantizer(z, xd, n_c=2, return_codes=True)
+        y = m.decoder(q[0])
+        torch.cuda.synchronize(dev)
+        outs.append((y.cpu(), [c.cpu() for c in q[5]]))
+        with pytest.raises(fb.FacError):
+            m.encoder(x.to(torch.device("cuda", 1 - d)))          # engine is bound to its device
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
