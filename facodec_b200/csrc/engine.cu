@@ -86,6 +86,8 @@ struct fac_handle {
     EncW enc; DecW dec; QuantW qw;
     RedW red; DecW dec2;            // voice-conversion model: Redecoder + its non-causal, LSTM-free decoder
     std::vector<RvqSet> rvqs; std::vector<float*> rvq_arenas;
+    struct Stream;                  // chunked (streaming) encoder / decoder state (fac_stream_*)
+    std::vector<Stream*> streams;
     struct HeadSet;                 // modules/quantize.py:106-125 CNNLSTM instances (fac_head_*)
     std::vector<HeadSet*> heads;
     char* ws = nullptr; size_t ws_bytes = 0;
@@ -116,6 +118,23 @@ struct fac_handle {
     std::map<std::string, ProfAgg> prof_agg;
     // debug taps: named intermediates copied out during a forward (fac_debug_tap)
     std::map<std::string, std::pair<float*, size_t>> taps;
+};
+
+// Streaming state of one batch of utterances: the encoder and the decoder are causal (README.md:105-107), so a chunk's
+// outputs depend on the past only through (a) a bounded window of earlier samples / frames of every FIR-like conv stack
+// and (b) the LSTM states.  Histories are kept on the device; chunks are computed on [history | chunk] windows with the
+// ordinary kernels and the history part of the output is dropped.
+struct fac_handle::Stream {
+    int B = 0;
+    bool alive = false;
+    long long enc_samples = 0, dec_frames = 0;
+    float* x_hist = nullptr; int x_hist_len = 0;            // [B][kEncCtx] last samples
+    float* ey_hist = nullptr; int ey_hist_len = 0;          // [B][2][1024] last encoder-LSTM output frames (conv_out, k = 3)
+    float* z_hist = nullptr; int z_hist_len = 0;            // [B][6][1024] last latent frames (decoder conv0, k = 7)
+    float* dy_hist = nullptr; int dy_hist_len = 0;          // [B][kDecCtx][1536] last decoder-LSTM output frames
+    uint32_t* enc_h[2] = {nullptr, nullptr}; float* enc_c[2] = {nullptr, nullptr};
+    uint32_t* dec_h[2] = {nullptr, nullptr}; float* dec_c[2] = {nullptr, nullptr};
+    void* all[12] = {nullptr};
 };
 
 // One CNNLSTM predictor head (modules/quantize.py:106-125): 3 ResidualUnits (alias-free SnakeBeta, k7 conv dilation
@@ -755,8 +774,12 @@ void residual_unit(Ctx& c, const ResW& r, const float* x, float* tmp, float* y, 
     sconv(c, r.c1, tmp, y, B, T, 1, 1, o2, "res.conv1", causal);
 }
 
-// SLSTM (encodec.py:272-288) on channels-last x [B][T][H]; y = lstm2(lstm1(x)) + x
-void slstm(Ctx& c, const LstmW& L, const float* x, float* y, int B, int T) {
+// Carried state of one 2-layer SLSTM (streaming): h in the kernel's published fp16 layout, c per CTA.
+struct LstmState { uint32_t* h[2] = {nullptr, nullptr}; float* c[2] = {nullptr, nullptr}; };
+
+// SLSTM (encodec.py:272-288) on channels-last x [B][T][H]; y = lstm2(lstm1(x)) + x.  st (streaming, B <= 32, resident-W
+// kernel only): initial state read from / final state written to st.
+void slstm(Ctx& c, const LstmW& L, const float* x, float* y, int B, int T, LstmState* st = nullptr) {
     const int H = L.H;
     float* xg = c.alloc<float>((size_t)B * T * 4 * H);
     float* h1 = c.alloc<float>((size_t)B * T * H);
@@ -782,9 +805,11 @@ void slstm(Ctx& c, const LstmW& L, const float* x, float* y, int B, int T) {
             p.hT = hT; p.bar = bar;
             p.B = nb; p.T = T; p.H = H; p.U = L.U; p.G = L.G;
             c.begin("lstm_rec", 2.0 * nb * T * 4.0 * H * H, 4.0 * ((double)nb * T * 5 * H + 4.0 * H * H));
+            if (st && (!v2 || B > 32)) { c.check(cudaErrorNotSupported, "lstm.stream (needs the resident-W kernel and B <= 32)"); c.end(); continue; }
             if (v2) {
                 p.whh_p2 = reinterpret_cast<const uint32_t*>(c.W(L.whh2[l][pass3]));
                 p.h16 = h16; p.pass3 = pass3;
+                if (st) { p.state_h = st->h[l]; p.state_c = st->c[l]; }
                 c.check(launch_lstm2_layer(p, c.st), "lstm.rec2");
             } else {
                 c.check(launch_lstm_layer(p, c.st), "lstm.rec");
@@ -800,9 +825,9 @@ size_t enc_stage_floats(int B, int T) {
 }
 
 // Encoder.forward (dac.py:69-104): x [B][T][1] -> z channels-last [B][Tz][1024] (or NCT when z_nct)
-int encoder_forward(Ctx& c, const float* x, int B, int T, float* z_out, bool z_nct) {
+// Encoder front: conv0 + the four EncoderBlocks (a causal FIR stack) -> features [B][ceil(T/300)][1024] in workspace.
+float* encoder_front(Ctx& c, const float* x, int B, int T, int* frames) {
     const EncW& e = c.h->enc;
-    c.vq_critical = true;
     size_t stage = enc_stage_floats(B, T);
     float* buf[3] = {c.alloc<float>(stage), c.alloc<float>(stage), c.alloc<float>(stage)};
     int cur = 0;
@@ -822,19 +847,28 @@ int encoder_forward(Ctx& c, const float* x, int B, int T, float* z_out, bool z_n
         cur = nxt;
         c.tap(blk_names[i], buf[cur], (size_t)B * t * e.blk[i].down.Cout);
     }
-    int nxt = (cur + 1) % 3;
-    slstm(c, e.lstm, buf[cur], buf[nxt], B, t);
-    cur = nxt;
-    c.tap("enc_lstm", buf[cur], (size_t)B * t * 1024);
+    *frames = t;
+    return buf[cur];
+}
+
+// Encoder.forward (dac.py:69-104): x [B][T][1] -> z channels-last [B][Tz][1024] (or NCT when z_nct)
+int encoder_forward(Ctx& c, const float* x, int B, int T, float* z_out, bool z_nct) {
+    const EncW& e = c.h->enc;
+    c.vq_critical = true;
+    int t = 0;
+    float* feats = encoder_front(c, x, B, T, &t);
+    float* ylstm = c.alloc<float>((size_t)B * t * LATENT);
+    slstm(c, e.lstm, feats, ylstm, B, t);
+    c.tap("enc_lstm", ylstm, (size_t)B * t * 1024);
     ConvOpts o;
     o.in_snake = &e.snake;
     if (z_nct) {
         // same kernel as the channels-last path (bit-identical z), then a [B][T][C] -> [B][C][T] transpose
-        int nx2 = (cur + 1) % 3;
-        sconv(c, e.conv_out, buf[cur], buf[nx2], B, t, 1, 1, o, "enc.conv_out");
-        if (!c.dry) c.check(launch_transpose(buf[nx2], z_out, B, t, LATENT, c.st), "enc.z_T");
+        float* zcl = c.alloc<float>((size_t)B * t * LATENT);
+        sconv(c, e.conv_out, ylstm, zcl, B, t, 1, 1, o, "enc.conv_out");
+        if (!c.dry) c.check(launch_transpose(zcl, z_out, B, t, LATENT, c.st), "enc.z_T");
     } else {
-        sconv(c, e.conv_out, buf[cur], z_out, B, t, 1, 1, o, "enc.conv_out");
+        sconv(c, e.conv_out, ylstm, z_out, B, t, 1, 1, o, "enc.conv_out");
     }
     c.vq_critical = false;
     return t;
@@ -842,10 +876,43 @@ int encoder_forward(Ctx& c, const float* x, int B, int T, float* z_out, bool z_n
 
 // Decoder.forward (dac.py:131-165): z channels-last [B][Tf][1024] -> y [B][300 Tf][1].  d = the codec's decoder (causal,
 // SLSTM) or the redecoder's (non-causal, no SLSTM).
-void decoder_forward(Ctx& c, const DecW& d, const float* z, int B, int Tf, float* y) {
+// The upsampling stack after the (optional) SLSTM: 4 DecoderBlocks, Snake, final conv, tanh.  in [B][Tf][1536] -> y [B][300 Tf].
+// buf[0..2]: three stage buffers of decoder_stage_floats(B, Tf) each; `in` may be one of them (index in_idx) or external (-1).
+size_t decoder_stage_floats(int B, int Tf) {
     size_t stage = (size_t)B * (size_t)Tf * 28800 + 1024;   // largest: [B][Tf*150][192] == [B][Tf*300][96]
     size_t first = (size_t)B * Tf * 1536;
-    if (first > stage) stage = first;
+    return first > stage ? first : stage;
+}
+void decoder_stack(Ctx& c, const DecW& d, const float* in, int in_idx, float* const* buf, int B, int Tf, float* y) {
+    int t = Tf;
+    const float* cur_p = in;
+    int cur = in_idx;
+    static const char* dblk_names[4] = {"dec_block1", "dec_block2", "dec_block3", "dec_block4"};
+    for (int i = 0; i < 4; ++i) {
+        // Snake -> SConvTranspose1d(k=2s, stride s) as a zero-padded conv with s*Cout phase-major channels:
+        // causal = 2 taps (x[t-1], x[t]), non-causal = 3 taps (x[t-1], x[t], x[t+1])
+        ConvOpts o;
+        o.in_snake = &d.blk[i].snake;
+        o.pad_left = 1; o.pad_right = d.causal ? 0 : 1; o.reflect = 0;
+        int nxt = cur < 0 ? 0 : (cur + 1) % 3;
+        run_conv(c, d.blk[i].up, cur_p, buf[nxt], B, t, t, o, "dec.up");
+        cur = nxt; cur_p = buf[cur];
+        t *= d.blk[i].stride;
+        for (int j = 0; j < 3; ++j) {
+            int tmp = (cur + 1) % 3, nx2 = (cur + 2) % 3;
+            residual_unit(c, d.blk[i].res[j], buf[cur], buf[tmp], buf[nx2], B, t, d.causal);
+            cur = nx2; cur_p = buf[cur];
+        }
+        c.tap(dblk_names[i], buf[cur], (size_t)B * t * d.blk[i].cout);
+    }
+    ConvOpts o;
+    o.in_snake = &d.snake;
+    o.act = ACT_TANH;
+    sconv(c, d.conv_out, buf[cur], y, B, t, 1, 1, o, "dec.conv_out", d.causal);
+}
+
+void decoder_forward(Ctx& c, const DecW& d, const float* z, int B, int Tf, float* y) {
+    const size_t stage = decoder_stage_floats(B, Tf);
     float* buf[3] = {c.alloc<float>(stage), c.alloc<float>(stage), c.alloc<float>(stage)};
     int cur = 0;
     int t = sconv(c, d.conv0, z, buf[0], B, Tf, 1, 1, ConvOpts(), "dec.conv0", d.causal);
@@ -855,28 +922,7 @@ void decoder_forward(Ctx& c, const DecW& d, const float* z, int B, int Tf, float
         cur = 1;
         c.tap("dec_lstm", buf[1], (size_t)B * t * 1536);
     }
-    static const char* dblk_names[4] = {"dec_block1", "dec_block2", "dec_block3", "dec_block4"};
-    for (int i = 0; i < 4; ++i) {
-        // Snake -> SConvTranspose1d(k=2s, stride s) as a zero-padded conv with s*Cout phase-major channels:
-        // causal = 2 taps (x[t-1], x[t]), non-causal = 3 taps (x[t-1], x[t], x[t+1])
-        ConvOpts o;
-        o.in_snake = &d.blk[i].snake;
-        o.pad_left = 1; o.pad_right = d.causal ? 0 : 1; o.reflect = 0;
-        int nxt = (cur + 1) % 3;
-        run_conv(c, d.blk[i].up, buf[cur], buf[nxt], B, t, t, o, "dec.up");
-        cur = nxt;
-        t *= d.blk[i].stride;
-        for (int j = 0; j < 3; ++j) {
-            int tmp = (cur + 1) % 3, nx2 = (cur + 2) % 3;
-            residual_unit(c, d.blk[i].res[j], buf[cur], buf[tmp], buf[nx2], B, t, d.causal);
-            cur = nx2;
-        }
-        c.tap(dblk_names[i], buf[cur], (size_t)B * t * d.blk[i].cout);
-    }
-    ConvOpts o;
-    o.in_snake = &d.snake;
-    o.act = ACT_TANH;
-    sconv(c, d.conv_out, buf[cur], y, B, t, 1, 1, o, "dec.conv_out", d.causal);
+    decoder_stack(c, d, buf[cur], cur, buf, B, t, y);
 }
 
 __global__ void embed_sum_kernel(const int64_t* __restrict__ codes_p, const int64_t* __restrict__ codes_c, int cc_stride,
@@ -1203,6 +1249,7 @@ int fac_destroy(fac_handle* h) {
     if (h->mel16_arena) cudaFree(h->mel16_arena);
     for (float* p : h->rvq_arenas) if (p) cudaFree(p);
     for (auto* hs : h->heads) { if (hs->arena) cudaFree(hs->arena); delete hs; }
+    for (auto* ss : h->streams) { for (void* p : ss->all) if (p) cudaFree(p); delete ss; }
     delete h;
     return FAC_OK;
 }
@@ -1396,6 +1443,164 @@ int fac_voice_convert(fac_handle* h, const int64_t* codes_p, const int64_t* code
         float* zcl = redecoder_forward(c, codes_p, codes_c, n_c_rows, timbre, B, T, use_p_code, use_c_code, n_c);
         decoder_forward(c, h->dec2, zcl, B, T, y);
     });
+}
+
+// ---- streaming: chunked encoder / decoder with LSTM-state carry and conv halos ----
+// Left context of the encoder's conv stack: 5581 samples (conv0 6 + stage 1 78 + down 3 + stage 2 156 + down 18 + stage 3 780
+// + down 90 + stage 4 3900 + down 550) -> 6000 (20 frames); of the decoder's stack after the LSTM: < 18 latent frames -> 20.
+constexpr int kEncCtx = 6000, kDecCtx = 20, kStreamMinFirst = 10;
+
+int fac_stream_begin(fac_handle* h, int B) {
+    if (!h || B < 1 || B > 32) { if (h) h->err = "fac_stream_begin: 1 <= B <= 32"; return FAC_ERR_INVALID; }
+    if (!h->finalized) { h->err = "module weights not loaded/finalized"; return FAC_ERR_STATE; }
+    cudaSetDevice(h->device);
+    auto* s = new fac_handle::Stream();
+    s->B = B;
+    const size_t sizes[12] = {
+        sizeof(float) * (size_t)B * kEncCtx, sizeof(float) * (size_t)B * 2 * LATENT, sizeof(float) * (size_t)B * 6 * LATENT,
+        sizeof(float) * (size_t)B * kDecCtx * 1536,
+        sizeof(uint32_t) * 2 * 512 * 32, sizeof(uint32_t) * 2 * 512 * 32, sizeof(float) * 128 * 32 * 8, sizeof(float) * 128 * 32 * 8,
+        sizeof(uint32_t) * 768 * 32, sizeof(uint32_t) * 768 * 32, sizeof(float) * 128 * 32 * 12, sizeof(float) * 128 * 32 * 12};
+    for (int i = 0; i < 12; ++i) {
+        cudaError_t e = cudaMalloc(&s->all[i], sizes[i]);
+        if (e == cudaSuccess) e = cudaMemset(s->all[i], 0, sizes[i]);
+        if (e != cudaSuccess) {
+            h->err = std::string("fac_stream_begin: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            for (void* p : s->all) if (p) cudaFree(p);
+            delete s;
+            return FAC_ERR_CUDA;
+        }
+    }
+    s->x_hist = (float*)s->all[0]; s->ey_hist = (float*)s->all[1]; s->z_hist = (float*)s->all[2]; s->dy_hist = (float*)s->all[3];
+    s->enc_h[0] = (uint32_t*)s->all[4]; s->enc_h[1] = (uint32_t*)s->all[5]; s->enc_c[0] = (float*)s->all[6]; s->enc_c[1] = (float*)s->all[7];
+    s->dec_h[0] = (uint32_t*)s->all[8]; s->dec_h[1] = (uint32_t*)s->all[9]; s->dec_c[0] = (float*)s->all[10]; s->dec_c[1] = (float*)s->all[11];
+    s->alive = true;
+    h->streams.push_back(s);
+    return (int)h->streams.size() - 1;
+}
+
+int fac_stream_end(fac_handle* h, int stream_id) {
+    if (!h || stream_id < 0 || stream_id >= (int)h->streams.size()) return FAC_ERR_INVALID;
+    fac_handle::Stream* s = h->streams[stream_id];
+    if (s->alive) {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        for (void*& p : s->all) { if (p) cudaFree(p); p = nullptr; }
+        s->alive = false;
+    }
+    return FAC_OK;
+}
+
+namespace {
+// dst[b][0..n) = src[b][off..off+n) for rows of `w` floats each (row pitches in rows)
+void copy_rows(Ctx& c, float* dst, int dst_pitch_rows, const float* src, int src_pitch_rows, int off_rows, int n_rows, int w, int B,
+               const char* what) {
+    if (c.dry || n_rows <= 0) return;
+    c.check_nk(cudaMemcpy2DAsync(dst, sizeof(float) * (size_t)dst_pitch_rows * w, src + (size_t)off_rows * w,
+                                 sizeof(float) * (size_t)src_pitch_rows * w, sizeof(float) * (size_t)n_rows * w, B,
+                                 cudaMemcpyDeviceToDevice, c.st), what);
+}
+}  // namespace
+
+int fac_stream_encode(fac_handle* h, int stream_id, const float* x, int T, float* z, void* stream) {
+    int rc = check_ready(h, FAC_ENCODER);
+    if (rc) return rc;
+    if (stream_id < 0 || stream_id >= (int)h->streams.size() || !h->streams[stream_id]->alive || !x || !z) { h->err = "fac_stream_encode: bad arguments"; return FAC_ERR_INVALID; }
+    fac_handle::Stream& s = *h->streams[stream_id];
+    if (T <= 0 || T % HOP != 0 || (s.enc_samples == 0 && T < kStreamMinFirst * HOP)) {
+        h->err = "fac_stream_encode: chunks must be multiples of 300 samples, the first one at least 3000";
+        return FAC_ERR_INVALID;
+    }
+    if (!h->lstm_v2 || !h->enc.lstm.has2[1]) { h->err = "fac_stream_encode: needs the resident-W LSTM kernel"; return FAC_ERR_UNSUPPORTED; }
+    const int B = s.B, hist = s.x_hist_len, Tw = hist + T, Fc = T / HOP, Fh = hist / HOP;
+    rc = two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        const EncW& e = h->enc;
+        c.vq_critical = true;
+        float* xw = c.alloc<float>((size_t)B * Tw);
+        copy_rows(c, xw, Tw, s.x_hist, kEncCtx, 0, hist, 1, B, "stream.xh");
+        copy_rows(c, xw + hist, Tw, x, T, 0, T, 1, B, "stream.xc");
+        int Fw = 0;
+        float* feats = encoder_front(c, xw, B, Tw, &Fw);                    // [B][Fw][1024], Fw == Fh + Fc
+        float* fnew = c.alloc<float>((size_t)B * Fc * LATENT);
+        copy_rows(c, fnew, Fc, feats, Fw, Fh, Fc, LATENT, B, "stream.fnew");
+        const int yh = s.ey_hist_len;
+        float* yw = c.alloc<float>((size_t)B * (yh + Fc) * LATENT);        // [hist | new] LSTM outputs
+        float* ynew = c.alloc<float>((size_t)B * Fc * LATENT);
+        LstmState st;
+        st.h[0] = s.enc_h[0]; st.h[1] = s.enc_h[1]; st.c[0] = s.enc_c[0]; st.c[1] = s.enc_c[1];
+        slstm(c, e.lstm, fnew, ynew, B, Fc, &st);
+        copy_rows(c, yw, yh + Fc, s.ey_hist, 2, 0, yh, LATENT, B, "stream.yh");
+        copy_rows(c, yw + (size_t)yh * LATENT, yh + Fc, ynew, Fc, 0, Fc, LATENT, B, "stream.yc");
+        float* zw = c.alloc<float>((size_t)B * (yh + Fc) * LATENT);
+        float* znew = c.alloc<float>((size_t)B * Fc * LATENT);
+        ConvOpts o;
+        o.in_snake = &e.snake;
+        sconv(c, e.conv_out, yw, zw, B, yh + Fc, 1, 1, o, "enc.conv_out");
+        copy_rows(c, znew, Fc, zw, yh + Fc, yh, Fc, LATENT, B, "stream.znew");
+        if (!c.dry) c.check(launch_transpose(znew, z, B, Fc, LATENT, c.st), "enc.z_T");
+        // new histories: the last kEncCtx samples / 2 LSTM-output frames of what has been seen so far
+        const int nh = Tw < kEncCtx ? Tw : kEncCtx, nyh = yh + Fc < 2 ? yh + Fc : 2;
+        float* tmpx = c.alloc<float>((size_t)B * kEncCtx);
+        copy_rows(c, tmpx, kEncCtx, xw, Tw, Tw - nh, nh, 1, B, "stream.xh2");
+        copy_rows(c, s.x_hist, kEncCtx, tmpx, kEncCtx, 0, nh, 1, B, "stream.xh3");
+        copy_rows(c, s.ey_hist, 2, yw, yh + Fc, yh + Fc - nyh, nyh, LATENT, B, "stream.yh2");
+        c.vq_critical = false;
+    });
+    if (rc == FAC_OK) {
+        s.x_hist_len = Tw < kEncCtx ? Tw : kEncCtx;
+        s.ey_hist_len = s.ey_hist_len + Fc < 2 ? s.ey_hist_len + Fc : 2;
+        s.enc_samples += T;
+    }
+    return rc;
+}
+
+int fac_stream_decode(fac_handle* h, int stream_id, const float* z, int Fc, float* y, void* stream) {
+    int rc = check_ready(h, FAC_DECODER);
+    if (rc) return rc;
+    if (stream_id < 0 || stream_id >= (int)h->streams.size() || !h->streams[stream_id]->alive || !z || !y) { h->err = "fac_stream_decode: bad arguments"; return FAC_ERR_INVALID; }
+    fac_handle::Stream& s = *h->streams[stream_id];
+    if (Fc <= 0 || (s.dec_frames == 0 && Fc < kStreamMinFirst)) { h->err = "fac_stream_decode: the first chunk needs at least 10 frames"; return FAC_ERR_INVALID; }
+    if (!h->lstm_v2 || !h->dec_bf16 || !h->dec_lstm_fp16 || !h->dec.lstm.has2[0]) { h->err = "fac_stream_decode: needs the resident-W LSTM kernel"; return FAC_ERR_UNSUPPORTED; }
+    const int B = s.B, zh = s.z_hist_len, dh = s.dy_hist_len;
+    rc = two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        const DecW& d = h->dec;
+        float* znew = c.alloc<float>((size_t)B * Fc * LATENT);
+        if (!c.dry) c.check(launch_transpose(z, znew, B, LATENT, Fc, c.st), "dec.z_transpose");
+        float* zw = c.alloc<float>((size_t)B * (zh + Fc) * LATENT);
+        copy_rows(c, zw, zh + Fc, s.z_hist, 6, 0, zh, LATENT, B, "stream.zh");
+        copy_rows(c, zw + (size_t)zh * LATENT, zh + Fc, znew, Fc, 0, Fc, LATENT, B, "stream.zc");
+        float* c0w = c.alloc<float>((size_t)B * (zh + Fc) * 1536);
+        sconv(c, d.conv0, zw, c0w, B, zh + Fc, 1, 1, ConvOpts(), "dec.conv0");
+        float* c0new = c.alloc<float>((size_t)B * Fc * 1536);
+        copy_rows(c, c0new, Fc, c0w, zh + Fc, zh, Fc, 1536, B, "stream.c0new");
+        float* ynew = c.alloc<float>((size_t)B * Fc * 1536);
+        LstmState st;
+        st.h[0] = s.dec_h[0]; st.h[1] = s.dec_h[1]; st.c[0] = s.dec_c[0]; st.c[1] = s.dec_c[1];
+        slstm(c, d.lstm, c0new, ynew, B, Fc, &st);
+        const int Fw = dh + Fc;
+        const size_t stage = decoder_stage_floats(B, Fw);
+        float* buf[3] = {c.alloc<float>(stage), c.alloc<float>(stage), c.alloc<float>(stage)};
+        float* yw_in = c.alloc<float>((size_t)B * Fw * 1536);
+        copy_rows(c, yw_in, Fw, s.dy_hist, kDecCtx, 0, dh, 1536, B, "stream.dh");
+        copy_rows(c, yw_in + (size_t)dh * 1536, Fw, ynew, Fc, 0, Fc, 1536, B, "stream.dc");
+        float* yw = c.alloc<float>((size_t)B * Fw * HOP);
+        decoder_stack(c, d, yw_in, -1, buf, B, Fw, yw);
+        copy_rows(c, y, Fc * HOP, yw, Fw * HOP, dh * HOP, Fc * HOP, 1, B, "stream.ynew");
+        const int nzh = zh + Fc < 6 ? zh + Fc : 6, ndh = Fw < kDecCtx ? Fw : kDecCtx;
+        float* tz = c.alloc<float>((size_t)B * 6 * LATENT);
+        float* td = c.alloc<float>((size_t)B * kDecCtx * 1536);
+        copy_rows(c, tz, 6, zw, zh + Fc, zh + Fc - nzh, nzh, LATENT, B, "stream.zh2");
+        copy_rows(c, s.z_hist, 6, tz, 6, 0, nzh, LATENT, B, "stream.zh3");
+        copy_rows(c, td, kDecCtx, yw_in, Fw, Fw - ndh, ndh, 1536, B, "stream.dh2");
+        copy_rows(c, s.dy_hist, kDecCtx, td, kDecCtx, 0, ndh, 1536, B, "stream.dh3");
+    });
+    if (rc == FAC_OK) {
+        s.z_hist_len = zh + Fc < 6 ? zh + Fc : 6;
+        s.dy_hist_len = dh + Fc < kDecCtx ? dh + Fc : kDecCtx;
+        s.dec_frames += Fc;
+    }
+    return rc;
 }
 
 // meldataset.py:37-47 preprocess: torchaudio MelSpectrogram(n_mels=80, n_fft=2048, win_length=1200, hop_length=300) with

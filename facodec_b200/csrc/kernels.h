@@ -86,6 +86,9 @@ struct LstmParams {
     const uint32_t* whh_p2 = nullptr;   // lstm2_pack layout
     uint32_t* h16 = nullptr;            // scratch [2 parities][planes][H/2][32] words
     int pass3 = 0;                      // 1 = fp16 hi + scaled-lo 3-pass (upstream of the VQ); 0 = one fp16 pass
+    // streaming (lstm2 only): state carried between chunks, updated in place; null = zero initial state, nothing saved
+    uint32_t* state_h = nullptr;        // [planes][H/2][32] words (h in the published fp16 layout)
+    float* state_c = nullptr;           // [G][32][U] cell state
     const float* skip = nullptr;  // [B][T][H] added to the output (SLSTM skip) or null
     float* y = nullptr;           // [B][T][H]
     float* hT = nullptr;          // scratch [2][H][32]

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(L2_WARPS * 32, 1) lstm_rec2_kernel(LstmParams 
         const int n16 = nsub_all * PL * 8 * R / 4;
         for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    for (int i = tid; i < L2_BT * U; i += blockDim.x) cstate[i] = 0.f;
+    // cell state: zero (nn.LSTM default) or carried over from the previous chunk of a stream (state_c: [G][32][U])
+    for (int i = tid; i < L2_BT * U; i += blockDim.x) cstate[i] = p.state_c ? p.state_c[(size_t)cta * L2_BT * U + i] : 0.f;
     __syncthreads();
 
     uint32_t* my_stage = stage_base + warp * L2_DEPTH * STAGE_W;
@@ -253,6 +254,10 @@ __global__ void __launch_bounds__(L2_WARPS * 32, 1) lstm_rec2_kernel(LstmParams 
         }
         if (probe) { long long n = clock64(); ph[3] += n - tc0; }
     }
+    if (p.state_c) {
+        __syncthreads();
+        for (int i = tid; i < L2_BT * U; i += blockDim.x) p.state_c[(size_t)cta * L2_BT * U + i] = cstate[i];
+    }
     if (probe) { for (int i = 0; i < 4; ++i) g_lstm2_phase_clock[i] = ph[i]; }
 }
 
@@ -299,11 +304,17 @@ static cudaError_t launch2_u(const LstmParams& p, cudaStream_t st) {
     // h_{-1} = 0 lives in parity slot 1 (all planes)
     const size_t plane_words = (size_t)(p.H / 2) * L2_BT;
     const int PL = PASS3 ? 2 : 1;
-    e = cudaMemsetAsync(p.h16 + (size_t)PL * plane_words, 0, sizeof(uint32_t) * PL * plane_words, st);
+    // ... or the carried-over h of a stream (state_h: [planes][H/2][32] words, the layout the kernel publishes)
+    if (p.state_h) e = cudaMemcpyAsync(p.h16 + (size_t)PL * plane_words, p.state_h, sizeof(uint32_t) * PL * plane_words, cudaMemcpyDeviceToDevice, st);
+    else e = cudaMemsetAsync(p.h16 + (size_t)PL * plane_words, 0, sizeof(uint32_t) * PL * plane_words, st);
     if (e != cudaSuccess) return e;
     LstmParams pp = p;
     void* args[] = {&pp};
-    return cudaLaunchCooperativeKernel((void*)lstm_rec2_kernel<U, PASS3>, dim3(p.G), dim3(L2_WARPS * 32), args, smem, st);
+    e = cudaLaunchCooperativeKernel((void*)lstm_rec2_kernel<U, PASS3>, dim3(p.G), dim3(L2_WARPS * 32), args, smem, st);
+    if (e != cudaSuccess) return e;
+    // h_{T-1} was published into parity slot (T-1) & 1
+    if (p.state_h) e = cudaMemcpyAsync(p.state_h, p.h16 + (size_t)((p.T - 1) & 1) * PL * plane_words, sizeof(uint32_t) * PL * plane_words, cudaMemcpyDeviceToDevice, st);
+    return e;
 }
 
 cudaError_t launch_lstm2_layer(const LstmParams& p, cudaStream_t st) {

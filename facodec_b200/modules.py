@@ -355,6 +355,62 @@ class Codec:
         return self.engine.L.fac_last_launch_count(self.engine.handle)
 
 
+class CodecStream:
+    """Chunked (streaming) use of the causal encoder / decoder of a build_model() Munch (README.md:105-107): feeding an
+    utterance in pieces gives the results of ONE offline model.encoder(x) / model.decoder(z) call (dac/model/dac.py:103-104,
+    :164-165).  The conv left context and the SLSTM (h, c) states live on the device between calls (fac_stream_*)."""
+
+    def __init__(self, model, batch, device=None):
+        self.model = model
+        self.engine = model.encoder._engine
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.engine.sync_weights(dev)
+        self.device = torch.device("cuda", self.engine.device_index)
+        self.batch = int(batch)
+        sid = self.engine.L.fac_stream_begin(self.engine.handle, self.batch)
+        _lib.check(self.engine.handle, sid, "fac_stream_begin")
+        self.sid = sid
+
+    def _check(self, t):
+        if t.device.type != "cuda" or (t.device.index if t.device.index is not None else torch.cuda.current_device()) != self.engine.device_index:
+            raise _lib.FacError("stream inputs must be on cuda:%d (no CPU fallback); got %s" % (self.engine.device_index, t.device))
+        if self.sid is None:
+            raise _lib.FacError("stream is closed")
+
+    def encode(self, x):
+        """x chunk [B,1,T] (T a multiple of 300; first chunk >= 3000 samples) -> z chunk [B,1024,T/300]."""
+        self._check(x)
+        x = _f32c(x)
+        B, C, T = x.shape
+        assert C == 1 and B == self.batch
+        z = torch.empty(B, 1024, max(T // 300, 0), device=x.device, dtype=torch.float32)
+        e = self.engine
+        _lib.check(e.handle, e.L.fac_stream_encode(e.handle, self.sid, _ptr(x), T, _ptr(z), _stream(x.device)), "fac_stream_encode")
+        return z
+
+    def decode(self, z):
+        """z chunk [B,1024,Fc] (first chunk >= 10 frames) -> y chunk [B,1,300*Fc]."""
+        self._check(z)
+        z = _f32c(z)
+        B, C, Fc = z.shape
+        assert C == 1024 and B == self.batch
+        y = torch.empty(B, 1, Fc * 300, device=z.device, dtype=torch.float32)
+        e = self.engine
+        _lib.check(e.handle, e.L.fac_stream_decode(e.handle, self.sid, _ptr(z), Fc, _ptr(y), _stream(z.device)), "fac_stream_decode")
+        return y
+
+    def close(self):
+        if self.sid is not None and self.engine.handle is not None:
+            self.engine.L.fac_stream_end(self.engine.handle, self.sid)
+        self.sid = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 class VoiceConverter:
     """reconstruct_redecoder.py:118-121 as one C call: z = model.encoder(codes[0], codes[1], timbre, use_p_code, n_c);
     wave = model.decoder(z) on a build_model(stage='redecoder') Munch, latents resident."""

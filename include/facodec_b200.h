@@ -103,6 +103,21 @@ int fac_redecoder_decode(fac_handle* h, const float* z, int B, int Tf, float* y,
 int fac_voice_convert(fac_handle* h, const int64_t* codes_p, const int64_t* codes_c, int n_c_rows, const float* timbre,
                       int B, int T, int use_p_code, int use_c_code, int n_c, float* y, void* stream);
 
+/* Streaming (README.md:105-107 "causal ... can be used for streaming"): the encoder and the codec's
+ * decoder are causal, so a long utterance can be processed in chunks with the SAME results as one offline call
+ * (dac/model/dac.py:103-104, :164-165).  The reference ships no streaming driver; these entry points carry what the
+ * causal graph needs between chunks on the device: the conv stacks' left context (6000 samples / 20 latent frames) and the
+ * SLSTM (h, c) states (dac/model/encodec.py:272-288: the SLSTM itself keeps none; it is explicit here).
+ * fac_stream_begin(B <= 32) -> stream id (>= 0) or a negative status; one stream holds one encoder and one decoder state.
+ * fac_stream_encode: x_chunk [B,1,T] (device; T a multiple of 300, the first chunk >= 3000) -> z_chunk [B,1024,T/300].
+ * fac_stream_decode: z_chunk [B,1024,Fc] (device; first chunk >= 10 frames) -> y_chunk [B,1,300*Fc].
+ * The quantizer is not part of the stream: its timbre branch pools over the whole utterance (modules/quantize.py:375-454),
+ * the VQ lookups themselves are per frame (fac_quantize on each z chunk is exact for the codes). */
+int fac_stream_begin(fac_handle* h, int B);
+int fac_stream_encode(fac_handle* h, int stream_id, const float* x, int T, float* z, void* stream);
+int fac_stream_decode(fac_handle* h, int stream_id, const float* z, int Fc, float* y, void* stream);
+int fac_stream_end(fac_handle* h, int stream_id);
+
 /* quantize/rvq.py:27-75 ResidualVQ.forward (eval) over quantize/fvq.py FactorizedVectorQuantize,
  * dim=1024, codebook_dim=8, 2^10 entries (BASELINE configs[3]).  Parameters are passed directly
  * (already weight-normed, HOST): per quantizer q: in_w [8,1024], in_b [8], out_w [1024,8],
