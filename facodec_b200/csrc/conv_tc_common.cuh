@@ -252,11 +252,20 @@ __device__ __forceinline__ void split_store_f16(float4 x4, int pc, int row, int 
     *reinterpret_cast<uint2*>(alo + off) = lv;
 }
 
+// ONE fp16 value per channel (conv_tc_kernel's g1f16 class): hi = rn_f16(x) only, same 8-byte-per-4-channels layout.
+__device__ __forceinline__ void store_f16_single(float4 x4, int pc, int row, int Rpad, uint8_t* ahi) {
+    __half2 h01 = __floats2half2_rn(x4.x, x4.y), h23 = __floats2half2_rn(x4.z, x4.w);
+    const size_t off = ((size_t)(pc >> 1) * Rpad + row) * 16 + (size_t)(pc & 1) * 8;
+    uint2 hv;
+    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(ahi + off) = hv;
+}
+
 // ---- activation producer shared by both kernels ------------------------------------------------
 // Thread `ptid` of NT producer threads owns 16-byte piece pc = ptid & 3 (4 input channels) of
 // rows ptid/4, ptid/4 + NT/4, ...: channel offset, Snake parameters and the smem column are
 // per-thread constants for the whole chunk; only the row varies.
-template <int NT, bool BF16, int BATCH = 4, bool INL = false, bool F16 = false>
+template <int NT, bool BF16, int BATCH = 4, bool INL = false, bool F16 = false, bool SINGLE = false>
 __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMap& pm, const float* __restrict__ xb,
                                               int c, int t0, int R, int Rpad, uint8_t* ahi, uint8_t* alo, int ptid) {
     const int pc = ptid & 3;
@@ -291,7 +300,8 @@ __device__ __forceinline__ void produce_chunk(const TcConvParams& p, const PadMa
             if (rr < R) {
                 float4 x4 = v[u];
                 if (has_alpha) x4 = snake4_sel<BF16, INL>(x4, al, ia);   // snake(0) == 0, so padded zeros stay zero
-                if constexpr (F16) split_store_f16(x4, pc, rr, Rpad, ahi, alo);
+                if constexpr (SINGLE) store_f16_single(x4, pc, rr, Rpad, ahi);
+                else if constexpr (F16) split_store_f16(x4, pc, rr, Rpad, ahi, alo);
                 else split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
             }
         }
@@ -326,7 +336,7 @@ __device__ __forceinline__ void load_chunk_regs(const TcConvParams& p, const Pad
     }
 }
 
-template <int NT, bool BF16>
+template <int NT, bool BF16, bool SINGLE = false>
 __device__ __forceinline__ void store_chunk_regs(const TcConvParams& p, int c, int R, int Rpad, uint8_t* ahi, uint8_t* alo,
                                                  int ptid, const ChunkRegs& cr) {
     const int pc = ptid & 3;
@@ -345,7 +355,8 @@ __device__ __forceinline__ void store_chunk_regs(const TcConvParams& p, int c, i
         if (rr < R) {
             float4 x4 = cr.v[u];
             if (has_alpha) x4 = snake4_sel<BF16>(x4, al, ia);
-            split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
+            if constexpr (SINGLE) store_f16_single(x4, pc, rr, Rpad, ahi);
+            else split_store<BF16>(x4, pc, rr, Rpad, ahi, alo);
         }
     }
 }

@@ -39,6 +39,7 @@ struct ConvW {
     bool tc = false; size_t tcw = 0; int vf = 1, Kr = 0, tcN = 0;   // tcN: channel tile the blob was laid out for
     bool promoted = false;   // blob built for conv_tcp_kernel (layers upstream of the VQ)
     bool has16 = false; size_t tcw16 = 0;   // 16-bit-operand blob: bf16 hi/lo (non-promoted layers) or fp16 hi / scaled lo (promoted)
+    bool has_f16s = false; size_t tcw_f16s = 0;   // hi-only fp16 blob: the one-pass class of the k = 7 convs downstream of the VQ
     bool has_tt = false; size_t tcw_tt = 0; // transposed-formulation blob (conv_tt_kernel, promoted layers): [co tile of 128][chunk][tap][hi|lo']
 };
 struct SnakeW { size_t a = 0, ia = 0; int C = 0; };
@@ -101,6 +102,7 @@ struct fac_handle {
     int dec_lstm_fp16 = 1;          // fac_set_option "decoder_lstm_fp16": downstream LSTMs run ONE fp16 pass (0 = bf16 hi/lo 3-pass)
     int enc_mufu = 0;               // fac_set_option "encoder_snake_mufu" (experiment)
     int attn_stream = 0;            // fac_set_option "attention_stream": 1 forces the recomputing attention kernel (test aid)
+    int dec_c7_f16 = 1;             // fac_set_option "decoder_conv7_fp16": k = 7 convs downstream of the VQ take ONE fp16 pass (0 = bf16 hi/lo 3-pass)
     int enc_tt = 1;                 // fac_set_option "encoder_tt": promoted layers run the transposed kernel (conv_tt_kernel)
     int enc_f16 = 0;                // fac_set_option "encoder_f16x2": promoted layers use the fp16 hi + scaled-lo split
     int tc_occ2 = 256;              // fac_set_option "tc_occ2_maxn": conv_tc tiles with N <= this are planned for two CTAs per SM (0 = off)
@@ -233,6 +235,18 @@ void attach_tc(fac_handle* h, ConvW& c, int stride, bool promoted) {
     }
 }
 
+// hi-only fp16 blob of a stride-1 layer downstream of the VQ (conv_tc_kernel's one-pass class; the dilated k = 7 convs of
+// the ResidualUnits: 7/8 of a unit's MACs, 1.4e-5 RMS on the waveform, scripts/cpu_decoder_precision.py)
+void attach_f16_single(fac_handle* h, ConvW& c) {
+    if (!c.tc || c.promoted || !c.has16 || c.vf != 1) return;
+    TcConvParams t1;
+    t1.Cin = c.Cin; t1.Cout = c.Cout; t1.dil = 1; t1.vf = 1; t1.Kr = c.K; t1.bf16 = 1; t1.g1f16 = 1;
+    if (!tc_conv_plan(t1) || t1.N != c.tcN) return;
+    c.tcw_f16s = pack_alloc(h, tc_blob_floats(t1));
+    tc_pack_blob(t1, h->pack.data() + c.w, c.ldw, h->pack.data() + c.tcw_f16s);
+    c.has_f16s = true;
+}
+
 // nn.Conv1d [Cout][Cin][K] -> packed [K*Cin][ldw]
 ConvW pack_conv(fac_handle* h, int m, const std::string& prefix, int stride = 1, bool promoted = false) {
     std::vector<int64_t> shp;
@@ -325,6 +339,7 @@ ResW pack_res(fac_handle* h, int m, const std::string& prefix, int dil, bool pro
     r.dil = dil;
     r.s1 = pack_snake(h, m, prefix + ".block.0.alpha");
     r.c7 = pack_conv(h, m, prefix + ".block.1.conv.conv", 1, promoted);
+    if (!promoted) attach_f16_single(h, r.c7);
     r.s2 = pack_snake(h, m, prefix + ".block.2.alpha");
     r.c1 = pack_conv(h, m, prefix + ".block.3.conv.conv", 1, promoted);
     return r;
@@ -661,13 +676,14 @@ void run_conv(Ctx& c, const ConvW& w, const float* x, float* y, int B, int Tin, 
         }
         tp.dil = w.vf == 1 ? o.dil : 1;
         tp.bf16 = (c.h->dec_bf16 && w.has16 && !w.promoted && !c.vq_critical) ? 1 : 0;
+        tp.g1f16 = (tp.bf16 && w.has_f16s && c.h->dec_c7_f16) ? 1 : 0;
         tp.f16x2 = (tp.promoted && c.h->enc_f16 && w.has16) ? 1 : 0;
         tp.occ2_maxn = c.h->tc_occ2;
         tp.Tout = Tout;
         const bool use_tt = tp.promoted && c.h->enc_tt && w.has_tt;
         tp.snake_mufu = c.h->enc_mufu;
         if (use_tt ? tt_conv_plan(tp) : tc_conv_plan(tp)) {
-            tp.x = x; tp.y = y; tp.wblob = c.W(use_tt ? w.tcw_tt : ((tp.bf16 || tp.f16x2) ? w.tcw16 : w.tcw)); tp.bias = c.W(w.b);
+            tp.x = x; tp.y = y; tp.wblob = c.W(use_tt ? w.tcw_tt : (tp.g1f16 ? w.tcw_f16s : ((tp.bf16 || tp.f16x2) ? w.tcw16 : w.tcw))); tp.bias = c.W(w.b);
             if (o.in_snake) { tp.in_alpha = c.W(o.in_snake->a); tp.in_inv_alpha = c.W(o.in_snake->ia); }
             tp.out_act = o.act;
             if (o.out_snake) { tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(o.out_snake->a); tp.out_inv_alpha = c.W(o.out_snake->ia); }
@@ -736,6 +752,7 @@ bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B,
     TcConvParams tp;
     tp.Cin = r.c7.Cin; tp.Cout = r.c7.Cout; tp.vf = 1; tp.Kr = r.c7.K; tp.dil = r.dil; tp.fused = 1;
     tp.bf16 = (c.h->dec_bf16 && r.c7.has16 && r.c1.has16) ? 1 : 0;
+    tp.g1f16 = (tp.bf16 && r.c7.has_f16s && c.h->dec_c7_f16) ? 1 : 0;
     tp.occ2_maxn = c.h->tc_occ2;
     tp.Tout = T;
     if (c.h->fuse_res == 2 && r.c7.Cout > 128) return false;
@@ -743,7 +760,7 @@ bool residual_unit_fused(Ctx& c, const ResW& r, const float* x, float* y, int B,
     if (c.dry) return true;
     const int k_eff = (r.c7.K - 1) * r.dil + 1;
     tp.x = x; tp.y = y; tp.res = x;
-    tp.wblob = c.W(tp.bf16 ? r.c7.tcw16 : r.c7.tcw); tp.bias = c.W(r.c7.b);
+    tp.wblob = c.W(tp.g1f16 ? r.c7.tcw_f16s : (tp.bf16 ? r.c7.tcw16 : r.c7.tcw)); tp.bias = c.W(r.c7.b);
     tp.wblob2 = c.W(tp.bf16 ? r.c1.tcw16 : r.c1.tcw); tp.bias2 = c.W(r.c1.b);
     tp.in_alpha = c.W(r.s1.a); tp.in_inv_alpha = c.W(r.s1.ia);
     tp.out_act = ACT_SNAKE; tp.out_alpha = c.W(r.s2.a); tp.out_inv_alpha = c.W(r.s2.ia);
@@ -1956,6 +1973,7 @@ int fac_set_option(fac_handle* h, const char* name, int value) {
     if (std::string(name) == "fuse_resunit") { h->fuse_res = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     if (std::string(name) == "tc_occ2_maxn") { h->tc_occ2 = value < 0 ? 0 : value; return FAC_OK; }
     if (std::string(name) == "encoder_f16x2") { h->enc_f16 = value != 0; return FAC_OK; }
+    if (std::string(name) == "decoder_conv7_fp16") { h->dec_c7_f16 = value != 0; return FAC_OK; }
     if (std::string(name) == "encoder_tt") { h->enc_tt = value != 0; return FAC_OK; }
     if (std::string(name) == "encoder_snake_mufu") { h->enc_mufu = value != 0; return FAC_OK; }
     if (std::string(name) == "overlap_front") { h->overlap_front = value != 0; return FAC_OK; }
@@ -1977,8 +1995,9 @@ int fac_debug_conv_tc(fac_handle* h, const float* x, const float* w_host, const 
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     TcConvParams tp;
-    tp.Cin = Cin; tp.Cout = Cout; tp.promoted = (promoted == 1 || promoted == 3) ? 1 : 0; tp.bf16 = promoted == 2 ? 1 : 0;
+    tp.Cin = Cin; tp.Cout = Cout; tp.promoted = (promoted == 1 || promoted == 3) ? 1 : 0; tp.bf16 = (promoted == 2 || promoted == 5) ? 1 : 0;
     tp.f16x2 = promoted == 3 ? 1 : 0;
+    tp.g1f16 = promoted == 5 ? 1 : 0;      // 5 = the one-pass fp16 class of conv_tc_kernel
     const bool use_tt = promoted == 4;
     tp.occ2_maxn = h->tc_occ2;
     tp.Tout = Tout;
@@ -2027,9 +2046,11 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
     if (!h || !x || !y || !w7_host || !w1_host) return FAC_ERR_INVALID;
     fac_handle tmp;
     tmp.device = h->device;
-    tmp.use_tc = mode == 0 ? 0 : 1;          // 0: fp32 FMA, 1: two tcgen05 launches, 2: fused launch; 3/4 = 1/2 with bf16 split
-    tmp.fuse_res = (mode == 2 || mode == 4) ? 1 : 0;
+    tmp.use_tc = mode == 0 ? 0 : 1;          // 0: fp32 FMA, 1: two tcgen05 launches, 2: fused launch; 3/4 = 1/2 with bf16 split;
+                                             // 5/6 = 3/4 with the k = 7 conv in one fp16 pass
+    tmp.fuse_res = (mode == 2 || mode == 4 || mode == 6) ? 1 : 0;
     tmp.dec_bf16 = mode >= 3;
+    tmp.dec_c7_f16 = mode >= 5;
     tmp.tc_occ2 = h->tc_occ2;
     auto put = [&](const char* key, const float* d, std::vector<int64_t> shp) {
         HostTensor t;
@@ -2060,7 +2081,7 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
         rc = finish(&tmp, c);
         cudaError_t e2 = cudaStreamSynchronize(st);
         if (rc == FAC_OK && e2 != cudaSuccess) { tmp.err = cudaGetErrorString(e2); rc = FAC_ERR_CUDA; }
-        if (rc == FAC_OK && (mode == 2 || mode == 4) && tmp.launches != 1) { tmp.err = "fused path not taken for this geometry"; rc = FAC_ERR_UNSUPPORTED; }
+        if (rc == FAC_OK && (mode == 2 || mode == 4 || mode == 6) && tmp.launches != 1) { tmp.err = "fused path not taken for this geometry"; rc = FAC_ERR_UNSUPPORTED; }
     }
     if (rc != FAC_OK) h->err = tmp.err;
     if (scratch) cudaFree(scratch);

@@ -44,6 +44,8 @@ struct TcConvParams {
     int out_act = 0;
     int promoted = 0;                  // 1 = conv_tcp_kernel (register-promoted accumulation)
     int bf16 = 0;                      // 1 = bf16 hi/lo split (kind::f16, K = 16) instead of tf32 hi/lo; decoder only
+    int g1f16 = 0;                     // with bf16 = 1 (downstream only): the layer's own GEMM (the k-tap conv; GEMM 1 of a fused unit) takes
+                                       // ONE fp16 pass (10-bit operands, fp32 accumulation) instead of the 3-pass bf16 hi/lo split
     int f16x2 = 0;                     // promoted only: fp16 hi + 2^11-scaled fp16 lo split (kind::f16, K = 16) instead of tf32 hi/lo
     int tt = 0;                        // 1 = conv_tt_kernel: transposed formulation (weights = MMA A operand, M = 128 output
                                        // channels; time = N = NT <= 256), fp16 hi + scaled-lo split, promoted (tt_conv_plan)
@@ -59,6 +61,8 @@ struct TcConvParams {
     // plan (tc_conv_plan)
     int promote_every = 1;
     int N = 0, MT = 0, nchunk = 0, Rpad = 0, stagesB = 0, tmem_cols = 0;
+    int tpt = 1, tpt2 = 1;             // conv_tc_kernel: weight tiles ((chunk, tap) / GEMM-2 chunk) per bulk copy into one ring slot
+    int b_slot = 0;                    // bytes of one weight-ring slot
     int R2pad = 0;                     // fused: row pitch (rows) of the resident GEMM-2 operand chunks
     size_t smem_bytes = 0;
     size_t x_bstride = 0, y_bstride = 0;

@@ -28,5 +28,5 @@ for spec in sys.argv[1:]:
     diff = sum(int((a != b).sum()) for a, b in zip(c, c0))
     rms = float(((y.double() - y0.double()) ** 2).mean().sqrt())
     print(f"{spec}: {ms:.2f} ms/step; codes differing from default {diff}; waveform rms diff {rms:.2e}")
-    DEFAULTS = {"encoder_tt": 1, "lstm_v2": 1, "decoder_lstm_fp16": 1, "overlap_front": 1, "fuse_resunit": 1, "decoder_bf16": 1, "tc_occ2_maxn": 256, "tensor_cores": 2}
+    DEFAULTS = {"encoder_tt": 1, "lstm_v2": 1, "decoder_lstm_fp16": 1, "overlap_front": 1, "fuse_resunit": 1, "decoder_bf16": 1, "tc_occ2_maxn": 256, "tensor_cores": 2, "decoder_conv7_fp16": 1}
     for k, v in kv: eng.set_option(k, DEFAULTS.get(k, 0))

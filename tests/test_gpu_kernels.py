@@ -148,7 +148,7 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("occ2", [0, 256])
-@pytest.mark.parametrize("promoted", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("promoted", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc_kernel_vs_torch(case, promoted, occ2, built_lib):
     """tcgen05 3xTF32 conv vs fp32 torch.  Operands are split exactly (hi + lo), but the tensor core adds
@@ -183,17 +183,19 @@ def test_conv_tc_kernel_vs_torch(case, promoted, occ2, built_lib):
     print(f"TCERR promoted={promoted} occ2={occ2} case={case} maxerr={err:.3e} scale={scale:.3f} rel_rms={rel_rms:.3e}")
     # TMEM-truncating 3xTF32 / promoted (fp32-grade) / bf16 hi+lo / promoted with the fp16 hi + scaled-lo split (fp32-grade)
     # 4 = the transposed formulation (conv_tt_kernel): same fp16 hi + scaled-lo split and promotion as 3, time as MMA N
-    tol = {0: 6e-5, 1: 4e-6, 2: 2e-4, 3: 4e-6, 4: 4e-6}[promoted]
+    # 5 = ONE fp16 pass (the k = 7 convs downstream of the VQ): 10-bit operands, error ~2e-4 of the output's RMS
+    tol = {0: 6e-5, 1: 4e-6, 2: 2e-4, 3: 4e-6, 4: 4e-6, 5: 2e-3}[promoted]
     assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
 
 
 @pytest.mark.parametrize("occ2", [0, 256])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("B,T,C,dil", [(2, 300, 96, 1), (1, 520, 96, 9), (2, 200, 192, 3), (1, 130, 256, 1), (2, 40, 96, 9),
                                        (1, 700, 64, 3)])
 def test_residual_unit_modes(B, T, C, dil, mode, occ2, built_lib):
     """ResidualUnit (dac.py:25-42) through the fp32 FMA path (0), two tcgen05 launches (1 tf32, 3 bf16 split), and the
-    fused launch (2 tf32, 4 bf16 split); occ2 = tiles planned for two CTAs per SM."""
+    fused launch (2 tf32, 4 bf16 split), 5/6 = 3/4 with the k = 7 conv in ONE fp16 pass (the product's default downstream of
+    the VQ); occ2 = tiles planned for two CTAs per SM."""
     from oracle import facodec_oracle as O
     if occ2 and mode == 0:
         pytest.skip("fp32 FMA path has no residency option")
@@ -224,6 +226,6 @@ def test_residual_unit_modes(B, T, C, dil, mode, occ2, built_lib):
     assert torch.isfinite(y).all()
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item()
-    tol = 2e-5 if mode == 0 else (8e-5 if mode <= 2 else 3e-4)
+    tol = 2e-5 if mode == 0 else (8e-5 if mode <= 2 else (3e-4 if mode <= 4 else 2e-3))
     print(f"RESUNIT mode={mode} C={C} d={dil} T={T} maxerr={err:.3e} scale={scale:.3f}")
     assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
