@@ -48,6 +48,108 @@ namespace fac {
 // for a free operand buffer, [2]/[3]/[4] MMA warp waiting for operands / weights / a free TMEM buffer, [5] accumulators
 // waiting for MMAs, [6] accumulators in the epilogue, [7] tiles processed.
 __device__ long long g_tc_phase_clock[8];
+// conv_tc_kernel, probe producer thread, totals over the tile's chunks: [0] waiting for a free operand buffer, [1] waiting
+// for the chunk's global loads to land, [2] Snake + split + stores + arrive, [3] chunks
+__device__ long long g_tc_prod_clock[4];
+// per-chunk timeline of the probe CTA (absolute clock64, same SM): [0][c] MMA warp saw chunk c's operands, [1][c] MMA warp
+// done issuing chunk c (MMAs + commits), [2][c] producer thread 0 saw buffer free for chunk c, [3][c] producer thread 0
+// arrived for chunk c, [4][c] cycles the MMA warp waited for weights inside chunk c
+__device__ long long g_tc_trace[5][16];
+
+
+// One chunk of the K loop issued by the (converged) MMA warp: KR taps x MT accumulators x NPASS split passes x K steps.
+// Every operand is a pre-pinned register; a tap is +dil rows on the A descriptor and +b1_16 on the B descriptor.
+__device__ __forceinline__ void pin_u(uint32_t& v) { v = __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ void pin_i(int& v) { v = __shfl_sync(0xffffffffu, v, 0); }
+struct IssueCtx {
+    uint32_t idesc, a_half16, b_half16, a_lbo16, b_lbo16, b1_16, dil, N;
+    int MT;
+};
+template <bool BF16, int NPASS, int KR>
+__device__ __forceinline__ void issue_taps(const IssueCtx& ic, uint32_t d_tmem0, uint32_t a_w, uint32_t b_w, bool first) {
+    constexpr int KSTEPS = BF16 ? 1 : 2;
+#pragma unroll
+    for (int tap = 0; tap < KR; ++tap) {
+        uint32_t a_t = a_w + (uint32_t)tap * ic.dil, d_t = d_tmem0;
+        const uint32_t b_t = b_w + (uint32_t)tap * ic.b1_16;
+#pragma unroll 1
+        for (int mt = 0; mt < ic.MT; ++mt, a_t += 128, d_t += ic.N) {
+#pragma unroll
+            for (int pass = 0; pass < NPASS; ++pass) {
+                const uint32_t aa = a_t + (pass == 2 ? ic.a_half16 : 0u);
+                const uint32_t bb = b_t + (pass == 1 ? ic.b_half16 : 0u);
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint32_t accum = (tap | pass | ks) != 0 ? 1u : (first ? 0u : 1u);
+                    uint64_t da, db;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(da) : "r"(aa + ks * 2 * ic.a_lbo16), "r"(0x4008u));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(db) : "r"(bb + ks * 2 * ic.b_lbo16), "r"(0x4008u));
+                    tc::umma<BF16>(d_t, da, db, ic.idesc, accum);
+                }
+            }
+        }
+    }
+}
+
+// GEMM-2 operand of a fused unit (see conv_tc_kernel): this warp's CW columns of every 16-channel chunk of D1, + b7, Snake,
+// hi/lo split, stored K-major into the resident operand; the TMEM load of chunk c2 + 1 stays in flight behind the
+// arithmetic on chunk c2.
+template <int CW>
+__device__ __forceinline__ void tmem_ldw_issue(uint32_t taddr, uint32_t (&v)[CW]) {
+    if constexpr (CW == 16) {
+        tc::tmem_ld16_issue(taddr, v);
+    } else if constexpr (CW == 8) {
+        tc::tmem_ld8_issue(taddr, v);
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+    }
+}
+template <int CW>
+__device__ __forceinline__ void tmem_ldw_wait(uint32_t (&v)[CW]) {
+    if constexpr (CW == 16) {
+        tc::tmem_ld_wait16(v);
+    } else if constexpr (CW == 8) {
+        tc::tmem_ld_wait8(v);
+    } else {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]) :: "memory");
+    }
+}
+template <int CW, bool BF16>
+__device__ __forceinline__ void a2_phase(const TcConvParams& p, tc::Smem* sm, uint32_t taddr0, int arow, int pc0,
+                                         uint8_t* a2_base, uint32_t a2_half) {
+    using namespace tc;
+    const int Rpad2 = p.R2pad;
+    uint32_t v[CW], vn[CW];
+    tmem_ldw_issue<CW>(taddr0, v);
+    tmem_ldw_wait<CW>(v);
+#pragma unroll 1
+    for (int c2 = 0; c2 < p.nchunk2; ++c2) {
+        uint8_t* ahi = a2_base + (size_t)c2 * 2 * a2_half;
+        uint8_t* alo = ahi + a2_half;
+        const bool more = c2 + 1 < p.nchunk2;
+        if (more) tmem_ldw_issue<CW>(taddr0 + (uint32_t)((c2 + 1) * 16), vn);
+#pragma unroll
+        for (int pp = 0; pp < CW / 4; ++pp) {
+            const int pc = pc0 + pp;
+            const int co = c2 * 16 + pc * 4;
+            float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+            float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
+            float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
+            float4 x4 = make_float4(__uint_as_float(v[pp * 4 + 0]) + bi.x, __uint_as_float(v[pp * 4 + 1]) + bi.y,
+                                    __uint_as_float(v[pp * 4 + 2]) + bi.z, __uint_as_float(v[pp * 4 + 3]) + bi.w);
+            x4 = snake4_sel<BF16>(x4, al, ia);
+            split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
+        }
+        fence_proxy_async();
+        mbar_arrive(&sm->a2_full[c2]);
+        if (more) {
+            tmem_ldw_wait<CW>(vn);
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] = vn[i];
+        }
+    }
+}
 
 
 // FUSED = true runs a whole ResidualUnit (dac.py:25-42) in one launch when all its channels fit one CTA:
@@ -64,10 +166,16 @@ __device__ long long g_tc_phase_clock[8];
 // ring holds a single fp16 plane, the weight tiles are hi-only, a third of the MMAs.  On the oracle this moves the
 // reconstructed waveform by 1.4e-5 RMS when applied to every k = 7 conv of the decoder (scripts/cpu_decoder_precision.py;
 // bar 1e-4); GEMM 2 of a fused unit keeps the bf16 hi/lo class.
-template <bool FUSED, bool BF16, bool G1F16 = false>
-__global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p) {
+// NW = worker warps (producers, then GEMM-2 operand, then epilogue): 8 for tiles planned for two CTAs per SM; 16 for tiles
+// that own a whole SM (fused C = 192: D1 + D2 = 384 TMEM columns) -- with one CTA of 8 workers an SM had 2 warps per
+// scheduler and every SIMT phase ran latency-bound while the MMA warp starved (profiles/r02 phase clocks).
+template <bool FUSED, bool BF16, bool G1F16 = false, int NW = 8>
+__global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(TcConvParams p) {
     static_assert(!G1F16 || BF16, "the one-pass fp16 class shares the 16-bit operand layout");
+    static_assert(NW == 8 || NW == 16, "worker warps");
     using namespace tc;
+    constexpr int NWT = NW * 32;                            // worker threads
+    constexpr int NSUB = NW / 4;                            // worker warps per TMEM lane quarter
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem* sm = reinterpret_cast<Smem*>(smem_raw);
     constexpr int KG = BF16 ? 2 : 4;                        // 16-byte k-groups per 16-channel chunk
@@ -98,10 +206,10 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
 
     if (tid == 0) {
         for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm->a_full[i], 256); mbar_init(&sm->a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->a_full[i], NWT); mbar_init(&sm->a_empty[i], 1); }
         mbar_init(&sm->acc_full, 1);
         mbar_init(&sm->acc2_full, 1);
-        if (FUSED) for (int i = 0; i < 16; ++i) mbar_init(&sm->a2_full[i], 256);
+        if (FUSED) for (int i = 0; i < 16; ++i) mbar_init(&sm->a2_full[i], NWT);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&sm->tmem_base, ncols);
@@ -116,21 +224,26 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
             const float* wsrc = p.wblob + (size_t)ntile * nchunk * Kr * (size_t)(b1_bytes / 4);
             // the blob is [chunk][tap] tiles back to back: TPT consecutive tiles travel as one bulk copy
             const int ntiles = nchunk * Kr;
+            uint32_t ws = 0, wph = 1;                // slot, parity of the EMPTY barrier to wait for (first round passes)
             int tr = 0;
             for (int it0 = 0; it0 < ntiles; it0 += TPT, ++tr) {
-                const int s = tr % S;
                 const uint32_t bytes = (uint32_t)(ntiles - it0 < TPT ? ntiles - it0 : TPT) * b1_bytes;
-                mbar_wait(&sm->b_empty[s], ((tr / S) & 1) ^ 1);
-                mbar_arrive_expect_tx(&sm->b_full[s], bytes);
-                bulk_g2s(b_base + (size_t)s * b_slot, wsrc + (size_t)it0 * (b1_bytes / 4), bytes, &sm->b_full[s]);
+                mbar_wait(&sm->b_empty[ws], wph);
+                if ((p.dbg & 1) && tr >= S) {           // TIMING EXPERIMENT: stale weights
+                    mbar_arrive(&sm->b_full[ws]);
+                } else {
+                    mbar_arrive_expect_tx(&sm->b_full[ws], bytes);
+                    bulk_g2s(b_base + (size_t)ws * b_slot, wsrc + (size_t)it0 * (b1_bytes / 4), bytes, &sm->b_full[ws]);
+                }
+                if (++ws == (uint32_t)S) { ws = 0; wph ^= 1; }
             }
             if (FUSED) {
-                for (int c20 = 0; c20 < p.nchunk2; c20 += TPT2, ++tr) {
-                    const int s = tr % S;
+                for (int c20 = 0; c20 < p.nchunk2; c20 += TPT2) {
                     const uint32_t bytes = (uint32_t)(p.nchunk2 - c20 < TPT2 ? p.nchunk2 - c20 : TPT2) * 2 * b_half;
-                    mbar_wait(&sm->b_empty[s], ((tr / S) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&sm->b_full[s], bytes);
-                    bulk_g2s(b_base + (size_t)s * b_slot, p.wblob2 + (size_t)c20 * (2 * b_half / 4), bytes, &sm->b_full[s]);
+                    mbar_wait(&sm->b_empty[ws], wph);
+                    mbar_arrive_expect_tx(&sm->b_full[ws], bytes);
+                    bulk_g2s(b_base + (size_t)ws * b_slot, p.wblob2 + (size_t)c20 * (2 * b_half / 4), bytes, &sm->b_full[ws]);
+                    if (++ws == (uint32_t)S) { ws = 0; wph ^= 1; }
                 }
             }
         }
@@ -149,16 +262,60 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
             const uint32_t b_base16 = __shfl_sync(0xffffffffu, smem_u32(b_base), 0) >> 4;
             const uint32_t a_lbo16 = (uint32_t)Rpad, b_lbo16 = (uint32_t)N;
             const uint32_t a_half16 = a_half >> 4, b_half16 = b_half >> 4;
-            int it = 0, tr = -1, s = 0, sub = 0;
-            const int ntiles = nchunk * Kr;
             const uint32_t b1_16 = b1_bytes >> 4;
             const bool mprobe = blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0;   // [6]/[7]: cycles waiting for operands / weights
             long long w_a = 0, w_b = 0;
+            const long long t_m0 = mprobe ? clock64() : 0;
+            uint32_t rs = 0, rph = 0;               // weight ring: slot, phase parity
+            if (p.cps > 0) {
+                // Slot-structured issue loop: a weight-ring slot holds ALL taps of `cps` consecutive chunks, so the loop nest
+                // is slot > chunk > tap (unrolled for Kr = 1 / 2 / 7) with no per-tap ring bookkeeping.  The generic loop
+                // below spent ~440 cycles of dependent scalar work per tap (two integer divisions per slot, parameters
+                // re-read from the constant bank, descriptor arithmetic) against 120-155 cycles of tensor-pipe time for the
+                // one MMA of a one-pass tap: the issuing warp, not the tensor pipe, set the pace of every N <= 192 layer
+                // (profiles/r02 per-chunk trace).
+                IssueCtx ic;
+                ic.idesc = idesc1; ic.a_half16 = a_half16; ic.b_half16 = b_half16; ic.a_lbo16 = a_lbo16; ic.b_lbo16 = b_lbo16;
+                ic.b1_16 = b1_16; ic.dil = (uint32_t)p.dil; ic.MT = MT; ic.N = (uint32_t)N;
+                uint32_t a_w0 = a_base16 + (a_lbo16 << 16), b_w0 = b_base16 + (b_lbo16 << 16);
+                uint32_t a_slot16r = a_slot16, b_slot16r = b_slot16, Sr = (uint32_t)S;
+                int cps = p.cps, nch = nchunk, kr = Kr;
+                // pin the loop invariants in registers: a shuffle is opaque to ptxas, which otherwise re-reads kernel
+                // parameters from the constant bank (LDC + dependent use, ~40 cycles each) inside the tap loop
+                pin_u(ic.idesc); pin_u(ic.a_half16); pin_u(ic.b_half16); pin_u(ic.a_lbo16); pin_u(ic.b_lbo16); pin_u(ic.b1_16);
+                pin_u(ic.dil); pin_i(ic.MT); pin_u(ic.N); pin_u(a_w0); pin_u(b_w0); pin_u(a_slot16r); pin_u(b_slot16r); pin_u(Sr);
+                pin_i(cps); pin_i(nch); pin_i(kr);
+                const uint32_t kstride = (uint32_t)kr * ic.b1_16;
+                for (int c0 = 0; c0 < nch; c0 += cps) {
+                    long long tq2 = mprobe ? clock64() : 0;
+                    mbar_wait(&sm->b_full[rs], rph);
+                    if (mprobe) w_b += clock64() - tq2;
+                    uint32_t b_w = b_w0 + rs * b_slot16r;
+                    const int ce = c0 + cps < nch ? c0 + cps : nch;
+                    for (int c = c0; c < ce; ++c, b_w += kstride) {
+                        const int buf = c & 1;
+                        long long tq = mprobe ? clock64() : 0;
+                        mbar_wait(&sm->a_full[buf], (c >> 1) & 1);
+                        if (mprobe) { w_a += clock64() - tq; if (lane == 0 && c < 16) { g_tc_trace[0][c] = clock64(); g_tc_trace[4][c] = 0; } }
+                        tc_fence_after();
+                        const uint32_t a_w = a_w0 + (uint32_t)buf * a_slot16r;
+                        if (kr == 7) issue_taps<BF16, NPASS1, 7>(ic, tmem_u, a_w, b_w, c == 0);
+                        else if (kr == 2) issue_taps<BF16, NPASS1, 2>(ic, tmem_u, a_w, b_w, c == 0);
+                        else issue_taps<BF16, NPASS1, 1>(ic, tmem_u, a_w, b_w, c == 0);
+                        umma_commit(&sm->a_empty[buf]);         // activation buffer free
+                        if (mprobe && lane == 0 && c < 16) g_tc_trace[1][c] = clock64();
+                    }
+                    umma_commit(&sm->b_empty[rs]);              // weight slot free once these MMAs retire
+                    if (++rs == Sr) { rs = 0; rph ^= 1; }
+                }
+            } else {
+            int it = 0, tr = -1, s = 0, sub = 0;
+            const int ntiles = nchunk * Kr;
             for (int c = 0; c < nchunk; ++c) {
                 const int buf = c & 1;
                 long long tq = mprobe ? clock64() : 0;
                 mbar_wait(&sm->a_full[buf], (c >> 1) & 1);
-                if (mprobe) w_a += clock64() - tq;
+                if (mprobe) { w_a += clock64() - tq; if (lane == 0 && c < 16) { g_tc_trace[0][c] = clock64(); g_tc_trace[4][c] = -w_b; } }
                 const uint32_t a_hi = a_base16 + (uint32_t)buf * a_slot16;
                 const uint32_t a_lo = a_hi + a_half16;
                 for (int tap = 0; tap < Kr; ++tap, ++it) {
@@ -192,158 +349,126 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
                     }
                 }
                 umma_commit(&sm->a_empty[buf]);         // activation buffer free
+                if (mprobe && lane == 0 && c < 16) { g_tc_trace[1][c] = clock64(); g_tc_trace[4][c] += w_b; }
+            }
+            const uint32_t trn = (uint32_t)(tr + 1);
+            rs = trn % (uint32_t)S; rph = (trn / (uint32_t)S) & 1u;
             }
             umma_commit(&sm->acc_full);
-            if (mprobe && lane == 0) { g_tc_phase_clock[6] = w_a; g_tc_phase_clock[7] = w_b; }
+            if (mprobe && lane == 0) { g_tc_phase_clock[6] = clock64() - t_m0; g_tc_phase_clock[7] = w_b + w_a; }
             if (FUSED) {
-                const uint32_t a2_lbo16 = (uint32_t)p.R2pad, a2_half16 = a2_half >> 4;
+                // GEMM 2 (the 1x1 conv): resident operand chunks, weight slots of TPT2 chunk tiles (hi|lo)
+                IssueCtx ic;
+                ic.idesc = idesc; ic.a_half16 = a2_half >> 4; ic.b_half16 = b_half16; ic.a_lbo16 = (uint32_t)p.R2pad; ic.b_lbo16 = b_lbo16;
+                ic.b1_16 = 2 * b_half16; ic.dil = 0; ic.MT = MT; ic.N = (uint32_t)N;
                 const uint32_t a2_base16 = __shfl_sync(0xffffffffu, smem_u32(a2_base), 0) >> 4;
-                sub = 0;
-                for (int c2 = 0; c2 < p.nchunk2; ++c2) {
-                    mbar_wait(&sm->a2_full[c2], 0);
-                    if (sub == 0) {
-                        ++tr;
-                        s = tr % S;
-                        mbar_wait(&sm->b_full[s], (tr / S) & 1);
+                uint32_t a_w0 = a2_base16 + (ic.a_lbo16 << 16), b_w0 = b_base16 + (b_lbo16 << 16);
+                uint32_t b_slot16r = b_slot16, Sr = (uint32_t)S;
+                const uint32_t a2_chunk16 = 2 * ic.a_half16;
+                int nch2 = p.nchunk2, tpt2 = TPT2;
+                pin_u(ic.idesc); pin_u(ic.a_half16); pin_u(ic.b_half16); pin_u(ic.a_lbo16); pin_u(ic.b_lbo16); pin_u(ic.b1_16);
+                pin_i(ic.MT); pin_u(ic.N); pin_u(a_w0); pin_u(b_w0); pin_u(b_slot16r); pin_u(Sr); pin_i(nch2); pin_i(tpt2);
+                const uint32_t d2 = tmem_u + (uint32_t)(MT * N);
+                for (int c20 = 0; c20 < nch2; c20 += tpt2) {
+                    mbar_wait(&sm->b_full[rs], rph);
+                    uint32_t b_w = b_w0 + rs * b_slot16r;
+                    const int ce = c20 + tpt2 < nch2 ? c20 + tpt2 : nch2;
+                    for (int c2 = c20; c2 < ce; ++c2, b_w += ic.b1_16) {
+                        mbar_wait(&sm->a2_full[c2], 0);
+                        tc_fence_after();
+                        issue_taps<BF16, 3, 1>(ic, d2, a_w0 + (uint32_t)c2 * a2_chunk16, b_w, c2 == 0);
                     }
-                    tc_fence_after();
-                    const uint32_t a_hi = a2_base16 + (uint32_t)c2 * 2 * a2_half16;
-                    const uint32_t a_lo = a_hi + a2_half16;
-                    const uint32_t b_hi = b_base16 + (uint32_t)s * b_slot16 + (uint32_t)sub * 2 * b_half16;
-                    const uint32_t b_lo = b_hi + b_half16;
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t row_off = (uint32_t)(mt * 128);
-                        const uint32_t d_tmem = tmem_u + (uint32_t)(MT * N + mt * N);
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint32_t aa = (pass == 2 ? a_lo : a_hi) + row_off;
-                            const uint32_t bb = (pass == 1 ? b_lo : b_hi);
-#pragma unroll
-                            for (int ks = 0; ks < KSTEPS; ++ks) {
-                                uint32_t accum = (c2 | pass | ks) != 0;
-                                umma<BF16>(d_tmem, desc_u(aa + ks * 2 * a2_lbo16, a2_lbo16), desc_u(bb + ks * 2 * b_lbo16, b_lbo16), idesc, accum);
-                            }
-                        }
-                    }
-                    if (++sub == TPT2 || c2 == p.nchunk2 - 1) {
-                        umma_commit(&sm->b_empty[s]);
-                        sub = 0;
-                    }
+                    umma_commit(&sm->b_empty[rs]);
+                    if (++rs == Sr) { rs = 0; rph ^= 1; }
                 }
                 umma_commit(&sm->acc2_full);
             }
         }
     } else {
-        // ================= activation producers (warps 2..9) =================
-        const int ptid = tid - 64;                                  // 0..255
+        // ================= activation producers (warps 2..NW+1) =================
+        const int ptid = tid - 64;                                  // 0..NWT-1
         const bool probe = (ptid == 0 && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0);
         if (probe) g_tc_phase_clock[0] = clock64();
         const PadMap pm = PadMap::make(p.Tin, p.pad_left_s, p.pad_right_s, p.reflect);
         const float* __restrict__ xb = p.x + (size_t)b * p.x_bstride;
-        if (R <= PIPE_P * 64) {
+        // interior tile: every row of the union exists in the input (no padding, no tail) and a row is one sample
+        const int vrow0 = t0 - p.PLr;
+        const bool interior = p.vf == 1 && vrow0 >= 0 && vrow0 + R <= p.Tin && vrow0 + R <= p.Tout + (Kr - 1) * p.dil;
+        const float* __restrict__ isrc = interior ? xb + (size_t)(vrow0 + (ptid >> 2)) * p.ldx + (ptid & 3) * 4 : xb;
+        const size_t pstride = (size_t)(NWT / 4) * p.ldx;
+        long long pw_e = 0, pw_l = 0, pw_x = 0;
+        if (R <= PIPE_P * (NWT / 4)) {
             // <= 5 pieces per thread: keep the next chunk's loads in flight while transforming this one
-            ChunkRegs cur, nxt;
-            load_chunk_regs<256>(p, pm, xb, 0, t0, R, ptid, cur);
+            ChunkRegs cur, nxt = {};
+            const int npc = (R - (ptid >> 2) + NWT / 4 - 1) / (NWT / 4);     // this thread's pieces per chunk
+            if (interior) load_chunk_interior<NWT>(isrc, pstride, npc, cur);
+            else load_chunk_regs<NWT>(p, pm, xb, 0, t0, R, ptid, cur);
             for (int c = 0; c < nchunk; ++c) {
                 const int buf = c & 1;
-                if (c + 1 < nchunk) load_chunk_regs<256>(p, pm, xb, c + 1, t0, R, ptid, nxt);
+                if (c + 1 < nchunk && !(p.dbg & 2)) {   // dbg bit 2, TIMING EXPERIMENT: chunk 0's values for every chunk
+                    if (interior) load_chunk_interior<NWT>(isrc + (c + 1) * kChunk, pstride, npc, nxt);
+                    else load_chunk_regs<NWT>(p, pm, xb, c + 1, t0, R, ptid, nxt);
+                }
+                long long tq = probe ? clock64() : 0;
                 mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                if (probe) {
+                    long long t1 = clock64();
+                    pw_e += t1 - tq;
+                    if (c < 16) g_tc_trace[2][c] = t1;
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int u = 0; u < PIPE_P; ++u) sacc += cur.v[u].x + cur.v[u].w;
+                    if (sacc == 1.2345e-33f) pw_e += 1;     // a real use of the loaded registers: stalls until they land
+                    tq = clock64();
+                    pw_l += tq - t1;
+                }
                 uint8_t* ahi = a_base + (size_t)buf * a_slot;
-                store_chunk_regs<256, BF16, G1F16>(p, c, R, Rpad, ahi, ahi + a_half, ptid, cur);
+                if (interior) store_chunk_interior<NWT, BF16, G1F16>(p, c, npc, Rpad, ahi, ahi + a_half, ptid, cur);
+                else store_chunk_regs<NWT, BF16, G1F16>(p, c, R, Rpad, ahi, ahi + a_half, ptid, cur);
                 fence_proxy_async();    // make the generic-proxy stores visible to the tensor core
                 mbar_arrive(&sm->a_full[buf]);
-                cur = nxt;
+                if (probe) { pw_x += clock64() - tq; if (c < 16) g_tc_trace[3][c] = clock64(); }
+                if (!(p.dbg & 2)) cur = nxt;
             }
         } else {
             for (int c = 0; c < nchunk; ++c) {
                 const int buf = c & 1;
+                long long tq = probe ? clock64() : 0;
                 mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                if (probe) { long long t1 = clock64(); pw_e += t1 - tq; tq = t1; }
                 uint8_t* ahi = a_base + (size_t)buf * a_slot;
-                produce_chunk<256, BF16, 4, false, false, G1F16>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
+                if (interior) produce_chunk_interior<NWT, BF16, G1F16>(p, isrc + c * kChunk, pstride, c, R, Rpad, ahi, ahi + a_half, ptid);
+                else produce_chunk<NWT, BF16, 4, false, false, G1F16>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
                 fence_proxy_async();
                 mbar_arrive(&sm->a_full[buf]);
+                if (probe) pw_x += clock64() - tq;
             }
         }
+        if (probe) { g_tc_prod_clock[0] = pw_e; g_tc_prod_clock[1] = pw_l; g_tc_prod_clock[2] = pw_x; g_tc_prod_clock[3] = nchunk; }
         // ================= epilogue =================
         if (probe) g_tc_phase_clock[1] = clock64();                 // all activation chunks produced
         mbar_wait_relaxed(&sm->acc_full, 0);
         tc_fence_after();
         if (probe) g_tc_phase_clock[2] = clock64();                 // GEMM 1 retired
         const int q = warp & 3;                                     // TMEM lane quarter of this warp
-        const int half = (warp - 2) >> 2;                           // two warps per quarter split the columns
+        const int h = (warp - 2) >> 2;                              // NSUB warps per quarter split the columns
+        const int half = h & 1;
         uint32_t d_base = tmem;                                     // accumulator the final epilogue reads
         const float* ep_bias = p.bias;
         int ep_act = p.out_act;
         if (FUSED) {
             // ---- GEMM-2 operand: snake2(D1 + b7), 16 channels per chunk, straight from TMEM ----
             // The whole operand stays resident (no ring, no waits): the MMA warp starts chunk c2 as soon as it is
-            // complete while the workers already transform the next ones.
-            const int Rpad2 = p.R2pad;
+            // complete while the workers already transform the next ones.  The NSUB warps of a lane quarter share the
+            // MT * 16 columns of a chunk: CW = 16 * MT / NSUB columns each (accumulator am, column offset coff).
             const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-            if (MT == 2) {
-                // warp (q, half) owns rows q*32.. of accumulator `half`, all 16 columns of a chunk
-                const int arow = half * 128 + q * 32 + lane;
-                uint32_t v[16], vn[16];
-                tmem_ld16_issue(lane_addr + (uint32_t)(half * N), v);
-                tmem_ld_wait16(v);
-#pragma unroll 1
-                for (int c2 = 0; c2 < p.nchunk2; ++c2) {
-                    uint8_t* ahi = a2_base + (size_t)c2 * 2 * a2_half;
-                    uint8_t* alo = ahi + a2_half;
-                    const bool more = c2 + 1 < p.nchunk2;
-                    if (more) tmem_ld16_issue(lane_addr + (uint32_t)(half * N + (c2 + 1) * 16), vn);
-#pragma unroll
-                    for (int pc = 0; pc < 4; ++pc) {
-                        const int co = c2 * 16 + pc * 4;
-                        float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-                        float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
-                        float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
-                        float4 x4 = make_float4(__uint_as_float(v[pc * 4 + 0]) + bi.x, __uint_as_float(v[pc * 4 + 1]) + bi.y,
-                                                __uint_as_float(v[pc * 4 + 2]) + bi.z, __uint_as_float(v[pc * 4 + 3]) + bi.w);
-                        x4 = snake4_sel<BF16>(x4, al, ia);
-                        split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
-                    }
-                    fence_proxy_async();
-                    mbar_arrive(&sm->a2_full[c2]);
-                    if (more) {
-                        tmem_ld_wait16(vn);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = vn[i];
-                    }
-                }
-            } else {
-                // MT == 1: the two warps of a lane quarter take 8 columns of every chunk each
-                const int arow = q * 32 + lane;
-                uint32_t v[8], vn[8];
-                tmem_ld8_issue(lane_addr + (uint32_t)(half * 8), v);
-                tmem_ld_wait8(v);
-#pragma unroll 1
-                for (int c2 = 0; c2 < p.nchunk2; ++c2) {
-                    uint8_t* ahi = a2_base + (size_t)c2 * 2 * a2_half;
-                    uint8_t* alo = ahi + a2_half;
-                    const bool more = c2 + 1 < p.nchunk2;
-                    if (more) tmem_ld8_issue(lane_addr + (uint32_t)((c2 + 1) * 16 + half * 8), vn);
-#pragma unroll
-                    for (int pp = 0; pp < 2; ++pp) {
-                        const int pc = half * 2 + pp;
-                        const int co = c2 * 16 + pc * 4;
-                        float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-                        float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
-                        float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
-                        float4 x4 = make_float4(__uint_as_float(v[pp * 4 + 0]) + bi.x, __uint_as_float(v[pp * 4 + 1]) + bi.y,
-                                                __uint_as_float(v[pp * 4 + 2]) + bi.z, __uint_as_float(v[pp * 4 + 3]) + bi.w);
-                        x4 = snake4_sel<BF16>(x4, al, ia);
-                        split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
-                    }
-                    fence_proxy_async();
-                    mbar_arrive(&sm->a2_full[c2]);
-                    if (more) {
-                        tmem_ld_wait8(vn);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = vn[i];
-                    }
-                }
-            }
+            const int CW = 16 * MT / NSUB;
+            const int am = (h * CW) >> 4, coff = (h * CW) & 15;
+            const int arow = am * 128 + q * 32 + lane;
+            const uint32_t taddr0 = lane_addr + (uint32_t)(am * N + coff);
+            if (CW == 16) a2_phase<16, BF16>(p, sm, taddr0, arow, coff >> 2, a2_base, a2_half);
+            else if (CW == 8) a2_phase<8, BF16>(p, sm, taddr0, arow, coff >> 2, a2_base, a2_half);
+            else a2_phase<4, BF16>(p, sm, taddr0, arow, coff >> 2, a2_base, a2_half);
             tc_fence_before();
             if (probe) g_tc_phase_clock[3] = clock64();             // GEMM-2 operand produced
             mbar_wait_relaxed(&sm->acc2_full, 0);
@@ -361,19 +486,18 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
         if ((N & 31) == 0) {
             // coalesced path: 32-column groups through the (now idle) activation buffers as transpose stage
             float* stage = reinterpret_cast<float*>(a_base) + (size_t)(warp - 2) * (32 * 36);
-            const int ng = N / 32, gsplit = (ng + 1) / 2;
-            const int gbeg = half ? gsplit : 0, gend = half ? ng : gsplit;
+            // the MT * N/32 column groups of a lane quarter are dealt to its NSUB warps in contiguous runs
+            const int ng = N / 32, items = MT * ng;
+            const int ibeg = h * items / NSUB, iend = (h + 1) * items / NSUB;
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll 1
-                for (int g = gbeg; g < gend; ++g) {
-                    uint32_t acc[32];
-                    tmem_ld32(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + g * 32), acc);
-                    float v[32];
+            for (int item = ibeg; item < iend; ++item) {
+                const int mt = item / ng, g = item - mt * ng;
+                uint32_t acc[32];
+                tmem_ld32(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + g * 32), acc);
+                float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-                    epilogue_tile32<true, BF16>(p, ep_bias, ep_act, v, stage, lane, t0 + mt * 128 + q * 32, ntile * N + g * 32, yb, rb);
-                }
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+                epilogue_tile32<true, BF16>(p, ep_bias, ep_act, v, stage, lane, t0 + mt * 128 + q * 32, ntile * N + g * 32, yb, rb);
             }
             if (probe) g_tc_phase_clock[5] = clock64();
         } else {
@@ -394,12 +518,14 @@ __global__ void __launch_bounds__(tc::kThreads, 2) conv_tc_kernel(TcConvParams p
                 for (int j4 = 0; j4 < 4; ++j4) dst[j4] = *reinterpret_cast<const float4*>(rrow + j4 * 4);
             }
         };
-        if (total > 0) fetch_res(0, rcur);
+        constexpr int GSTEP = NSUB / 2;                             // NW = 16: the two warps of a column half alternate groups
+        const int g0 = h >> 1;
+        if (g0 < total) fetch_res(g0, rcur);
 #pragma unroll 1
-        for (int g = 0; g < total; ++g) {
+        for (int g = g0; g < total; g += GSTEP) {
             const int mt = g / ngrp, c0 = cbeg + (g - mt * ngrp) * 16;
             const int t = t0 + mt * 128 + row;
-            if (g + 1 < total) fetch_res(g + 1, rnxt);
+            if (g + GSTEP < total) fetch_res(g + GSTEP, rnxt);
             uint32_t acc[16];
             tmem_ld16(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + c0), acc);
             if (t < p.Tout) {
@@ -748,7 +874,13 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+int g_tc_dbg = 0;       // fac_set_option "tc_dbg": timing experiments with WRONG results (bit 0: stale weights, bit 1: stale activations)
+int g_tc_wide_ok = 1;
+int g_tc_slot_issue = 1;   // fac_set_option "tc_slot_issue": 0 = legacy per-tap weight-ring bookkeeping in the MMA warp (A/B aid)   // fac_set_option "tc_wide": 0 plans every conv_tc tile with 8 worker warps (A/B aid, process-wide)
+
 bool tc_conv_plan(TcConvParams& p) {
+    p.wide = 0;
+    p.cps = 0;
     // p.Cin, p.vf, p.Kr, p.dil, p.Cout, p.promoted must be set; fills N, MT, nchunk, Rpad, stagesB, ...
     if ((p.Cin % 4) != 0 || ((p.Cin * p.vf) % tc::kChunk) != 0 || (p.Cout % 16) != 0) return false;
     int N = 0;
@@ -821,8 +953,21 @@ bool tc_conv_plan(TcConvParams& p) {
             // (capped: beyond ~96 KB nothing is gained), preferring more stages on ties.
             const size_t avail = smemcap - tc::kSmemHdr - a_bytes - a2_bytes;
             const int ntiles = p.nchunk * p.Kr;
-            int S = 0, tpt = 1;
+            int S = 0, tpt = 1, cps = 0;
             size_t best = 0;
+            // preferred: a slot = every tap of `c` consecutive chunks (slot-structured issue loop, unrolled taps)
+            if (g_tc_slot_issue && (p.Kr == 1 || p.Kr == 2 || p.Kr == 7))
+                for (int c = 1; c <= 16 && c <= p.nchunk; ++c) {
+                    size_t slot = (size_t)c * p.Kr * tile1;
+                    if (p.fused && slot < tile2) slot = tile2;
+                    int s_max = (int)(avail / slot);
+                    if (s_max > tc::kMaxStagesB) s_max = tc::kMaxStagesB;
+                    if (s_max < 2) break;
+                    size_t flight = (size_t)s_max * slot;
+                    if (flight > 96 * 1024) flight = 96 * 1024;
+                    if (flight > best || (flight == best && s_max > S)) { best = flight; S = s_max; tpt = c * p.Kr; cps = c; }
+                }
+            if (S < 2)
             for (int cand = 1; cand <= 16 && cand <= ntiles; ++cand) {
                 size_t slot = cand * tile1;
                 if (p.fused && slot < tile2) slot = tile2;
@@ -836,11 +981,13 @@ bool tc_conv_plan(TcConvParams& p) {
             if (S < 2) continue;
             size_t b_stage = tpt * tile1;
             if (p.fused && b_stage < tile2) b_stage = tile2;
-            p.tpt = tpt; p.b_slot = (int)b_stage;
+            p.tpt = tpt; p.cps = cps; p.b_slot = (int)b_stage;
             p.tpt2 = p.fused ? (int)(b_stage / tile2) : 1;
             if (p.tpt2 < 1) p.tpt2 = 1;
             size_t total = tc::kSmemHdr + a_bytes + S * b_stage + a2_bytes;
-            const size_t stage = (size_t)8 * 32 * 36 * 4 + tc::kSmemHdr;   // epilogue transpose stage (8 warps x [32][36] floats)
+            // a tile that owns the SM (one CTA resident) runs 16 worker warps instead of 8 (bf16-class kernels only)
+            p.wide = (pass == 1 && g_tc_wide_ok && p.bf16 && (N % 32) == 0) ? 1 : 0;
+            const size_t stage = (size_t)(p.wide ? 16 : 8) * 32 * 36 * 4 + tc::kSmemHdr;   // epilogue transpose stage (one [32][36] float tile per worker warp)
             if (total < stage) total = stage;
             p.MT = MT; p.Rpad = Rpad; p.R2pad = R2pad; p.tmem_cols = pow2; p.stagesB = S; p.smem_bytes = total;
             return true;
@@ -953,6 +1100,12 @@ void tc_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob) 
 cudaError_t tc_read_phase_clocks(long long* out8) {
     return cudaMemcpyFromSymbol(out8, g_tc_phase_clock, sizeof(long long) * 8);
 }
+cudaError_t tc_read_producer_clocks(long long* out4) {
+    return cudaMemcpyFromSymbol(out4, g_tc_prod_clock, sizeof(long long) * 4);
+}
+cudaError_t tc_read_trace(long long* out80) {
+    return cudaMemcpyFromSymbol(out80, g_tc_trace, sizeof(long long) * 80);
+}
 
 // Function attributes (the > 48 KB dynamic shared-memory opt-in) and the SM count are PER DEVICE: a process may hold
 // handles on several GPUs (fac_create(out, device)), so both are tracked per device id under a mutex.
@@ -975,6 +1128,10 @@ cudaError_t ensure_device_config(int& sm_count) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e != cudaSuccess) return e;
@@ -986,8 +1143,10 @@ cudaError_t ensure_device_config(int& sm_count) {
 }
 }  // namespace
 
-cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
-    if (p.Tout <= 0 || p.B <= 0) return cudaSuccess;
+cudaError_t launch_conv_tc(const TcConvParams& p_in, cudaStream_t st) {
+    if (p_in.Tout <= 0 || p_in.B <= 0) return cudaSuccess;
+    TcConvParams p = p_in;
+    p.dbg = g_tc_dbg;
     int sm_count = 148;
     cudaError_t e0 = ensure_device_config(sm_count);
     if (e0 != cudaSuccess) return e0;
@@ -999,7 +1158,13 @@ cudaError_t launch_conv_tc(const TcConvParams& p, cudaStream_t st) {
         else conv_tcp_kernel<false><<<dim3(nctas), tc::kThreadsP, p.smem_bytes, st>>>(p);
     } else {
         if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
-        if (p.fused && p.bf16 && p.g1f16) conv_tc_kernel<true, true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        constexpr int kThreadsW = 64 + 32 * 16;
+        if (p.wide && !p.bf16) return cudaErrorInvalidValue;
+        if (p.wide && p.fused && p.g1f16) conv_tc_kernel<true, true, true, 16><<<grid, kThreadsW, p.smem_bytes, st>>>(p);
+        else if (p.wide && p.g1f16) conv_tc_kernel<false, true, true, 16><<<grid, kThreadsW, p.smem_bytes, st>>>(p);
+        else if (p.wide && p.fused) conv_tc_kernel<true, true, false, 16><<<grid, kThreadsW, p.smem_bytes, st>>>(p);
+        else if (p.wide) conv_tc_kernel<false, true, false, 16><<<grid, kThreadsW, p.smem_bytes, st>>>(p);
+        else if (p.fused && p.bf16 && p.g1f16) conv_tc_kernel<true, true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.bf16 && p.g1f16) conv_tc_kernel<false, true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.fused && p.bf16) conv_tc_kernel<true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.fused) conv_tc_kernel<true, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);

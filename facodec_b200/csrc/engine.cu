@@ -1971,6 +1971,9 @@ int fac_debug_slstm(fac_handle* h, const float* x, const float* const* w_host, i
 int fac_set_option(fac_handle* h, const char* name, int value) {
     if (!h || !name) return FAC_ERR_INVALID;
     if (std::string(name) == "fuse_resunit") { h->fuse_res = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
+    if (std::string(name) == "tc_dbg") { g_tc_dbg = value; return FAC_OK; }
+    if (std::string(name) == "tc_slot_issue") { g_tc_slot_issue = value != 0; return FAC_OK; }
+    if (std::string(name) == "tc_wide") { g_tc_wide_ok = value != 0; return FAC_OK; }
     if (std::string(name) == "tc_occ2_maxn") { h->tc_occ2 = value < 0 ? 0 : value; return FAC_OK; }
     if (std::string(name) == "encoder_f16x2") { h->enc_f16 = value != 0; return FAC_OK; }
     if (std::string(name) == "decoder_conv7_fp16") { h->dec_c7_f16 = value != 0; return FAC_OK; }
@@ -2212,6 +2215,24 @@ int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8) {
     cudaDeviceSynchronize();
     cudaError_t e = g_tt_probe_on ? tt_read_probe(out8) : tc_read_phase_clocks(out8);
 
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
+}
+
+int fac_debug_tc_trace(fac_handle* h, long long* out80) {
+    if (!h || !out80) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaError_t e = tc_read_trace(out80);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
+}
+
+int fac_debug_tc_producer_clocks(fac_handle* h, long long* out4) {
+    if (!h || !out4) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaError_t e = tc_read_producer_clocks(out4);
     if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return FAC_ERR_CUDA; }
     return FAC_OK;
 }

@@ -61,9 +61,12 @@ struct TcConvParams {
     // plan (tc_conv_plan)
     int promote_every = 1;
     int N = 0, MT = 0, nchunk = 0, Rpad = 0, stagesB = 0, tmem_cols = 0;
+    int cps = 0;                       // conv_tc_kernel: > 0 = a weight-ring slot holds every tap of `cps` consecutive chunks (tpt = Kr * cps)
     int tpt = 1, tpt2 = 1;             // conv_tc_kernel: weight tiles ((chunk, tap) / GEMM-2 chunk) per bulk copy into one ring slot
     int b_slot = 0;                    // bytes of one weight-ring slot
     int R2pad = 0;                     // fused: row pitch (rows) of the resident GEMM-2 operand chunks
+    int dbg = 0;                       // conv_tc_kernel timing experiments (g_tc_dbg); results are wrong when non-zero
+    int wide = 0;                      // conv_tc_kernel: 1 = 16 worker warps (tile planned for one CTA per SM), 0 = 8
     size_t smem_bytes = 0;
     size_t x_bstride = 0, y_bstride = 0;
 };
@@ -75,8 +78,13 @@ bool tt_conv_plan(TcConvParams& p);                 // conv_tt.cu
 size_t tt_blob_floats(const TcConvParams& p);
 void tt_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob);
 cudaError_t launch_conv_tt(const TcConvParams& p, cudaStream_t st);
+extern int g_tc_dbg;
+extern int g_tc_slot_issue;
+extern int g_tc_wide_ok;                             // conv_tc.cu: 0 = never plan 16-worker tiles (A/B aid)
 extern int g_tt_probe_on;                            // 1 = launch the probing variant (process-wide test aid)
 cudaError_t tt_read_probe(long long* out8);
+cudaError_t tc_read_trace(long long* out80);          // per-chunk timeline of the probe CTA (conv_tc.cu g_tc_trace)
+cudaError_t tc_read_producer_clocks(long long* out4); // probe producer thread of the last conv_tc_kernel
 cudaError_t tc_read_phase_clocks(long long* out8);   // probe-CTA phase timestamps of the last conv_tc_kernel
 
 // ---- LSTM recurrence (lstm.cu) -----------------------------------------------------------

@@ -45,6 +45,13 @@ int fac_debug_resunit(fac_handle* h, const float* x, const float* w7_host, const
  * [0] start, [1] all activation chunks produced, [2] GEMM 1 retired, [3] GEMM-2 operand produced (fused),
  * [4] GEMM 2 retired (fused), [5] epilogue done.  Kernel-tuning aid. */
 int fac_debug_tc_phase_clocks(fac_handle* h, long long* out8);
+/* Probe producer thread of the same launch, cycles summed over the tile's chunks: [0] waiting for a free operand buffer,
+ * [1] waiting for the chunk's global loads, [2] Snake + split + stores + arrive, [3] number of chunks. */
+int fac_debug_tc_producer_clocks(fac_handle* h, long long* out4);
+/* Per-chunk timeline of the same probe CTA, out80 = [5][16] absolute clock64 values for chunks 0..15: [0] MMA warp saw the
+ * chunk's operands, [1] MMA warp finished issuing the chunk, [2] producer thread 0 saw the operand buffer free,
+ * [3] producer thread 0 arrived (chunk stored), [4] cycles the MMA warp waited for weights inside the chunk. */
+int fac_debug_tc_trace(fac_handle* h, long long* out80);
 /* Host-only: the recurrent-weight packing of lstm_rec_kernel for one nn.LSTM weight_hh [4H][H] (HOST, gate order
  * i,f,g,o): bf16 = 0 -> fp32 [G][H][4U] (row r = gate*U + u of the CTA owning hidden units g*U..g*U+U-1);
  * bf16 = 1 -> [G][H/16][hi|lo][8 k-pairs][4U] words of two bf16 (even k in the low half), lo = rn_bf16(w - hi).
