@@ -115,6 +115,12 @@ __device__ __forceinline__ void tmem_ldw_wait(uint32_t (&v)[CW]) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]) :: "memory");
     }
 }
+// One mbarrier arrival per WARP: every lane has fenced its own stores (fence.proxy.async), the warp converges, lane 0
+// arrives.  With one arrival per thread a chunk hand-off was 256-512 serialised shared-memory atomics.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
+}
 template <int CW, bool BF16>
 __device__ __forceinline__ void a2_phase(const TcConvParams& p, tc::Smem* sm, uint32_t taddr0, int arow, int pc0,
                                          uint8_t* a2_base, uint32_t a2_half) {
@@ -142,7 +148,7 @@ __device__ __forceinline__ void a2_phase(const TcConvParams& p, tc::Smem* sm, ui
             split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
         }
         fence_proxy_async();
-        mbar_arrive(&sm->a2_full[c2]);
+        warp_arrive(&sm->a2_full[c2]);
         if (more) {
             tmem_ldw_wait<CW>(vn);
 #pragma unroll
@@ -176,6 +182,12 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
     using namespace tc;
     constexpr int NWT = NW * 32;                            // worker threads
     constexpr int NSUB = NW / 4;                            // worker warps per TMEM lane quarter
+    // 16 workers produce as TWO groups of 8 warps on alternate chunks into a 4-deep operand ring: a group's chunk is one
+    // dependent chain (loads -> Snake -> split -> stores -> proxy fence -> arrive, ~1.5 k cycles whatever the thread count),
+    // so two chunks in flight is what shortens the K loop, not more threads per chunk.
+    constexpr int NG = NW == 16 ? 2 : 1;
+    constexpr int NBUF = 2 * NG;
+    constexpr int GT = NWT / NG;                            // producer threads per group
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem* sm = reinterpret_cast<Smem*>(smem_raw);
     constexpr int KG = BF16 ? 2 : 4;                        // 16-byte k-groups per 16-channel chunk
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
     const int TPT = p.tpt, TPT2 = p.tpt2;                   // tiles per bulk copy: a 3-12 KB tile per round trip left the MMA warp
                                                             // waiting on L2 latency (~500 cycles per tap for N = 96)
     uint8_t* a_base = smem_raw + kSmemHdr;                  // [2 bufs][hi|lo][4 k4][Rpad][16B]
-    uint8_t* b_base = a_base + 2 * a_slot;                  // [S][hi|lo][4 k4][N][16B]
+    uint8_t* b_base = a_base + NBUF * a_slot;               // [S][hi|lo][4 k4][N][16B]
     const int S = p.stagesB;
     // fused: resident GEMM-2 operand, [nchunk2][hi|lo][KG][R2pad][16B]
     const uint32_t a2_half = (uint32_t)p.R2pad * 16 * KG;
@@ -206,10 +218,10 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
 
     if (tid == 0) {
         for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm->a_full[i], NWT); mbar_init(&sm->a_empty[i], 1); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&sm->a_full[i], NW / NG); mbar_init(&sm->a_empty[i], 1); }
         mbar_init(&sm->acc_full, 1);
         mbar_init(&sm->acc2_full, 1);
-        if (FUSED) for (int i = 0; i < 16; ++i) mbar_init(&sm->a2_full[i], NWT);
+        if (FUSED) for (int i = 0; i < 16; ++i) mbar_init(&sm->a2_full[i], NW);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&sm->tmem_base, ncols);
@@ -293,9 +305,9 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
                     uint32_t b_w = b_w0 + rs * b_slot16r;
                     const int ce = c0 + cps < nch ? c0 + cps : nch;
                     for (int c = c0; c < ce; ++c, b_w += kstride) {
-                        const int buf = c & 1;
+                        const int buf = c % NBUF;
                         long long tq = mprobe ? clock64() : 0;
-                        mbar_wait(&sm->a_full[buf], (c >> 1) & 1);
+                        mbar_wait(&sm->a_full[buf], (c / NBUF) & 1);
                         if (mprobe) { w_a += clock64() - tq; if (lane == 0 && c < 16) { g_tc_trace[0][c] = clock64(); g_tc_trace[4][c] = 0; } }
                         tc_fence_after();
                         const uint32_t a_w = a_w0 + (uint32_t)buf * a_slot16r;
@@ -312,9 +324,9 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
             int it = 0, tr = -1, s = 0, sub = 0;
             const int ntiles = nchunk * Kr;
             for (int c = 0; c < nchunk; ++c) {
-                const int buf = c & 1;
+                const int buf = c % NBUF;
                 long long tq = mprobe ? clock64() : 0;
-                mbar_wait(&sm->a_full[buf], (c >> 1) & 1);
+                mbar_wait(&sm->a_full[buf], (c / NBUF) & 1);
                 if (mprobe) { w_a += clock64() - tq; if (lane == 0 && c < 16) { g_tc_trace[0][c] = clock64(); g_tc_trace[4][c] = -w_b; } }
                 const uint32_t a_hi = a_base16 + (uint32_t)buf * a_slot16;
                 const uint32_t a_lo = a_hi + a_half16;
@@ -394,23 +406,26 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
         // interior tile: every row of the union exists in the input (no padding, no tail) and a row is one sample
         const int vrow0 = t0 - p.PLr;
         const bool interior = p.vf == 1 && vrow0 >= 0 && vrow0 + R <= p.Tin && vrow0 + R <= p.Tout + (Kr - 1) * p.dil;
-        const float* __restrict__ isrc = interior ? xb + (size_t)(vrow0 + (ptid >> 2)) * p.ldx + (ptid & 3) * 4 : xb;
-        const size_t pstride = (size_t)(NWT / 4) * p.ldx;
+        const int grp = ptid / GT, gtid = ptid - grp * GT;           // producer group (chunks grp, grp + NG, ...) and thread in it
+        const float* __restrict__ isrc = interior ? xb + (size_t)(vrow0 + (gtid >> 2)) * p.ldx + (gtid & 3) * 4 : xb;
+        const size_t pstride = (size_t)(GT / 4) * p.ldx;
         long long pw_e = 0, pw_l = 0, pw_x = 0;
-        if (R <= PIPE_P * (NWT / 4)) {
-            // <= 5 pieces per thread: keep the next chunk's loads in flight while transforming this one
+        if (R <= PIPE_P * (GT / 4)) {
+            // <= 5 pieces per thread: keep the group's next chunk's loads in flight while transforming this one
             ChunkRegs cur, nxt = {};
-            const int npc = (R - (ptid >> 2) + NWT / 4 - 1) / (NWT / 4);     // this thread's pieces per chunk
-            if (interior) load_chunk_interior<NWT>(isrc, pstride, npc, cur);
-            else load_chunk_regs<NWT>(p, pm, xb, 0, t0, R, ptid, cur);
-            for (int c = 0; c < nchunk; ++c) {
-                const int buf = c & 1;
-                if (c + 1 < nchunk && !(p.dbg & 2)) {   // dbg bit 2, TIMING EXPERIMENT: chunk 0's values for every chunk
-                    if (interior) load_chunk_interior<NWT>(isrc + (c + 1) * kChunk, pstride, npc, nxt);
-                    else load_chunk_regs<NWT>(p, pm, xb, c + 1, t0, R, ptid, nxt);
+            const int npc = (R - (gtid >> 2) + GT / 4 - 1) / (GT / 4);     // this thread's pieces per chunk
+            if (grp < nchunk) {
+                if (interior) load_chunk_interior<GT>(isrc + grp * kChunk, pstride, npc, cur);
+                else load_chunk_regs<GT>(p, pm, xb, grp, t0, R, gtid, cur);
+            }
+            for (int c = grp; c < nchunk; c += NG) {
+                const int buf = c % NBUF;
+                if (c + NG < nchunk && !(p.dbg & 2)) {   // dbg bit 2, TIMING EXPERIMENT: the first chunk's values for every chunk
+                    if (interior) load_chunk_interior<GT>(isrc + (c + NG) * kChunk, pstride, npc, nxt);
+                    else load_chunk_regs<GT>(p, pm, xb, c + NG, t0, R, gtid, nxt);
                 }
                 long long tq = probe ? clock64() : 0;
-                mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                mbar_wait(&sm->a_empty[buf], ((c / NBUF) & 1) ^ 1);
                 if (probe) {
                     long long t1 = clock64();
                     pw_e += t1 - tq;
@@ -423,24 +438,24 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
                     pw_l += tq - t1;
                 }
                 uint8_t* ahi = a_base + (size_t)buf * a_slot;
-                if (interior) store_chunk_interior<NWT, BF16, G1F16>(p, c, npc, Rpad, ahi, ahi + a_half, ptid, cur);
-                else store_chunk_regs<NWT, BF16, G1F16>(p, c, R, Rpad, ahi, ahi + a_half, ptid, cur);
+                if (interior) store_chunk_interior<GT, BF16, G1F16>(p, c, npc, Rpad, ahi, ahi + a_half, gtid, cur);
+                else store_chunk_regs<GT, BF16, G1F16>(p, c, R, Rpad, ahi, ahi + a_half, gtid, cur);
                 fence_proxy_async();    // make the generic-proxy stores visible to the tensor core
-                mbar_arrive(&sm->a_full[buf]);
+                warp_arrive(&sm->a_full[buf]);
                 if (probe) { pw_x += clock64() - tq; if (c < 16) g_tc_trace[3][c] = clock64(); }
                 if (!(p.dbg & 2)) cur = nxt;
             }
         } else {
-            for (int c = 0; c < nchunk; ++c) {
-                const int buf = c & 1;
+            for (int c = grp; c < nchunk; c += NG) {
+                const int buf = c % NBUF;
                 long long tq = probe ? clock64() : 0;
-                mbar_wait(&sm->a_empty[buf], ((c >> 1) & 1) ^ 1);
+                mbar_wait(&sm->a_empty[buf], ((c / NBUF) & 1) ^ 1);
                 if (probe) { long long t1 = clock64(); pw_e += t1 - tq; tq = t1; }
                 uint8_t* ahi = a_base + (size_t)buf * a_slot;
-                if (interior) produce_chunk_interior<NWT, BF16, G1F16>(p, isrc + c * kChunk, pstride, c, R, Rpad, ahi, ahi + a_half, ptid);
-                else produce_chunk<NWT, BF16, 4, false, false, G1F16>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, ptid);
+                if (interior) produce_chunk_interior<GT, BF16, G1F16>(p, isrc + c * kChunk, pstride, c, R, Rpad, ahi, ahi + a_half, gtid);
+                else produce_chunk<GT, BF16, 4, false, false, G1F16>(p, pm, xb, c, t0, R, Rpad, ahi, ahi + a_half, gtid);
                 fence_proxy_async();
-                mbar_arrive(&sm->a_full[buf]);
+                warp_arrive(&sm->a_full[buf]);
                 if (probe) pw_x += clock64() - tq;
             }
         }
@@ -937,12 +952,16 @@ bool tc_conv_plan(TcConvParams& p) {
         MT = MT >= 4 ? 4 : (MT >= 2 ? 2 : MT);
         if (p.fused && MT > 2) MT = 2;
         if (MT >= 1) MT = trim_mt(MT);
-        for (; MT >= 1; MT >>= 1) {
+        // a tile that owns the SM (one CTA resident) runs 16 worker warps in two producer groups over a 4-deep operand ring
+        // (bf16-class kernels only); if that does not fit, 8 workers and 2 buffers
+        const bool want_wide = pass == 1 && g_tc_wide_ok && p.bf16 && (N % 32) == 0;
+        for (; MT >= 1; MT >>= 1)
+        for (int wide = want_wide ? 1 : 0; wide >= 0; --wide) {
             int R = 128 * MT + (p.Kr - 1) * p.dil, Rpad = R;
             while (Rpad % 8 != 2) ++Rpad;
             int cols = MT * per, pow2 = 32;
             while (pow2 < cols) pow2 <<= 1;
-            size_t a_bytes = (size_t)(p.g1f16 ? 2 : 4) * Rpad * 16 * KG;             // 2 bufs x (hi,lo) [hi only: one fp16 pass]
+            size_t a_bytes = (size_t)(wide ? 2 : 1) * (p.g1f16 ? 2 : 4) * Rpad * 16 * KG;   // 2 (4) bufs x (hi,lo) [hi only: one fp16 pass]
             const size_t tile1 = (size_t)(p.g1f16 ? 1 : 2) * N * 16 * KG, tile2 = (size_t)2 * N * 16 * KG;
             // fused: the whole GEMM-2 operand snake2(D1 + b7) stays resident: nchunk2 chunks of (hi,lo) x KG x R2pad x 16 B
             const int R2pad = 128 * MT + 2;
@@ -985,8 +1004,7 @@ bool tc_conv_plan(TcConvParams& p) {
             p.tpt2 = p.fused ? (int)(b_stage / tile2) : 1;
             if (p.tpt2 < 1) p.tpt2 = 1;
             size_t total = tc::kSmemHdr + a_bytes + S * b_stage + a2_bytes;
-            // a tile that owns the SM (one CTA resident) runs 16 worker warps instead of 8 (bf16-class kernels only)
-            p.wide = (pass == 1 && g_tc_wide_ok && p.bf16 && (N % 32) == 0) ? 1 : 0;
+            p.wide = wide;
             const size_t stage = (size_t)(p.wide ? 16 : 8) * 32 * 36 * 4 + tc::kSmemHdr;   // epilogue transpose stage (one [32][36] float tile per worker warp)
             if (total < stage) total = stage;
             p.MT = MT; p.Rpad = Rpad; p.R2pad = R2pad; p.tmem_cols = pow2; p.stagesB = S; p.smem_bytes = total;

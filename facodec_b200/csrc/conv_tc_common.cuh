@@ -14,7 +14,7 @@ namespace tc {
 constexpr int kThreads = 320;      // warp 0: weights, warp 1: MMA, warps 2..9: activation producers + epilogue
 constexpr int kChunk = 16;        // K elements (channels) per pipeline chunk
 constexpr int kMaxStagesB = 4;
-constexpr int kSmemHdr = 256;     // barriers + TMEM base at the start of dynamic shared memory
+constexpr int kSmemHdr = 384;     // barriers + TMEM base at the start of dynamic shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -513,15 +513,15 @@ __device__ __forceinline__ void epilogue_tile32(const TcConvParams& p, const flo
 struct Smem {
     uint64_t b_full[kMaxStagesB];
     uint64_t b_empty[kMaxStagesB];
-    uint64_t a_full[2];
-    uint64_t a_empty[2];
+    uint64_t a_full[4];            // operand ring: 2 buffers (8 workers) or 4 (16 workers in two producer groups)
+    uint64_t a_empty[4];
     uint64_t acc_full;
     uint64_t acc2_full;
     uint64_t a2_full[16];          // fused: GEMM-2 operand chunk c2 written (256 worker arrivals)
     uint32_t tmem_base;
     uint32_t pad;
 };
-static_assert(sizeof(Smem) <= 256, "Smem header");
+static_assert(sizeof(Smem) <= kSmemHdr, "Smem header");
 
 template <int R>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }

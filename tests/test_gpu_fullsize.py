@@ -126,7 +126,10 @@ def test_attention_long_sequence_kernel_matches_stored_scores(built_lib):
     assert float((t0 - t1).abs().max()) <= 2e-6 * max(1.0, float(t0.abs().max()))
     for a, b in zip(c0, c1):
         assert torch.equal(a, b)
-    assert float(((y0 - y1).double() ** 2).mean().sqrt()) <= 1e-6
+    # the two attention kernels differ by fp32 round-off in `timbre`; downstream of the VQ the k = 7 convs run one fp16 pass
+    # (decoder_conv7_fp16), where a 1e-6 input change re-rounds operands: the waveform moves by the class's own noise
+    # (1.4e-5 RMS against the oracle), so the bound is that noise, not fp32 round-off
+    assert float(((y0 - y1).double() ** 2).mean().sqrt()) <= 3e-5
 
 
 def test_n_c_1_at_4s_vs_oracle(built_lib):
