@@ -422,3 +422,32 @@ def test_transposed_conv_as_conv_causal_and_noncausal(stride, built_lib):
         ref = O.sconvtr1d(x, sd, "c", stride, causal=bool(causal))
         assert ref.shape == y.shape
         assert float((y - ref).abs().max()) <= 1e-5
+
+
+def test_dac_code_file_round_trip(tmp_path):
+    """facodec_b200.codefile (dac/model/base.py:15-54 format) without the reference: round trip, uint16 range check,
+    version check, the [p | c | r] codebook order."""
+    import numpy as np
+    import pytest
+    import torch
+    from facodec_b200 import codefile
+    g = torch.Generator().manual_seed(1)
+    codes = [torch.randint(0, 1024, (3, n, 11), generator=g) for n in (1, 1, 3)]
+    f = codefile.from_forward(codes, original_length=3300)
+    p = f.save(tmp_path / "x.anything")
+    assert p.name == "x.dac"
+    raw = np.load(p, allow_pickle=True)[()]
+    assert raw["codes"].dtype == np.uint16 and raw["codes"].shape == (3, 5, 11)
+    assert set(raw["metadata"]) == {"input_db", "original_length", "sample_rate", "chunk_length", "channels", "padding", "dac_version"}
+    back = codefile.DACFile.load(p)
+    for u, v in zip(codefile.unpack_codes(back.codes, n_c=1), codes):
+        assert torch.equal(u, v)
+    with pytest.raises(ValueError):
+        codefile.from_forward([torch.full((1, 1, 2), 70000)] * 3, 600).save(tmp_path / "big")
+    raw["metadata"]["dac_version"] = "9.9"
+    with open(tmp_path / "bad.dac", "wb") as fh:
+        np.save(fh, raw)
+    with pytest.raises(RuntimeError):
+        codefile.DACFile.load(tmp_path / "bad.dac")
+    with pytest.raises(ValueError):
+        codefile.unpack_codes(back.codes, n_c=2)

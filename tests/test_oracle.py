@@ -234,3 +234,26 @@ def test_dataset_mel_matches_imported_meldataset():
         got = O.dataset_mel(w, synth.hann_window_periodic(1200), fb)
     assert tuple(ref.shape) == (1, 80, 5000 // 300 + 1)
     assert float((got - ref).abs().max()) <= 2e-5
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+def test_dac_code_file_matches_imported_dacfile(tmp_path):
+    """dac/model/base.py:15-54: files written here are byte-identical to the reference class's, and each side loads the
+    other's (codes, every metadata field)."""
+    from facodec_b200 import codefile
+    ref_import.import_reference()
+    from dac.model.base import DACFile as RefFile
+    g = torch.Generator().manual_seed(9)
+    codes = [torch.randint(0, 1024, (2, n, 37), generator=g) for n in (1, 2, 3)]
+    mine = codefile.from_forward(codes, original_length=37 * 300, input_db=torch.tensor([-23.5, -17.25]))
+    ref = RefFile(codes=codefile.pack_codes(codes), chunk_length=37, original_length=37 * 300,
+                  input_db=torch.tensor([-23.5, -17.25]), channels=1, sample_rate=24000, padding=True, dac_version="1.0.0")
+    pa, pb = mine.save(tmp_path / "mine"), ref.save(tmp_path / "ref")
+    assert pa.suffix == ".dac" and open(pa, "rb").read() == open(pb, "rb").read()
+    a, b = RefFile.load(pa), codefile.DACFile.load(pb)
+    for f in (a, b):
+        assert torch.equal(f.codes, codefile.pack_codes(codes))
+        assert (f.chunk_length, f.original_length, f.channels, f.sample_rate, f.padding, f.dac_version) == (37, 11100, 1, 24000, True, "1.0.0")
+        assert np.array_equal(np.asarray(f.input_db), np.array([-23.5, -17.25], np.float32))
+    for u, v in zip(codefile.unpack_codes(b.codes, n_c=2), codes):
+        assert torch.equal(u, v)
