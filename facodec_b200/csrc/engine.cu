@@ -112,6 +112,10 @@ struct fac_handle {
     float* aa_filter = nullptr;
     // dataset-side mel (meldataset.py:29-47: MelSpectrogram with its default sample_rate 16000): own constants, built lazily
     float* mel16_arena = nullptr; ConvW mel16_dft, mel16_dft_tc; size_t mel16_fb = 0;
+    // losses.py:65-89 reconstruction_loss: per scale s = 64 << i the window-folded DFT basis [s][ld] (+ tensor-core blobs)
+    // and the 64-band HTK filterbank [n_fft/2 + 1][64]; built on first use
+    struct LossScale { ConvW dft; size_t fb = 0; int s = 0, nfft = 0, nb = 0, ld = 0; };
+    float* loss_arena = nullptr; LossScale loss_scale[6];
     // optional per-kernel-family timing (fac_profile_*): CUDA events around every launch
     bool profiling = false;
     struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
@@ -1264,6 +1268,7 @@ int fac_destroy(fac_handle* h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->aa_filter) cudaFree(h->aa_filter);
     if (h->mel16_arena) cudaFree(h->mel16_arena);
+    if (h->loss_arena) cudaFree(h->loss_arena);
     for (float* p : h->rvq_arenas) if (p) cudaFree(p);
     for (auto* hs : h->heads) { if (hs->arena) cudaFree(hs->arena); delete hs; }
     for (auto* ss : h->streams) { for (void* p : ss->all) if (p) cudaFree(p); delete ss; }
@@ -1660,6 +1665,102 @@ int fac_dataset_mel(fac_handle* h, const float* wave, int B, int T, float* mel, 
         float* mel_cl = mel_forward(c, wave, B, T, F, &mw);
         c.vq_critical = false;
         if (!c.dry) c.check(launch_transpose(mel_cl, mel, B, F, N_MELS, c.st), "mel16.T");
+    });
+    h->warena = saved;
+    return rc;
+}
+
+// ---- losses.py:65-89 reconstruction_loss (the loss forward of the training step) ----
+// L = 100 * mse(x, G_x) + sum_{s = 64..2048} (l1_s + sqrt(s/2) * l2_s) over 64-band mel spectrograms
+// (torchaudio MelSpectrogram(sample_rate=16000, n_fft=max(s,512), win_length=s, hop_length=s/4, n_mels=64): periodic Hann
+// window of s samples centred in the n_fft frame, centre = True reflect padding, power 2, HTK bands over [0, 8000] Hz).
+// Per scale: frame gather of both signals -> one GEMM against the window-folded DFT basis (fp32-faithful tensor-core class)
+// -> mel_loss_terms_kernel -> fp64 sums in a fixed order.
+int fac_reconstruction_loss(fac_handle* h, const float* x, const float* gx, int B, int T, float* loss, float* terms, void* stream) {
+    if (!h || !x || !gx || !loss || B <= 0 || T <= 0) return FAC_ERR_INVALID;
+    if (T <= 1024) { h->err = "fac_reconstruction_loss: signals must be longer than the largest STFT reflect padding (1024), as torch.stft"; return FAC_ERR_INVALID; }
+    if (B > 32767) { h->err = "fac_reconstruction_loss: B > 32767"; return FAC_ERR_UNSUPPORTED; }
+    cudaSetDevice(h->device);
+    if (!h->loss_arena) {
+        fac_handle tmp;
+        tmp.device = h->device;
+        const int NM = 64;
+        auto hz2mel = [](double f) { return 2595.0 * std::log10(1.0 + f / 700.0); };
+        auto mel2hz = [](double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); };
+        std::vector<double> fpts(NM + 2);
+        for (int i = 0; i < NM + 2; ++i) fpts[i] = mel2hz(hz2mel(0.0) + (hz2mel(8000.0) - hz2mel(0.0)) * i / (NM + 1));
+        try {
+            for (int i = 0; i < 6; ++i) {
+                fac_handle::LossScale& L = h->loss_scale[i];
+                L.s = 64 << i; L.nfft = L.s < 512 ? 512 : L.s; L.nb = L.nfft / 2 + 1;
+                L.ld = (2 * L.nb + 127) / 128 * 128;            // zero columns beyond 2 * nb: whole 128-channel MMA tiles
+                ConvW& d = L.dft;
+                d = ConvW();
+                d.Cin = L.s; d.Cout = L.ld; d.K = 1; d.ldw = L.ld;
+                d.w = pack_alloc(&tmp, (size_t)L.s * L.ld);
+                d.b = pack_alloc(&tmp, L.ld);
+                const int left = (L.nfft - L.s) / 2;
+                for (int n = 0; n < L.s; ++n) {
+                    const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)L.s);       // periodic Hann(s)
+                    for (int k = 0; k < L.nb; ++k) {
+                        const long long ph = ((long long)k * (n + left)) % L.nfft;
+                        const double ang = 2.0 * M_PI * (double)ph / (double)L.nfft;
+                        tmp.pack[d.w + (size_t)n * L.ld + 2 * k] = (float)(w * std::cos(ang));
+                        tmp.pack[d.w + (size_t)n * L.ld + 2 * k + 1] = (float)(-w * std::sin(ang));
+                    }
+                }
+                attach_tc(&tmp, d, 1, true);
+                // torchaudio.functional.melscale_fbanks(n_freqs, 0, 8000, 64, sample_rate=16000, norm=None, "htk")
+                L.fb = pack_alloc(&tmp, (size_t)L.nb * NM);
+                for (int k = 0; k < L.nb; ++k) {
+                    const double f = 8000.0 * k / (L.nb - 1);
+                    for (int m = 0; m < NM; ++m) {
+                        const double down = (f - fpts[m]) / (fpts[m + 1] - fpts[m]), up = (fpts[m + 2] - f) / (fpts[m + 2] - fpts[m + 1]);
+                        tmp.pack[L.fb + (size_t)k * NM + m] = (float)std::max(0.0, std::min(down, up));
+                    }
+                }
+            }
+        } catch (const PackError& e) { h->err = e.msg; return FAC_ERR_STATE; }
+        cudaError_t e = cudaMalloc(&h->loss_arena, (tmp.pack.size() + 64) * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->loss_arena, tmp.pack.data(), tmp.pack.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); h->loss_arena = nullptr; return FAC_ERR_CUDA; }
+    }
+    float* saved = h->warena;
+    h->warena = h->loss_arena;
+    int rc = two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        double* sums = c.alloc<double>(16);
+        const int nblk = 1024;
+        float* part = c.alloc<float>(nblk);
+        if (!c.dry) {
+            c.check(launch_sqdiff_partial(x, gx, (long long)B * T, part, nblk, c.st), "loss.mse");
+            c.check(launch_strided_sum(part, nblk, 1, 1.0 / ((double)B * T), sums, c.st), "loss.mse.sum");
+        }
+        const size_t mark = c.off;                                   // the scales run one after another on one stream:
+        size_t peak = c.off;                                         // they share the scratch above this mark
+        c.vq_critical = true;                                        // fp32-faithful DFT (promoted tensor-core class)
+        for (int i = 0; i < 6; ++i) {
+            c.off = mark;
+            const fac_handle::LossScale& L = c.h->loss_scale[i];
+            const int hop = L.s / 4, F = T / hop + 1;
+            const size_t rows = (size_t)2 * B * F;
+            float* frames = c.alloc<float>(rows * L.s);
+            float* spec = c.alloc<float>(rows * L.ld);
+            float* tr = c.alloc<float>((size_t)B * F * 2);
+            if (!c.dry) {
+                c.check(launch_stft_frames(x, frames, B, T, F, hop, L.s, L.s / 2, c.st), "loss.frames");
+                c.check(launch_stft_frames(gx, frames + (size_t)B * F * L.s, B, T, F, hop, L.s, L.s / 2, c.st), "loss.frames");
+            }
+            run_conv(c, L.dft, frames, spec, 1, (int)rows, (int)rows, ConvOpts(), "loss.dft");
+            if (!c.dry) {
+                c.check(launch_mel_loss_terms(spec, L.ld, L.nb, c.W(L.fb), B, F, 1e-7f, tr, c.st), "loss.mel");
+                c.check(launch_strided_sum(tr, (long long)B * F, 2, 1.0 / ((double)B * F * 64.0), sums + 1 + 2 * i, c.st), "loss.l1");
+                c.check(launch_strided_sum(tr + 1, (long long)B * F, 2, 1.0 / ((double)B * F), sums + 2 + 2 * i, c.st), "loss.l2");
+            }
+            if (c.off > peak) peak = c.off;
+        }
+        c.vq_critical = false;
+        c.off = peak;
+        if (!c.dry) c.check(launch_loss_combine(sums, loss, terms, c.st), "loss.combine");
     });
     h->warena = saved;
     return rc;

@@ -72,4 +72,123 @@ cudaError_t launch_mel_from_spec(const float* spec, int ldspec, const float* fb,
     return cudaGetLastError();
 }
 
+// ---- losses.py:65-89 reconstruction_loss: the per-frame tail of one mel scale ----------------------------------------
+// spec holds the windowed DFT of 2B signals (rows [0, B*F): x, rows [B*F, 2*B*F): G_x), [row][2*bin] = Re, [2*bin+1] = Im.
+// One CTA per (frame, utterance): power spectra of both signals -> 64 HTK mel bands each (torchaudio MelSpectrogram,
+// power = 2) -> this frame's share of  l1 = mean |S_x - S_G|  and of
+// l2 = mean_{b,frame} sqrt(mean_mel (log(|S_x| + eps) - log(|S_G| + eps))^2):   terms[(b*F+f)*2] = sum_mel |dS|,
+// terms[.. + 1] = sqrt(sum_mel dlog^2 / 64).
+constexpr int LOSS_MELS = 64;
+__global__ void __launch_bounds__(128) mel_loss_terms_kernel(const float* __restrict__ spec, int ldspec, int nb,
+                                                             const float* __restrict__ fb, int B, int F, float eps,
+                                                             float* __restrict__ terms) {
+    extern __shared__ float pw[];                    // [2][nb] power spectra
+    __shared__ float mels[2][LOSS_MELS];
+    __shared__ float red[2][2];
+    const int b = blockIdx.y, f = blockIdx.x, tid = threadIdx.x;
+    const float* rx = spec + ((size_t)b * F + f) * ldspec;
+    const float* rg = spec + ((size_t)(B + b) * F + f) * ldspec;
+    for (int i = tid; i < nb; i += blockDim.x) {
+        const float2 cx = *reinterpret_cast<const float2*>(rx + 2 * i), cg = *reinterpret_cast<const float2*>(rg + 2 * i);
+        pw[i] = cx.x * cx.x + cx.y * cx.y;
+        pw[nb + i] = cg.x * cg.x + cg.y * cg.y;
+    }
+    __syncthreads();
+    {
+        const int sig = tid >> 6, m = tid & 63;
+        const float* q = pw + sig * nb;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int i = 0;
+        for (; i + 3 < nb; i += 4) {
+            a0 = fmaf(q[i], __ldg(fb + (size_t)i * LOSS_MELS + m), a0);
+            a1 = fmaf(q[i + 1], __ldg(fb + (size_t)(i + 1) * LOSS_MELS + m), a1);
+            a2 = fmaf(q[i + 2], __ldg(fb + (size_t)(i + 2) * LOSS_MELS + m), a2);
+            a3 = fmaf(q[i + 3], __ldg(fb + (size_t)(i + 3) * LOSS_MELS + m), a3);
+        }
+        for (; i < nb; ++i) a0 = fmaf(q[i], __ldg(fb + (size_t)i * LOSS_MELS + m), a0);
+        mels[sig][m] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    if (tid < LOSS_MELS) {
+        const float sx = mels[0][tid], sg = mels[1][tid];
+        float d1 = fabsf(sx - sg);
+        const float dl = logf(fabsf(sx) + eps) - logf(fabsf(sg) + eps);
+        float d2 = dl * dl;
+        d1 = warp_sum(d1); d2 = warp_sum(d2);
+        if ((tid & 31) == 0) { red[tid >> 5][0] = d1; red[tid >> 5][1] = d2; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        terms[((size_t)b * F + f) * 2] = red[0][0] + red[1][0];
+        terms[((size_t)b * F + f) * 2 + 1] = sqrtf((red[0][1] + red[1][1]) / (float)LOSS_MELS);
+    }
+}
+cudaError_t launch_mel_loss_terms(const float* spec, int ldspec, int nb, const float* fb, int B, int F, float eps, float* terms,
+                                  cudaStream_t st) {
+    if (B <= 0 || F <= 0) return cudaSuccess;
+    if (B > 65535) return cudaErrorInvalidValue;
+    mel_loss_terms_kernel<<<dim3(F, B), 128, (size_t)2 * nb * sizeof(float), st>>>(spec, ldspec, nb, fb, B, F, eps, terms);
+    return cudaGetLastError();
+}
+
+// Deterministic fp64 sums (fixed partition, fixed tree): out[0] = sum of in[i*stride] * scale, i < n -- one CTA.
+__global__ void __launch_bounds__(1024) strided_sum_kernel(const float* __restrict__ in, long long n, int stride, double scale,
+                                                           double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double a = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) a += (double)in[i * stride];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0] * scale;
+}
+cudaError_t launch_strided_sum(const float* in, long long n, int stride, double scale, double* out, cudaStream_t st) {
+    strided_sum_kernel<<<1, 1024, 0, st>>>(in, n, stride, scale, out);
+    return cudaGetLastError();
+}
+
+// squared error of two [n] signals: per-block fp64 partials (fixed partition), then strided_sum over the partials
+__global__ void __launch_bounds__(256) sqdiff_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                                             float* __restrict__ part) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const double d = (double)a[i] - (double)b[i];
+        acc += d * d;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = (float)sh[0];
+}
+cudaError_t launch_sqdiff_partial(const float* a, const float* b, long long n, float* part, int nblocks, cudaStream_t st) {
+    sqdiff_partial_kernel<<<nblocks, 256, 0, st>>>(a, b, n, part);
+    return cudaGetLastError();
+}
+
+// L = 100 * mse + sum_i (l1_i + sqrt(s_i / 2) * l2_i), s_i = 64 << i  (losses.py:65-89, accumulated in fp32 in that order)
+__global__ void loss_combine_kernel(const double* __restrict__ v /* [1 + 2*6]: mse, then (l1, l2) per scale */,
+                                    float* __restrict__ loss, float* __restrict__ terms) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float L = 100.0f * (float)v[0];
+    if (terms) terms[0] = (float)v[0];
+    for (int i = 0; i < 6; ++i) {
+        const float l1 = (float)v[1 + 2 * i], l2 = (float)v[2 + 2 * i];
+        const float alpha = sqrtf((float)(64 << i) * 0.5f);
+        L += l1 + alpha * l2;
+        if (terms) { terms[1 + 2 * i] = l1; terms[2 + 2 * i] = l2; }
+    }
+    loss[0] = L;
+}
+cudaError_t launch_loss_combine(const double* v, float* loss, float* terms, cudaStream_t st) {
+    loss_combine_kernel<<<1, 32, 0, st>>>(v, loss, terms);
+    return cudaGetLastError();
+}
+
 }  // namespace fac

@@ -255,6 +255,15 @@ def synth_state_dicts(seed=0):
     }
 
 
+def synth_loss_pair(batch, n_samples, seed=11):
+    """(x, G_x) for the reconstruction-loss fixtures: x = synth_waves, G_x = 0.7 x + 0.05 n (n from a numpy RandomState:
+    host-independent bits, exact fp32 arithmetic).  Both float32 [batch, 1, n_samples]."""
+    x = synth_waves(batch, n_samples, seed=seed)
+    n = np.random.RandomState(seed + 7).randn(batch, 1, n_samples).astype(np.float32)
+    g = np.float32(0.7) * x.numpy() + np.float32(0.05) * n
+    return x, torch.from_numpy(g.astype(np.float32))
+
+
 def synth_waves(batch, n_samples=4 * SR, seed=114514):
     """PseudoDataset law (meldataset.py:67-68): randn(n)/max|.|, seed from meldataset.py:26;
     utterance i uses the next n_samples draws. Returns float32 [batch, 1, n_samples]."""

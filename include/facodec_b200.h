@@ -141,6 +141,13 @@ int fac_alias_free_act(fac_handle* h, const float* x, int B, int C, int T, int a
  * (log(1e-5 + mel) + 4) / 4.  wave [B,T] (device, T > 1024) -> mel [B,80,T/300+1]. */
 int fac_dataset_mel(fac_handle* h, const float* wave, int B, int T, float* mel, void* stream);
 
+/* Training-side reconstruction loss, forward only: losses.py:65-89 reconstruction_loss(x, G_x) =
+ * 100 * mse(x, G_x) + sum over s in {64, 128, ..., 2048} of (l1_s + sqrt(s/2) * l2_s) between the 64-band mel spectrograms
+ * torchaudio MelSpectrogram(sample_rate=16000, n_fft=max(s,512), win_length=s, hop_length=s/4, n_mels=64) gives for x and G_x:
+ * l1 = mean |S_x - S_G|, l2 = mean over (utterance, frame) of sqrt(mean over bands of (log(|S_x|+1e-7) - log(|S_G|+1e-7))^2).
+ * x, gx [B,T] (device, T > 1024).  loss: 1 float (device).  terms: NULL or 13 floats (device): mse, then (l1, l2) per scale. */
+int fac_reconstruction_loss(fac_handle* h, const float* x, const float* gx, int B, int T, float* loss, float* terms, void* stream);
+
 /* Predictor heads: modules/quantize.py:106-125 CNNLSTM(indim, outdim, head, global_pred) forward (3 ResidualUnits of
  * alias-free SnakeBeta + weight-normed Conv1d k7 (dilation 1, 2, 3, zero padding) / k1, a final alias-free SnakeBeta,
  * `nheads` nn.Linear layers; mean over time first when global_pred).  fac_head_begin returns a head id; feed the reference

@@ -528,3 +528,36 @@ def dataset_mel(wave, window, fb, n_fft=2048, hop=HOP, win_length=1200):
     spec = spec.abs().pow(2.0)
     mel = torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2)
     return (torch.log(1e-5 + mel) - (-4)) / 4
+
+
+# ----------------------------------------------------------------------------
+# losses.py:65-89 reconstruction_loss (training-side loss forward)
+# ----------------------------------------------------------------------------
+def reconstruction_loss(x, G_x, eps=1e-7, return_terms=False):
+    """losses.py:65-89: 100 * mse + sum_{i=6..11} (l1 + sqrt(2^i / 2) * l2) over torchaudio MelSpectrogram(sample_rate=16000,
+    n_fft=max(s, 512), win_length=s, hop_length=s // 4, n_mels=64), restated with torch.stft + the HTK filterbank the
+    transform builds (torchaudio.functional.melscale_fbanks) -- the same ATen calls in the same order."""
+    import torch.nn.functional as F
+    import torchaudio
+    L = 100 * F.mse_loss(x, G_x)
+    terms = [F.mse_loss(x, G_x)]
+    for i in range(6, 12):
+        s = 2 ** i
+        n_fft = max(s, 512)
+        window = torch.hann_window(s, device=x.device)
+        fb = torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, 0.0, 8000.0, 64, 16000, None, "htk").to(x.device)
+
+        def melspec(w):
+            shape = w.shape
+            spec = torch.stft(w.reshape(-1, shape[-1]), n_fft, hop_length=s // 4, win_length=s, window=window, center=True,
+                              pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+            spec = spec.reshape(shape[:-1] + spec.shape[-2:]).abs().pow(2.0)
+            return torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2)
+
+        S_x, S_G_x = melspec(x), melspec(G_x)
+        l1_loss = (S_x - S_G_x).abs().mean()
+        l2_loss = (((torch.log(S_x.abs() + eps) - torch.log(S_G_x.abs() + eps)) ** 2).mean(dim=-2) ** 0.5).mean()
+        alpha = (s / 2) ** 0.5
+        L = L + (l1_loss + alpha * l2_loss)
+        terms += [l1_loss, l2_loss]
+    return (L, torch.stack(terms)) if return_terms else L

@@ -117,8 +117,37 @@ def main_redecoder():
         print(name, {k: v.shape for k, v in out.items()}, os.path.getsize(path) // 1024, "KiB")
 
 
+RECON_LOSS_CASE = dict(B=2, T=4800, seed=11)
+
+
+def main_recon_loss():
+    """tests/golden/recon_loss.npz: losses.py:65-89 reconstruction_loss of the imported reference for one seeded pair, plus
+    its 13 components (mse; l1, l2 per scale) formed with the same torchaudio transforms the reference constructs."""
+    import warnings
+    warnings.simplefilter("ignore")
+    from torchaudio.transforms import MelSpectrogram
+    ref_import.import_reference()
+    import losses as ref_losses
+    c = RECON_LOSS_CASE
+    x, G_x = synth.synth_loss_pair(c["B"], c["T"], c["seed"])
+    with torch.no_grad():
+        loss = ref_losses.reconstruction_loss(x, G_x)
+        terms = [torch.nn.functional.mse_loss(x, G_x)]
+        for i in range(6, 12):
+            s = 2 ** i
+            melspec = MelSpectrogram(sample_rate=16000, n_fft=max(s, 512), win_length=s, hop_length=s // 4, n_mels=64)
+            S_x, S_G = melspec(x), melspec(G_x)
+            terms.append((S_x - S_G).abs().mean())
+            terms.append((((torch.log(S_x.abs() + 1e-7) - torch.log(S_G.abs() + 1e-7)) ** 2).mean(dim=-2) ** 0.5).mean())
+    path = os.path.join(GOLDEN_DIR, "recon_loss.npz")
+    np.savez(path, loss=np.float32(loss), terms=torch.stack(terms).numpy(), B=c["B"], T=c["T"], seed=c["seed"])
+    print("recon_loss", float(loss), [float(t) for t in terms])
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "redecoder":
+    if len(sys.argv) > 1 and sys.argv[1] == "recon_loss":
+        main_recon_loss()
+    elif len(sys.argv) > 1 and sys.argv[1] == "redecoder":
         main_redecoder()
     else:
         main()

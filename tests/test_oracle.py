@@ -11,6 +11,8 @@ from conftest import GOLDEN_CASES, case_inputs, load_golden, state_dicts
 from oracle import facodec_oracle as O
 from oracle import ref_import
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 # Bit-exact in the build container (same CPU, same ATen kernels as when the fixtures were made);
 # on another host CPU oneDNN may pick other kernels, so floats get a tight tolerance there.
 SAME_HOST = ref_import.available()
@@ -257,3 +259,34 @@ def test_dac_code_file_matches_imported_dacfile(tmp_path):
         assert np.array_equal(np.asarray(f.input_db), np.array([-23.5, -17.25], np.float32))
     for u, v in zip(codefile.unpack_codes(b.codes, n_c=2), codes):
         assert torch.equal(u, v)
+
+
+def _loss_signals(B=2, T=4800, seed=11):
+    from facodec_b200 import synth
+    return synth.synth_loss_pair(B, T, seed)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+def test_reconstruction_loss_matches_imported_losses_py():
+    """losses.py:65-89 imported unmodified (torchaudio is installed) against the restatement: same scalar, bit for bit."""
+    import warnings
+    warnings.simplefilter("ignore")
+    ref_import.import_reference()
+    import losses as ref_losses
+    x, G_x = _loss_signals()
+    with torch.no_grad():
+        ref = ref_losses.reconstruction_loss(x, G_x)
+        got = O.reconstruction_loss(x, G_x)
+    assert ref.dim() == 0 and torch.equal(ref, got)
+
+
+def test_reconstruction_loss_golden():
+    """tests/golden/recon_loss.npz: loss + 13 terms the imported reference modules gave for the seeded pair (oracle/make_golden.py)."""
+    import warnings
+    warnings.simplefilter("ignore")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "recon_loss.npz"))
+    x, G_x = _loss_signals(int(gold["B"]), int(gold["T"]), int(gold["seed"]))
+    with torch.no_grad():
+        L, terms = O.reconstruction_loss(x, G_x, return_terms=True)
+    assert abs(float(L) - float(gold["loss"])) <= 2e-6 * abs(float(gold["loss"]))
+    assert np.allclose(terms.numpy(), gold["terms"], rtol=2e-6, atol=0)
