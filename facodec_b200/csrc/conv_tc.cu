@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
                     else load_chunk_regs<GT>(p, pm, xb, c + NG, t0, R, gtid, nxt);
                 }
                 long long tq = probe ? clock64() : 0;
-                mbar_wait(&sm->a_empty[buf], ((c / NBUF) & 1) ^ 1);
+                mbar_wait(&sm->a_empty[buf], ((c / NBUF) & 1) ^ 1);   // polled: a 200 ns parked wait here measured +1 ms/step
                 if (probe) {
                     long long t1 = clock64();
                     pw_e += t1 - tq;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(
             for (int c = grp; c < nchunk; c += NG) {
                 const int buf = c % NBUF;
                 long long tq = probe ? clock64() : 0;
-                mbar_wait(&sm->a_empty[buf], ((c / NBUF) & 1) ^ 1);
+                mbar_wait(&sm->a_empty[buf], ((c / NBUF) & 1) ^ 1);   // polled: a 200 ns parked wait here measured +1 ms/step
                 if (probe) { long long t1 = clock64(); pw_e += t1 - tq; tq = t1; }
                 uint8_t* ahi = a_base + (size_t)buf * a_slot;
                 if (interior) produce_chunk_interior<GT, BF16, G1F16>(p, isrc + c * kChunk, pstride, c, R, Rpad, ahi, ahi + a_half, gtid);

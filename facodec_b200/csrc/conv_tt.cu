@@ -284,13 +284,18 @@ __global__ void __launch_bounds__(tc::kThreadsT, 1) conv_tt_kernel(TcConvParams 
     constexpr uint32_t w_half = (uint32_t)kMT * 16 * KG;    // one hi (or lo) weight tile: 4 KB
     uint8_t* a_base = smem_raw + kSmemHdr;                  // [kABufT bufs][hi|lo][KG][Rpad][16 B]
     uint8_t* w_base = a_base + (size_t)kABufT * 2 * a_half;                  // [S][hi|lo][KG][128][16 B]
-    uint8_t* stg_base = w_base + (size_t)kStagesT * 2 * w_half;   // [kPfT][7][192 threads][16 B] raw fp32 pieces (producers)
+    // PAIR mode (p.pair): a CTA tile is TWO 128-channel weight tiles x NT <= 128 time steps instead of one x 256: the produced
+    // activation operand (the SIMT work that bounds every 1-3 tap layer: Snake + split of NT + halo rows per 16 channels) is
+    // shared by both, i.e. produced Cout/256 times instead of Cout/128 times per time step; a weight-ring stage holds both tiles.
+    const int CT = p.pair ? 2 : 1;
+    const uint32_t w_stage = (uint32_t)CT * 2 * w_half;
+    uint8_t* stg_base = w_base + (size_t)kStagesT * w_stage;   // [kPfT][7][192 threads][16 B] raw fp32 pieces (producers)
     constexpr int S = kStagesT;
     const int P = p.promote_every;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunk = p.nchunk, Kr = p.Kr;
-    const int gx = (p.Tout + NT - 1) / NT, gy = (p.Cout + kMT - 1) / kMT;
+    const int gx = (p.Tout + NT - 1) / NT, gy = ((p.Cout + kMT - 1) / kMT) / CT;   // gy: channel tiles (pairs of tiles in PAIR mode)
     const int ntiles = gx * gy * p.B;                       // L -> (channel tile, time tile, batch), channel tile fastest
     const int G = (nchunk + P - 1) / P;
 
@@ -317,13 +322,16 @@ __global__ void __launch_bounds__(tc::kThreadsT, 1) conv_tt_kernel(TcConvParams 
         if (lane == 0) {
             int it = 0;
             for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
-                const int ntile = L % gy;
-                const float* wsrc = p.wblob + (size_t)ntile * nchunk * Kr * (size_t)(2 * w_half / 4);
+                const int ntile = (L % gy) * CT;
+                const size_t tile_floats = (size_t)nchunk * Kr * (size_t)(2 * w_half / 4);
+                const float* wsrc = p.wblob + (size_t)ntile * tile_floats;
                 for (int j = 0; j < nchunk * Kr; ++j, ++it) {
                     const int s = it % S;
                     mbar_wait_park<200>(&sm->b_empty[s], ((it / S) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&sm->b_full[s], 2 * w_half);
-                    bulk_g2s(w_base + (size_t)s * 2 * w_half, wsrc + (size_t)j * (2 * w_half / 4), 2 * w_half, &sm->b_full[s]);
+                    mbar_arrive_expect_tx(&sm->b_full[s], w_stage);
+                    for (int ct = 0; ct < CT; ++ct)
+                        bulk_g2s(w_base + (size_t)s * w_stage + (size_t)ct * 2 * w_half, wsrc + (size_t)ct * tile_floats + (size_t)j * (2 * w_half / 4),
+                                 2 * w_half, &sm->b_full[s]);
                 }
             }
         }
@@ -361,13 +369,16 @@ __global__ void __launch_bounds__(tc::kThreadsT, 1) conv_tt_kernel(TcConvParams 
                         mbar_wait(&sm->b_full[s], (it / S) & 1);
                         if (mprobe) w_b += clock64() - tq;
                         tc_fence_after();
-                        const uint32_t w_hi = w_base16 + (uint32_t)s * 2 * w_half16;
-                        const uint32_t w_lo = w_hi + w_half16;
                         const uint32_t row_off = (uint32_t)(tap * p.dil);
                         const uint32_t first0 = ((c - c_begin) | tap) != 0, first1 = (g | (c - c_begin) | tap) != 0;
-                        umma_bf16(d0, desc_u(w_hi, w_lbo16), desc_u(x_hi + row_off, a_lbo16), idesc, first0);
-                        umma_bf16(d1, desc_u(w_hi, w_lbo16), desc_u(x_lo + row_off, a_lbo16), idesc, first1);
-                        umma_bf16(d1, desc_u(w_lo, w_lbo16), desc_u(x_hi + row_off, a_lbo16), idesc, 1u);
+                        for (int ct = 0; ct < CT; ++ct) {
+                            const uint32_t w_hi = w_base16 + (uint32_t)s * (w_stage >> 4) + (uint32_t)ct * 2 * w_half16;
+                            const uint32_t w_lo = w_hi + w_half16;
+                            const uint32_t dc = (uint32_t)ct * 128u;
+                            umma_bf16(d0 + dc, desc_u(w_hi, w_lbo16), desc_u(x_hi + row_off, a_lbo16), idesc, first0);
+                            umma_bf16(d1 + dc, desc_u(w_hi, w_lbo16), desc_u(x_lo + row_off, a_lbo16), idesc, first1);
+                            umma_bf16(d1 + dc, desc_u(w_lo, w_lbo16), desc_u(x_hi + row_off, a_lbo16), idesc, 1u);
+                        }
                         umma_commit(&sm->b_empty[s]);
                     }
                     umma_commit(&sm->a_empty[buf]);
@@ -435,14 +446,16 @@ __global__ void __launch_bounds__(tc::kThreadsT, 1) conv_tt_kernel(TcConvParams 
         const int half = warp >> 2;                                 // time half of the tile
         int split = ((NT / 2 + 15) / 16) * 16;
         if (split > NT) split = NT;
-        const int mycol0 = half ? split : 0;
-        const int mycols = half ? NT - split : split;               // <= 128
+        // PAIR mode: warp (q, half) owns channel tile `half` of the pair and all NT <= 128 time steps (TMEM columns half * 128 ..)
+        const int mycol0 = CT == 2 ? half * 128 : (half ? split : 0);        // first TMEM column of this warp
+        const int mytime0 = CT == 2 ? 0 : mycol0;                            // first time step of this warp inside the tile
+        const int mycols = CT == 2 ? NT : (half ? NT - split : split);      // <= 128
         const int act = p.out_act;
         int gg = 0;
         const bool aprobe = PROBE && blockIdx.x == 3 && tid == 0;
         long long w_ar = 0, t_dr = 0, t_ep = 0, tq = 0;
         for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
-            const int ntile = L % gy;
+            const int ntile = (L % gy) * CT + (CT == 2 ? half : 0);
             const int t0 = ((L / gy) % gx) * NT;
             const int b = L / (gx * gy);
             const int co = ntile * kMT + q * 32 + lane;
@@ -491,7 +504,7 @@ __global__ void __launch_bounds__(tc::kThreadsT, 1) conv_tt_kernel(TcConvParams 
                 if (p.bias) bi = __ldg(p.bias + co);
                 if (act == ACT_SNAKE) { al = __ldg(p.out_alpha + co); ia = __ldg(p.out_inv_alpha + co); }
             }
-            const int tbeg = t0 + mycol0;
+            const int tbeg = t0 + mytime0;
             const uint32_t ldy = (uint32_t)p.ldy;
 #pragma unroll 1
             for (int sl = 0; sl * 8 < mycols; ++sl) {
@@ -530,6 +543,8 @@ __global__ void __launch_bounds__(tc::kThreadsT, 1) conv_tt_kernel(TcConvParams 
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+int g_tt_pair_ok = 1;   // fac_set_option "tt_pair": 0 = never plan PAIR-mode tiles (A/B aid, process-wide)
+
 bool tt_conv_plan(TcConvParams& p) {
     // p.Cin, p.vf, p.Kr, p.dil, p.Cout (and p.Tout when known) must be set
     if ((p.Cin % 4) != 0 || ((p.Cin * p.vf) % tc::kChunk) != 0 || p.Cout < 1) return false;
@@ -545,6 +560,19 @@ bool tt_conv_plan(TcConvParams& p) {
         for (int cand = 240; cand >= 128; cand -= 16)
             if (padded(cand) * 10 < best * 9) { best = padded(cand); NT = cand; }
     }
+    // PAIR mode for the producer-bound short-tap layers (1x1 convs, 2-tap down convs, input projections, k = 3 conv_out)
+    // with an even number of 128-channel tiles: two weight tiles share one produced operand of NT <= 128 time steps
+    const int ntile_co = (p.Cout + tc::kMT - 1) / tc::kMT;
+    p.pair = (g_tt_pair_ok && p.Kr <= 3 && ntile_co >= 2 && ntile_co % 2 == 0) ? 1 : 0;
+    if (p.pair) {
+        NT = 128;
+        if (p.Tout > 0) {
+            auto padded = [&](int nt) { return (long long)((p.Tout + nt - 1) / nt) * nt; };
+            long long best = padded(128);
+            for (int cand = 112; cand >= 64; cand -= 16)
+                if (padded(cand) * 10 < best * 9) { best = padded(cand); NT = cand; }
+        }
+    }
     p.NT = NT;
     p.promote_every = 48 / p.Kr < 1 ? 1 : 48 / p.Kr;
     int R = NT + (p.Kr - 1) * p.dil, Rpad = R;
@@ -552,7 +580,7 @@ bool tt_conv_plan(TcConvParams& p) {
     p.Rpad = Rpad;
     p.tmem_cols = 512;
     p.stagesB = tc::kStagesT;
-    const size_t a_bytes = (size_t)tc::kABufT * 2 * Rpad * 16 * 2, w_bytes = (size_t)tc::kStagesT * 2 * tc::kMT * 16 * 2;
+    const size_t a_bytes = (size_t)tc::kABufT * 2 * Rpad * 16 * 2, w_bytes = (size_t)(p.pair ? 2 : 1) * tc::kStagesT * 2 * tc::kMT * 16 * 2;
     p.smem_bytes = tc::kSmemHdr + a_bytes + w_bytes + (size_t)tc::kPfT * 7 * tc::kProdT * 16;
     return p.smem_bytes <= 225 * 1024;
 }
@@ -618,7 +646,7 @@ cudaError_t launch_conv_tt(const TcConvParams& p, cudaStream_t st) {
         }
         sm_count = d.sm_count;
     }
-    const long long gx = (p.Tout + p.NT - 1) / p.NT, gy = (p.Cout + tc::kMT - 1) / tc::kMT;
+    const long long gx = (p.Tout + p.NT - 1) / p.NT, gy = ((p.Cout + tc::kMT - 1) / tc::kMT) / (p.pair ? 2 : 1);
     const long long ntiles = gx * gy * p.B;
     if (ntiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned nctas = (unsigned)(ntiles < sm_count ? ntiles : sm_count);

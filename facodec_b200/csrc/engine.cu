@@ -2074,6 +2074,7 @@ int fac_set_option(fac_handle* h, const char* name, int value) {
     if (std::string(name) == "fuse_resunit") { h->fuse_res = value < 0 ? 0 : (value > 2 ? 2 : value); return FAC_OK; }
     if (std::string(name) == "tc_dbg") { g_tc_dbg = value; return FAC_OK; }
     if (std::string(name) == "tc_slot_issue") { g_tc_slot_issue = value != 0; return FAC_OK; }
+    if (std::string(name) == "tt_pair") { g_tt_pair_ok = value != 0; return FAC_OK; }
     if (std::string(name) == "tc_wide") { g_tc_wide_ok = value != 0; return FAC_OK; }
     if (std::string(name) == "tc_occ2_maxn") { h->tc_occ2 = value < 0 ? 0 : value; return FAC_OK; }
     if (std::string(name) == "encoder_f16x2") { h->enc_f16 = value != 0; return FAC_OK; }
@@ -2274,7 +2275,8 @@ int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, i
     if (mode == 6) {
         tp.promoted = 0; tp.bf16 = 0; tp.f16x2 = 0; tp.fused = 0;
         if (!tt_conv_plan(tp)) return FAC_ERR_UNSUPPORTED;
-        out8[0] = tp.N; out8[1] = tp.NT; out8[2] = tp.nchunk; out8[3] = tp.stagesB; out8[4] = tp.tmem_cols;
+        out8[0] = tp.N * (tp.pair ? 2 : 1);   // output channels per CTA tile: 128, or 256 in PAIR mode (two weight tiles)
+        out8[1] = tp.NT; out8[2] = tp.nchunk; out8[3] = tp.stagesB; out8[4] = tp.tmem_cols;
         out8[5] = (int)tp.smem_bytes; out8[6] = tp.Rpad; out8[7] = tp.promote_every;
         return FAC_OK;
     }

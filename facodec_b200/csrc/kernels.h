@@ -49,6 +49,7 @@ struct TcConvParams {
     int f16x2 = 0;                     // promoted only: fp16 hi + 2^11-scaled fp16 lo split (kind::f16, K = 16) instead of tf32 hi/lo
     int tt = 0;                        // 1 = conv_tt_kernel: transposed formulation (weights = MMA A operand, M = 128 output
                                        // channels; time = N = NT <= 256), fp16 hi + scaled-lo split, promoted (tt_conv_plan)
+    int pair = 0;                      // tt (plan): 1 = PAIR mode, a CTA tile is two 128-channel weight tiles x NT <= 128 time steps
     int NT = 0;                        // tt: time steps per tile
     int snake_mufu = 0;                // tt, EXPERIMENT: Snake via the SFU sine (abs error ~4e-7 instead of 2.5e-7)
     int fused = 0;                     // 1 = whole ResidualUnit: conv7 -> +b7 -> Snake -> 1x1 conv -> +b1 -> +x
@@ -81,6 +82,7 @@ cudaError_t launch_conv_tt(const TcConvParams& p, cudaStream_t st);
 extern int g_tc_dbg;
 extern int g_tc_slot_issue;
 extern int g_tc_wide_ok;                             // conv_tc.cu: 0 = never plan 16-worker tiles (A/B aid)
+extern int g_tt_pair_ok;                             // conv_tt.cu: 0 = never plan PAIR-mode tiles
 extern int g_tt_probe_on;                            // 1 = launch the probing variant (process-wide test aid)
 cudaError_t tt_read_probe(long long* out8);
 cudaError_t tc_read_trace(long long* out80);          // per-chunk timeline of the probe CTA (conv_tc.cu g_tc_trace)

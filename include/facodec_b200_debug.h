@@ -65,7 +65,8 @@ long long fac_debug_lstm_pack(const float* whh_host, int H, int bf16, float* out
 int fac_debug_pad_map(int L, int pad_left, int pad_right, int reflect, int* out, int n);
 /* Host-only (no GPU, no handle): the tile plan of the tcgen05 conv kernels for one layer geometry.  mode: 0 conv_tc TF32,
  * 1 conv_tcp (promoted) TF32, 2 conv_tc bf16, 3 conv_tcp fp16 hi + scaled lo, 4 fused ResidualUnit bf16, 5 fused TF32,
- * 6 conv_tt (transposed: out8[0] = 128 output channels per tile, out8[1] = time steps per tile).
+ * 6 conv_tt (transposed: out8[0] = output channels per CTA tile -- 128, or 256 in PAIR mode where two weight tiles share one
+ * produced operand --, out8[1] = time steps per tile).
  * Tout may be 0 (unknown).  out8 = {N, MT, K chunks, weight-ring stages, TMEM columns, dynamic shared-memory bytes,
  * padded rows of the operand buffer, chunks per promotion}.  FAC_ERR_UNSUPPORTED when the layer is not eligible. */
 int fac_debug_tc_plan(int Cin, int Cout, int K, int dil, int stride, int Tout, int mode, int occ2_maxn, int* out8);

@@ -19,14 +19,22 @@ def run(n=5):
     for _ in range(n): out = codec.forward(x, n_c=2)
     b.record(); torch.cuda.synchronize()
     return out, a.elapsed_time(b) / n
+DEFAULTS = {"encoder_tt": 1, "lstm_v2": 1, "decoder_lstm_fp16": 1, "overlap_front": 1, "fuse_resunit": 1, "decoder_bf16": 1, "tc_occ2_maxn": 256,
+            "tensor_cores": 2, "decoder_conv7_fp16": 1, "tc_wide": 1, "tc_slot_issue": 1, "tt_pair": 1}
 (y0, c0, t0), ms0 = run()
 print(f"default: {ms0:.2f} ms/step")
 for spec in sys.argv[1:]:
     kv = [s.split("=") for s in spec.split(",") if s]
-    for k, v in kv: eng.set_option(k, int(v))
-    (y, c, t), ms = run()
+    # interleaved rounds (spec, default, spec, default, ...): run-to-run drift inside one process is ~0.5 ms
+    ms_s, ms_d = [], []
+    for r in range(3):
+        for k, v in kv: eng.set_option(k, int(v))
+        (y, c, t), ms = run(8)
+        ms_s.append(ms)
+        for k, v in kv: eng.set_option(k, DEFAULTS.get(k, 0))
+        ms_d.append(run(8)[1])
     diff = sum(int((a != b).sum()) for a, b in zip(c, c0))
     rms = float(((y.double() - y0.double()) ** 2).mean().sqrt())
-    print(f"{spec}: {ms:.2f} ms/step; codes differing from default {diff}; waveform rms diff {rms:.2e}")
-    DEFAULTS = {"encoder_tt": 1, "lstm_v2": 1, "decoder_lstm_fp16": 1, "overlap_front": 1, "fuse_resunit": 1, "decoder_bf16": 1, "tc_occ2_maxn": 256, "tensor_cores": 2, "decoder_conv7_fp16": 1}
-    for k, v in kv: eng.set_option(k, DEFAULTS.get(k, 0))
+    med = lambda v: sorted(v)[len(v) // 2]
+    print(f"{spec}: {med(ms_s):.2f} ms/step (rounds {' '.join(f'{m:.2f}' for m in ms_s)}) vs default {med(ms_d):.2f} ({' '.join(f'{m:.2f}' for m in ms_d)}); "
+          f"codes differing from default {diff}; waveform rms diff {rms:.2e}")

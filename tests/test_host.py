@@ -329,10 +329,15 @@ def test_transposed_kernel_weight_blob(geom, built_lib):
     assert L.fac_debug_tc_pack(P(w), Cin, Cout, K, stride, 4, P(blob), n) == n
     out = (ctypes.c_int * 8)()
     assert L.fac_debug_tc_plan(Cin, Cout, K, 1, stride, 96000, 6, 0, out) == 0
-    assert out[0] == 128 and out[1] == 256 and out[4] == 512 and out[5] <= 225 * 1024 and out[7] * (K if stride == 1 else 2) <= 48
-    assert L.fac_debug_tc_plan(Cin, Cout, K, 1, stride, 320, 6, 0, out) == 0 and out[1] == 160      # T' = 320: two full tiles
-    nchunk = out[2]
     Kr, vf = (K, 1) if stride == 1 else (2, stride)
+    # PAIR mode (two 128-channel weight tiles share one produced operand of <= 128 time steps) for short-tap layers with an
+    # even number of channel tiles; everything else: one tile x 256 time steps
+    pair = Kr <= 3 and ((Cout + 127) // 128) % 2 == 0
+    assert out[0] == (256 if pair else 128) and out[1] == (128 if pair else 256) and out[4] == 512 and out[5] <= 225 * 1024
+    assert out[7] * Kr <= 48
+    assert L.fac_debug_tc_plan(Cin, Cout, K, 1, stride, 320, 6, 0, out) == 0
+    assert out[1] == (112 if pair else 160)      # T' = 320: three tiles of 112 / two full tiles of 160
+    nchunk = out[2]
     Wg = np.zeros((Kr, vf * Cin, Cout), np.float32)
     for k in range(K):
         Wg[k // vf, (k % vf) * Cin:(k % vf + 1) * Cin, :] = w[:, :, k].T
