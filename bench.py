@@ -229,6 +229,82 @@ def vq_bench(args, rank, local_rank, world):
     return 0
 
 
+def trainfwd_bench(args, rank, local_rank, world):
+    """BASELINE configs[4], the part of it this repo builds: the training step's FORWARD (encoder -> quantizer n_c=2 ->
+    decoder, train.py:265-272, eval-mode arithmetic) plus the forward of the reference's own reconstruction loss
+    (losses.py:65-89) between input and reconstruction, fp32-faithful, 8 utterances x 4 s per GPU (batch 64 on 8 GPUs).
+    No backward, no discriminators, no audiotools losses.  Parity: the loss value of the first
+    timed batch against the CPU oracle fed with the GPU's reconstruction."""
+    import torch
+    import torch.distributed as dist
+    import facodec_b200 as fb
+    from facodec_b200 import distributed as D
+    from facodec_b200 import losses, synth
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = 8
+    sds = synth.synth_state_dicts(0) if rank == 0 else None
+    if world > 1:
+        sds = D.broadcast_state_dicts(sds, 0, dev)
+    model = fb.build_model()
+    for k in ("encoder", "quantizer", "decoder"):
+        model[k].load_state_dict(sds[k]); model[k].eval()
+    codec = fb.Codec(model)
+    xs = [synth.synth_waves(B, UTT_SAMPLES, seed=1000 + 17 * rank + i).to(dev) for i in range(4)]
+
+    def step(x):
+        y, _, _ = codec.forward(x, n_c=2)
+        return y, losses.reconstruction_loss(x, y)
+
+    for i in range(max(3, args.warmup)):
+        step(xs[i % 4])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(args.steps):
+        y, L = step(xs[i % 4])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        dist.barrier()
+        ms = D.max_over_ranks(ms, dev)
+    # loss-only timing (device events) and parity on rank 0
+    a.record()
+    for i in range(args.steps):
+        losses.reconstruction_loss(xs[i % 4], y)
+    b.record()
+    torch.cuda.synchronize()
+    ms_loss = a.elapsed_time(b) / args.steps
+    if rank == 0:
+        from oracle import facodec_oracle as O
+        torch.set_num_threads(usable_cores())
+        x0 = xs[(args.steps - 1) % 4]
+        with torch.no_grad():
+            Lo = float(O.reconstruction_loss(x0.cpu(), y.cpu()))
+        value = world * B * UTT_SECONDS * args.steps / (ms * 1e-3)
+        print(json.dumps({"metric": "train-step forward + reconstruction loss, 24 kHz audio-seconds per second", "value": value, "unit": UNIT,
+                          "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32 I/O; 3-MMA split products (see the codec line); loss sums in fp64", "data": "synthetic",
+                          "config": {"workload": "BASELINE configs[4], forward half only: codec forward (train.py:265-272, eval arithmetic) + "
+                                                 "losses.reconstruction_loss forward (losses.py:65-89), 8 x 4 s utterances per GPU; no backward, "
+                                                 "no discriminator, no audiotools losses",
+                                     "l2": "inputs rotate over 4 distinct batches; the loss alone streams ~1.5 GB of scratch per step"},
+                          "loss_ms_per_step": ms_loss,
+                          "parity": {"loss_gpu": float(L), "loss_oracle_cpu": Lo, "rel_err": abs(float(L) - Lo) / abs(Lo)},
+                          "gpu_launches": (codec.launch_count() + 60) * args.steps}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -237,8 +313,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
-    ap.add_argument("--workload", default="codec", choices=["codec", "vq"],
-                    help="codec = BASELINE configs[1] (the headline); vq = configs[3] FVQ/RVQ codebook-distance microbench")
+    ap.add_argument("--workload", default="codec", choices=["codec", "vq", "trainfwd"],
+                    help="codec = BASELINE configs[1] (the headline); vq = configs[3] FVQ/RVQ codebook-distance microbench; "
+                         "trainfwd = the forward half of configs[4] (codec forward + losses.reconstruction_loss)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,6 +329,8 @@ def main():
 
     if args.workload == "vq":
         return vq_bench(args, rank, local_rank, world)
+    if args.workload == "trainfwd":
+        return trainfwd_bench(args, rank, local_rank, world)
 
     if args.impl == "reference":
         if rank != 0:

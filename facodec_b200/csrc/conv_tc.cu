@@ -175,17 +175,19 @@ __device__ __forceinline__ void a2_phase(const TcConvParams& p, tc::Smem* sm, ui
 // NW = worker warps (producers, then GEMM-2 operand, then epilogue): 8 for tiles planned for two CTAs per SM; 16 for tiles
 // that own a whole SM (fused C = 192: D1 + D2 = 384 TMEM columns) -- with one CTA of 8 workers an SM had 2 warps per
 // scheduler and every SIMT phase ran latency-bound while the MMA warp starved (profiles/r02 phase clocks).
-template <bool FUSED, bool BF16, bool G1F16 = false, int NW = 8>
+template <bool FUSED, bool BF16, bool G1F16 = false, int NW = 8, int NG = (NW == 16 ? 2 : 1)>
 __global__ void __launch_bounds__(64 + 32 * NW, NW == 8 ? 2 : 1) conv_tc_kernel(TcConvParams p) {
     static_assert(!G1F16 || BF16, "the one-pass fp16 class shares the 16-bit operand layout");
     static_assert(NW == 8 || NW == 16, "worker warps");
     using namespace tc;
     constexpr int NWT = NW * 32;                            // worker threads
     constexpr int NSUB = NW / 4;                            // worker warps per TMEM lane quarter
-    // 16 workers produce as TWO groups of 8 warps on alternate chunks into a 4-deep operand ring: a group's chunk is one
+    // NG = 2: the workers produce as TWO groups on alternate chunks into a 4-deep operand ring: a group's chunk is one
     // dependent chain (loads -> Snake -> split -> stores -> proxy fence -> arrive, ~1.5 k cycles whatever the thread count),
-    // so two chunks in flight is what shortens the K loop, not more threads per chunk.
-    constexpr int NG = NW == 16 ? 2 : 1;
+    // so two chunks in flight is what shortens the K loop, not more threads per chunk.  Always with 16 workers; with 8
+    // workers when a group of 4 warps covers a chunk in <= PIPE_P pieces per thread (128-row tiles of 1- and 2-tap layers
+    // and of the k = 7 convs with dilation 1 / 3).
+    static_assert(NG == 1 || NG == 2, "producer groups");
     constexpr int NBUF = 2 * NG;
     constexpr int GT = NWT / NG;                            // producer threads per group
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -890,11 +892,12 @@ __global__ void __launch_bounds__(tc::kThreadsP, 1) conv_tcp_kernel(TcConvParams
 
 // ---- host side ---------------------------------------------------------------------------------
 int g_tc_dbg = 0;       // fac_set_option "tc_dbg": timing experiments with WRONG results (bit 0: stale weights, bit 1: stale activations)
+int g_tc_groups_ok = 1; // fac_set_option "tc_groups": 0 = one producer group on 8-worker tiles (A/B aid, process-wide)
 int g_tc_wide_ok = 1;
 int g_tc_slot_issue = 1;   // fac_set_option "tc_slot_issue": 0 = legacy per-tap weight-ring bookkeeping in the MMA warp (A/B aid)   // fac_set_option "tc_wide": 0 plans every conv_tc tile with 8 worker warps (A/B aid, process-wide)
 
 bool tc_conv_plan(TcConvParams& p) {
-    p.wide = 0;
+    p.wide = 0; p.ng = 1;
     p.cps = 0;
     // p.Cin, p.vf, p.Kr, p.dil, p.Cout, p.promoted must be set; fills N, MT, nchunk, Rpad, stagesB, ...
     if ((p.Cin % 4) != 0 || ((p.Cin * p.vf) % tc::kChunk) != 0 || (p.Cout % 16) != 0) return false;
@@ -956,12 +959,17 @@ bool tc_conv_plan(TcConvParams& p) {
         // (bf16-class kernels only); if that does not fit, 8 workers and 2 buffers
         const bool want_wide = pass == 1 && g_tc_wide_ok && p.bf16 && (N % 32) == 0;
         for (; MT >= 1; MT >>= 1)
-        for (int wide = want_wide ? 1 : 0; wide >= 0; --wide) {
+        for (int wide = want_wide ? 1 : 0; wide >= 0; --wide)
+        for (int ng = 2; ng >= 1; --ng) {
             int R = 128 * MT + (p.Kr - 1) * p.dil, Rpad = R;
             while (Rpad % 8 != 2) ++Rpad;
+            // producer groups: 16 workers always run two; 8 workers when a 4-warp group covers a chunk in <= PIPE_P (5)
+            // pieces per thread (R <= 160 rows), bf16-class kernels only
+            if (wide && ng == 1) continue;
+            if (!wide && ng == 2 && !(g_tc_groups_ok && p.bf16 && R <= 5 * 32)) continue;
             int cols = MT * per, pow2 = 32;
             while (pow2 < cols) pow2 <<= 1;
-            size_t a_bytes = (size_t)(wide ? 2 : 1) * (p.g1f16 ? 2 : 4) * Rpad * 16 * KG;   // 2 (4) bufs x (hi,lo) [hi only: one fp16 pass]
+            size_t a_bytes = (size_t)ng * (p.g1f16 ? 2 : 4) * Rpad * 16 * KG;   // 2 (4) bufs x (hi,lo) [hi only: one fp16 pass]
             const size_t tile1 = (size_t)(p.g1f16 ? 1 : 2) * N * 16 * KG, tile2 = (size_t)2 * N * 16 * KG;
             // fused: the whole GEMM-2 operand snake2(D1 + b7) stays resident: nchunk2 chunks of (hi,lo) x KG x R2pad x 16 B
             const int R2pad = 128 * MT + 2;
@@ -1004,7 +1012,7 @@ bool tc_conv_plan(TcConvParams& p) {
             p.tpt2 = p.fused ? (int)(b_stage / tile2) : 1;
             if (p.tpt2 < 1) p.tpt2 = 1;
             size_t total = tc::kSmemHdr + a_bytes + S * b_stage + a2_bytes;
-            p.wide = wide;
+            p.wide = wide; p.ng = ng;
             const size_t stage = (size_t)(p.wide ? 16 : 8) * 32 * 36 * 4 + tc::kSmemHdr;   // epilogue transpose stage (one [32][36] float tile per worker warp)
             if (total < stage) total = stage;
             p.MT = MT; p.Rpad = Rpad; p.R2pad = R2pad; p.tmem_cols = pow2; p.stagesB = S; p.smem_bytes = total;
@@ -1150,6 +1158,10 @@ cudaError_t ensure_device_config(int& sm_count) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true, false, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true, false, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true, true, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, true, true, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         if (e != cudaSuccess) return e;
@@ -1182,6 +1194,11 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, cudaStream_t st) {
         else if (p.wide && p.g1f16) conv_tc_kernel<false, true, true, 16><<<grid, kThreadsW, p.smem_bytes, st>>>(p);
         else if (p.wide && p.fused) conv_tc_kernel<true, true, false, 16><<<grid, kThreadsW, p.smem_bytes, st>>>(p);
         else if (p.wide) conv_tc_kernel<false, true, false, 16><<<grid, kThreadsW, p.smem_bytes, st>>>(p);
+        else if (p.ng == 2 && !p.bf16) return cudaErrorInvalidValue;
+        else if (p.ng == 2 && p.fused && p.g1f16) conv_tc_kernel<true, true, true, 8, 2><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        else if (p.ng == 2 && p.g1f16) conv_tc_kernel<false, true, true, 8, 2><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        else if (p.ng == 2 && p.fused) conv_tc_kernel<true, true, false, 8, 2><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
+        else if (p.ng == 2) conv_tc_kernel<false, true, false, 8, 2><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.fused && p.bf16 && p.g1f16) conv_tc_kernel<true, true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.bf16 && p.g1f16) conv_tc_kernel<false, true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);
         else if (p.fused && p.bf16) conv_tc_kernel<true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p);

@@ -2075,6 +2075,7 @@ int fac_set_option(fac_handle* h, const char* name, int value) {
     if (std::string(name) == "tc_dbg") { g_tc_dbg = value; return FAC_OK; }
     if (std::string(name) == "tc_slot_issue") { g_tc_slot_issue = value != 0; return FAC_OK; }
     if (std::string(name) == "tt_pair") { g_tt_pair_ok = value != 0; return FAC_OK; }
+    if (std::string(name) == "tc_groups") { g_tc_groups_ok = value != 0; return FAC_OK; }
     if (std::string(name) == "tc_wide") { g_tc_wide_ok = value != 0; return FAC_OK; }
     if (std::string(name) == "tc_occ2_maxn") { h->tc_occ2 = value < 0 ? 0 : value; return FAC_OK; }
     if (std::string(name) == "encoder_f16x2") { h->enc_f16 = value != 0; return FAC_OK; }

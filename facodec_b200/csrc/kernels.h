@@ -67,6 +67,7 @@ struct TcConvParams {
     int b_slot = 0;                    // bytes of one weight-ring slot
     int R2pad = 0;                     // fused: row pitch (rows) of the resident GEMM-2 operand chunks
     int dbg = 0;                       // conv_tc_kernel timing experiments (g_tc_dbg); results are wrong when non-zero
+    int ng = 1;                        // conv_tc_kernel: producer groups (2 = alternate chunks over a 4-deep operand ring)
     int wide = 0;                      // conv_tc_kernel: 1 = 16 worker warps (tile planned for one CTA per SM), 0 = 8
     size_t smem_bytes = 0;
     size_t x_bstride = 0, y_bstride = 0;
@@ -81,6 +82,7 @@ void tt_pack_blob(const TcConvParams& p, const float* wp, int ldw, float* blob);
 cudaError_t launch_conv_tt(const TcConvParams& p, cudaStream_t st);
 extern int g_tc_dbg;
 extern int g_tc_slot_issue;
+extern int g_tc_groups_ok;
 extern int g_tc_wide_ok;                             // conv_tc.cu: 0 = never plan 16-worker tiles (A/B aid)
 extern int g_tt_pair_ok;                             // conv_tt.cu: 0 = never plan PAIR-mode tiles
 extern int g_tt_probe_on;                            // 1 = launch the probing variant (process-wide test aid)

@@ -20,7 +20,7 @@ def run(n=5):
     b.record(); torch.cuda.synchronize()
     return out, a.elapsed_time(b) / n
 DEFAULTS = {"encoder_tt": 1, "lstm_v2": 1, "decoder_lstm_fp16": 1, "overlap_front": 1, "fuse_resunit": 1, "decoder_bf16": 1, "tc_occ2_maxn": 256,
-            "tensor_cores": 2, "decoder_conv7_fp16": 1, "tc_wide": 1, "tc_slot_issue": 1, "tt_pair": 1}
+            "tensor_cores": 2, "decoder_conv7_fp16": 1, "tc_wide": 1, "tc_slot_issue": 1, "tt_pair": 1, "tc_groups": 1}
 (y0, c0, t0), ms0 = run()
 print(f"default: {ms0:.2f} ms/step")
 for spec in sys.argv[1:]:
