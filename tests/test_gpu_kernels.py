@@ -144,6 +144,8 @@ TC_CASES = [
     (1, 640, 1024, 4096, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0),   # LSTM input projection geometry
     (2, 320, 256, 512, 5, 1, 1, 4, 0, 1, 0, 0, 0, 0),     # WN in_layer geometry, T' = 320 (time tile 160 in the transposed kernel)
     (1, 1000, 128, 128, 7, 3, 1, 18, 0, 1, 1, 1, 0, 1),   # several time tiles + residual + both Snakes
+    (2, 700, 256, 256, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1),     # encoder 1x1 + residual: conv_tt PAIR mode (two channel tiles x 128 steps), ragged tail
+    (1, 1000, 64, 512, 3, 1, 1, 2, 0, 1, 1, 1, 0, 0),     # 3 taps, 4 channel tiles (two pairs), both Snakes, several time tiles
 ]
 
 
