@@ -108,6 +108,26 @@ def test_live_oracle_new_seed(built_lib):
     assert rms(y, yo) <= RMS_TOL
 
 
+@pytest.mark.parametrize("B,T,n_c", [(35, 4500, 2), (1, 1030, 2), (2, 2999, 1), (3, 12345, 2)])
+def test_live_oracle_odd_shapes(B, T, n_c, built_lib):
+    """Shapes the fixtures do not hold, against the oracle run on this box's CPU: more than 32 utterances (the LSTM takes 32
+    sequences per launch), the shortest length the quantizer's centred STFT accepts (+ ragged), lengths that are not
+    multiples of the 300-sample hop or of any tile size."""
+    from facodec_b200 import synth
+    from oracle import facodec_oracle as O
+    sds = state_dicts(0)
+    m = model_for(0)
+    x = synth.synth_waves(B, T, seed=1000 + B + T)
+    torch.set_num_threads(max(1, min(16, len(__import__("os").sched_getaffinity(0)))))
+    zo, qo, yo = O.codec_forward(sds, x, n_c=n_c)
+    z, q, y = run_model(m, x, n_c, {})
+    assert z.shape == zo.shape and y.shape == yo.shape
+    assert (z.cpu() - zo).abs().max() <= Z_RTOL * zo.abs().max()
+    for a, b in zip(q[5], qo[5]):
+        assert torch.equal(a.cpu(), b), f"{int((a.cpu() != b).sum())} of {b.numel()} indices differ"
+    assert rms(y, yo) <= RMS_TOL
+
+
 def test_fused_codec_forward_equals_three_calls(built_lib):
     import facodec_b200 as fb
     from facodec_b200 import synth
