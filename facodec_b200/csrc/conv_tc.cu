@@ -121,32 +121,82 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
 }
+// wait for two TMEM loads in flight (tcgen05.wait::ld covers every outstanding load of the thread; both register sets are
+// named so that no read of either can move above the wait)
+template <int CW>
+__device__ __forceinline__ void tmem_ldw_wait2(uint32_t (&a)[CW], uint32_t (&b)[CW]) {
+    static_assert(CW == 4 || CW == 8, "paired wait");
+    if constexpr (CW == 4) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]) :: "memory");
+    } else {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                       "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]) :: "memory");
+    }
+}
+// one chunk's share of this warp: + b7, Snake, hi/lo split, K-major stores
+template <int CW, bool BF16>
+__device__ __forceinline__ void a2_transform(const TcConvParams& p, const uint32_t (&v)[CW], int c2, int arow, int pc0, int Rpad2,
+                                             uint8_t* a2_base, uint32_t a2_half) {
+    using namespace tc;
+    uint8_t* ahi = a2_base + (size_t)c2 * 2 * a2_half;
+    uint8_t* alo = ahi + a2_half;
+#pragma unroll
+    for (int pp = 0; pp < CW / 4; ++pp) {
+        const int pc = pc0 + pp;
+        const int co = c2 * 16 + pc * 4;
+        float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+        float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
+        float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
+        float4 x4 = make_float4(__uint_as_float(v[pp * 4 + 0]) + bi.x, __uint_as_float(v[pp * 4 + 1]) + bi.y,
+                                __uint_as_float(v[pp * 4 + 2]) + bi.z, __uint_as_float(v[pp * 4 + 3]) + bi.w);
+        x4 = snake4_sel<BF16>(x4, al, ia);
+        split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
+    }
+}
 template <int CW, bool BF16>
 __device__ __forceinline__ void a2_phase(const TcConvParams& p, tc::Smem* sm, uint32_t taddr0, int arow, int pc0,
                                          uint8_t* a2_base, uint32_t a2_half) {
     using namespace tc;
     const int Rpad2 = p.R2pad;
+    if constexpr (CW <= 8) {
+        // Two chunks per step when the warp's share is small (4 / 8 columns): a chunk is one dependent chain (TMEM load ->
+        // Snake -> split -> stores -> proxy fence -> arrive), so pairing them halves the fence / arrive round trips.
+        if ((p.nchunk2 & 1) == 0 && !(p.dbg & 8)) {
+            uint32_t v0[CW], v1[CW], n0[CW], n1[CW];
+            tmem_ldw_issue<CW>(taddr0, v0);
+            tmem_ldw_issue<CW>(taddr0 + 16u, v1);
+            tmem_ldw_wait2<CW>(v0, v1);
+#pragma unroll 1
+            for (int c2 = 0; c2 < p.nchunk2; c2 += 2) {
+                const bool more = c2 + 2 < p.nchunk2;
+                if (more) {
+                    tmem_ldw_issue<CW>(taddr0 + (uint32_t)((c2 + 2) * 16), n0);
+                    tmem_ldw_issue<CW>(taddr0 + (uint32_t)((c2 + 3) * 16), n1);
+                }
+                a2_transform<CW, BF16>(p, v0, c2, arow, pc0, Rpad2, a2_base, a2_half);
+                a2_transform<CW, BF16>(p, v1, c2 + 1, arow, pc0, Rpad2, a2_base, a2_half);
+                fence_proxy_async();
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) { mbar_arrive(&sm->a2_full[c2]); mbar_arrive(&sm->a2_full[c2 + 1]); }
+                if (more) {
+                    tmem_ldw_wait2<CW>(n0, n1);
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) { v0[i] = n0[i]; v1[i] = n1[i]; }
+                }
+            }
+            return;
+        }
+    }
     uint32_t v[CW], vn[CW];
     tmem_ldw_issue<CW>(taddr0, v);
     tmem_ldw_wait<CW>(v);
 #pragma unroll 1
     for (int c2 = 0; c2 < p.nchunk2; ++c2) {
-        uint8_t* ahi = a2_base + (size_t)c2 * 2 * a2_half;
-        uint8_t* alo = ahi + a2_half;
         const bool more = c2 + 1 < p.nchunk2;
         if (more) tmem_ldw_issue<CW>(taddr0 + (uint32_t)((c2 + 1) * 16), vn);
-#pragma unroll
-        for (int pp = 0; pp < CW / 4; ++pp) {
-            const int pc = pc0 + pp;
-            const int co = c2 * 16 + pc * 4;
-            float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-            float4 al = __ldg(reinterpret_cast<const float4*>(p.out_alpha + co));
-            float4 ia = __ldg(reinterpret_cast<const float4*>(p.out_inv_alpha + co));
-            float4 x4 = make_float4(__uint_as_float(v[pp * 4 + 0]) + bi.x, __uint_as_float(v[pp * 4 + 1]) + bi.y,
-                                    __uint_as_float(v[pp * 4 + 2]) + bi.z, __uint_as_float(v[pp * 4 + 3]) + bi.w);
-            x4 = snake4_sel<BF16>(x4, al, ia);
-            split_store<BF16>(x4, pc, arow, Rpad2, ahi, alo);
-        }
+        a2_transform<CW, BF16>(p, v, c2, arow, pc0, Rpad2, a2_base, a2_half);
         fence_proxy_async();
         warp_arrive(&sm->a2_full[c2]);
         if (more) {
