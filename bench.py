@@ -487,6 +487,12 @@ def main():
     latency = {"workload": "BASELINE configs[0]: single 4 s 24 kHz utterance, full codec forward, 1 GPU",
                "ms_device_resident": ms_b1, "ms_e2e_host_buffers": ms_b1_e2e,
                "audio_s_per_s": UTT_SECONDS / (ms_b1 * 1e-3), "launches": codec.launch_count()}
+    try:    # the same forward replayed from one CUDA graph (Codec.forward_graphed)
+        for _ in range(2):
+            codec.forward_graphed(x1, n_c=2)
+        latency["ms_cuda_graph_replay"] = timed(lambda i: codec.forward_graphed(x1, n_c=2), nlat) / nlat
+    except Exception as exc:   # report, do not hide: the eager numbers above stand on their own
+        latency["cuda_graph_error"] = str(exc).splitlines()[0][:200]
 
     # ---- library baseline (rank 0, N=1 only): the reference's own ATen call sequence under PyTorch eager on THIS GPU ----
     library = None

@@ -351,6 +351,29 @@ class Codec:
         _lib.check(e.handle, rc, "fac_codec_forward_host")
         return y, [cp, cc, cr]
 
+    def forward_graphed(self, x, n_c=2):
+        """The same call replayed from a CUDA graph (one graph per (B, T, n_c, device), captured on first use after one
+        eager call has sized the workspace): for latency-bound shapes (B = 1: 115 launches, two of them cooperative LSTM
+        layers, plus the forked quantizer front) the launches leave the host in one go.  Returns the graph's OWN output
+        tensors: they are overwritten by the next replay of the same shape -- clone what must survive."""
+        x = _f32c(x)
+        key = (tuple(x.shape), int(n_c), x.device.index)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        ent = self._graphs.get(key)
+        if ent is None:
+            self.forward(x, n_c)                                  # sizes the workspace, creates the side stream (not capturable)
+            torch.cuda.synchronize(x.device)
+            sx = x.clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.forward(sx, n_c)
+            ent = self._graphs[key] = (g, sx, out, self.launch_count())
+        g, sx, out, _ = ent
+        sx.copy_(x)
+        g.replay()
+        return out
+
     def launch_count(self):
         return self.engine.L.fac_last_launch_count(self.engine.handle)
 

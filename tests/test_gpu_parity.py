@@ -148,6 +148,26 @@ def test_fused_codec_forward_equals_three_calls(built_lib):
     assert codec.launch_count() > 50
 
 
+def test_cuda_graph_replay_equals_eager(built_lib):
+    """Codec.forward_graphed: the whole forward (cooperative LSTM launches, the forked quantizer front) captured once and
+    replayed -- same bits as the eager call, also for a second input of the same shape and after another shape was used."""
+    import facodec_b200 as fb
+    from facodec_b200 import synth
+    m = model_for(0)
+    codec = fb.Codec(m)
+    xa = synth.synth_waves(1, 24000, seed=21).cuda()
+    xb = synth.synth_waves(1, 24000, seed=22).cuda()
+    xc = synth.synth_waves(2, 6000, seed=23).cuda()
+    for x in (xa, xc, xb, xa):
+        y, codes, timbre = codec.forward(x, n_c=2)
+        yg, codes_g, timbre_g = codec.forward_graphed(x, n_c=2)
+        torch.cuda.synchronize()
+        assert torch.equal(y, yg) and torch.equal(timbre, timbre_g)
+        for a, b in zip(codes, codes_g):
+            assert torch.equal(a, b)
+    assert len(codec._graphs) == 2
+
+
 def test_full_size_properties(built_lib):
     """BASELINE configs[1]: B=32 x 4 s.  (1) utterance 0 == golden b1_t96000 (same PseudoDataset
     stream); (2) batch invariance: an utterance decodes to the same bits alone or inside the batch;
