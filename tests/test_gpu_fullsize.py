@@ -85,6 +85,28 @@ def test_all_32_utterances_of_configs1_vs_oracle(built_lib):
     print(f"FULLSIZE B=32: 61440/61440 indices equal, waveform RMS max {float(r.max()):.3e} mean {float(r.mean()):.3e}")
 
 
+@pytest.mark.parametrize("seed", [3, 11])
+def test_other_weight_sets_at_4s(seed, built_lib):
+    """The benchmark geometry with OTHER synthetic checkpoints (weight seeds 3 and 11; every fixture and the B = 32 test use
+    seed 0 / 1): 8 utterances x 4 s, all 15 360 indices against the oracle, per-utterance RMS <= 1e-4."""
+    import facodec_b200 as fb
+    from facodec_b200 import synth
+    m, sds = _model(seed)
+    codec = fb.Codec(m)
+    x = synth.synth_waves(8, 96000, seed=500 + seed)
+    y, codes, _ = codec.forward(x.cuda(), n_c=2)
+    torch.cuda.synchronize()
+    ocodes, oy = _oracle_chunks(sds, x, 2, 4)
+    total = 0
+    for name, a, b in zip(("codes_p", "codes_c", "codes_r"), codes, ocodes):
+        nbad = int((a.cpu() != b).sum())
+        assert nbad == 0, f"seed {seed} {name}: {nbad} of {b.numel()} indices differ from the oracle"
+        total += b.numel()
+    assert total == 15360
+    r = _rms_per_utt(y, oy)
+    assert float(r.max()) <= RMS_TOL, f"per-utterance waveform RMS {r.tolist()}"
+
+
 def test_b1_30s_reference_inference_shape(built_lib):
     """reconstruct.py:52 crops to 30 s: B = 1 x 720 000 samples, 2400 frames (long-sequence attention path)."""
     import facodec_b200 as fb
