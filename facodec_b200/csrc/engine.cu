@@ -1793,6 +1793,13 @@ int fac_head_finalize(fac_handle* h, int head_id, int indim, int outdim, int nhe
     tmp.host[0] = hs.staged;
     hs.indim = indim; hs.outdim = outdim; hs.nheads = nheads; hs.global_pred = global_pred;
     try {
+        if (global_pred == 2) {
+            // kind "linear": a plain nn.Linear(indim, outdim) staged as linear.weight [outdim][indim] / linear.bias
+            // (FApredictors.timbre_predictor under timbre_norm, modules/quantize.py:470-473)
+            if (nheads != 1) throw PackError{"a linear head has exactly one output"};
+            hs.lin[0] = pack_conv(&tmp, 0, "linear");
+            if (hs.lin[0].Cin != indim || hs.lin[0].Cout != outdim) throw PackError{"Linear geometry"};
+        } else {
         auto expv = [&](const std::string& key) {
             const HostTensor& t = need(&tmp, 0, key);
             if ((int)t.numel() != indim) throw PackError{"shape of " + key};
@@ -1815,6 +1822,7 @@ int fac_head_finalize(fac_handle* h, int head_id, int indim, int outdim, int nhe
         for (int i = 0; i < nheads; ++i) {
             hs.lin[i] = pack_conv(&tmp, 0, "heads." + std::to_string(i));
             if (hs.lin[i].Cin != indim || hs.lin[i].Cout != outdim) throw PackError{"head Linear geometry"};
+        }
         }
     } catch (const PackError& e) {
         h->err = e.msg;
@@ -1842,6 +1850,14 @@ int fac_head_forward(fac_handle* h, int head_id, const float* x, int B, int T, f
     float* saved = h->warena;
     h->warena = hs.arena;
     const int C = hs.indim;
+    if (hs.global_pred == 2) {
+        // kind "linear": x [B*T rows][indim] -> outs[0] [B*T][outdim]
+        rc = two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+            run_conv(c, hs.lin[0], x, outs[0], 1, B * T, B * T, ConvOpts(), "head.linear");
+        });
+        h->warena = saved;
+        return rc;
+    }
     rc = two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
         const size_t n = (size_t)B * T * C;
         float* a_nct = c.alloc<float>(n);
@@ -1890,6 +1906,16 @@ int fac_head_forward(fac_handle* h, int head_id, const float* x, int B, int T, f
     });
     h->warena = saved;
     return rc;
+}
+
+// out = a + b (+ c): the latent sums FApredictors.forward_v2 feeds its reversal heads (modules/quantize.py:571-586), in the
+// reference's left-to-right order
+int fac_add3(fac_handle* h, const float* a, const float* b, const float* c3, long long n, float* out, void* stream) {
+    if (!h || !a || !b || !out || n <= 0) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaError_t e = launch_add3(a, b, c3, n, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) { h->err = std::string("CUDA error at add3: ") + cudaGetErrorString(e); return FAC_ERR_CUDA; }
+    return FAC_OK;
 }
 
 int fac_rvq_create(fac_handle* h, int nq, const float* const* in_w, const float* const* in_b, const float* const* out_w,

@@ -191,4 +191,19 @@ cudaError_t launch_loss_combine(const double* v, float* loss, float* terms, cuda
     return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                                   long long n, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        float v = a[i] + b[i];
+        if (c) v += c[i];
+        out[i] = v;
+    }
+}
+cudaError_t launch_add3(const float* a, const float* b, const float* c, long long n, float* out, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    add3_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, b, c, n, out);
+    return cudaGetLastError();
+}
+
 }  // namespace fac

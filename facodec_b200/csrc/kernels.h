@@ -173,6 +173,7 @@ cudaError_t launch_mel_loss_terms(const float* spec, int ldspec, int nb, const f
                                   float* terms /*[B*F][2]*/, cudaStream_t st);
 cudaError_t launch_strided_sum(const float* in, long long n, int stride, double scale, double* out, cudaStream_t st);
 cudaError_t launch_sqdiff_partial(const float* a, const float* b, long long n, float* part, int nblocks, cudaStream_t st);
+cudaError_t launch_add3(const float* a, const float* b, const float* c /* or null */, long long n, float* out, cudaStream_t st);
 cudaError_t launch_loss_combine(const double* v13, float* loss, float* terms, cudaStream_t st);
 cudaError_t launch_transpose(const float* in, float* out, int B, int R, int C, cudaStream_t st);  // [B][R][C]->[B][C][R]
 // tanh(a + g_a) * sigmoid(b + g_b); g = null or one [2*hidden] conditioning row per utterance (rows_per_utt rows each, g_stride floats apart)

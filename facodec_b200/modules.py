@@ -457,10 +457,178 @@ class VoiceConverter:
         return y
 
 
-def build_model(args=None, stage="codec"):
+class _HeadLinear(nn.Module):
+    """A plain nn.Linear(indim, outdim) run through the head machinery (kind "linear" of fac_head_finalize)."""
+
+    def __init__(self, indim, outdim, seed=0, engine=None):
+        super().__init__()
+        self.indim, self.outdim = int(indim), int(outdim)
+        g = synth._Gen(900 + seed)
+        b = 1.0 / (indim ** 0.5)
+        self.weight = nn.Parameter(g.uniform((outdim, indim), b), requires_grad=False)
+        self.bias = nn.Parameter(g.uniform((outdim,), b), requires_grad=False)
+        self._engine = engine if engine is not None else Engine()
+        self._head_id = None
+        self._tag = None
+
+    def _sync(self, device):
+        e = self._engine
+        e._ensure(device)
+        tag = (self.weight._version, self.bias._version)
+        if self._tag == tag:
+            return
+        L, h = e.L, e.handle
+        if self._head_id is None:
+            self._head_id = _lib.check(h, L.fac_head_begin(h), "fac_head_begin")
+        for k, p in (("linear.weight", self.weight), ("linear.bias", self.bias)):
+            t = p.detach().to("cpu", torch.float32).contiguous()
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            _lib.check(h, L.fac_head_tensor(h, self._head_id, k.encode(), _ptr(t), shape, t.dim()), "fac_head_tensor(%s)" % k)
+        _lib.check(h, L.fac_head_finalize(h, self._head_id, self.indim, self.outdim, 1, 2), "fac_head_finalize")
+        self._tag = tag
+
+    def forward(self, x):
+        self._sync(x.device)
+        e = self._engine
+        x = _f32c(x)
+        rows = x.numel() // self.indim
+        out = torch.empty(tuple(x.shape[:-1]) + (self.outdim,), device=x.device)
+        arr = (ctypes.c_void_p * 1)(out.data_ptr())
+        _lib.check(e.handle, e.L.fac_head_forward(e.handle, self._head_id, _ptr(x), rows, 1, arr, _stream(x.device)), "fac_head_forward")
+        return out
+
+
+class FApredictors(nn.Module):
+    """modules/quantize.py:456-619 FApredictors, forward only (training-side in the reference; the GradientReversal layers are
+    identities in the forward pass): the f0 / phone / timbre predictors and their reversal counterparts over the quantizer's
+    latents -- CNNLSTM heads (fac_head_*), one nn.Linear (timbre_predictor under timbre_norm) and the latent sums
+    (fac_add3).  Same constructor flags, same state_dict keys (``rev_*_predictor.1.*`` for the heads inside nn.Sequential),
+    same ``(preds, rev_preds)`` dicts; ``forward`` is ``forward_v2(quantized, timbre)`` when ``timbre_norm`` (config.yml),
+    else the 4-latent ``forward(quantized)``."""
+
+    def __init__(self, in_dim=1024, use_gr_content_f0=False, use_gr_prosody_phone=False, use_gr_residual_f0=False,
+                 use_gr_residual_phone=False, use_gr_timbre_content=True, use_gr_timbre_prosody=True, use_gr_x_timbre=False,
+                 norm_f0=True, timbre_norm=False, use_gr_content_global_f0=False, n_speakers=20000, engine=None):
+        super().__init__()
+        eng = engine if engine is not None else Engine()
+        self._engine = eng
+        self.in_dim = int(in_dim)
+        self.flags = dict(use_gr_content_f0=use_gr_content_f0, use_gr_prosody_phone=use_gr_prosody_phone,
+                          use_gr_residual_f0=use_gr_residual_f0, use_gr_residual_phone=use_gr_residual_phone,
+                          use_gr_timbre_content=use_gr_timbre_content, use_gr_timbre_prosody=use_gr_timbre_prosody,
+                          use_gr_x_timbre=use_gr_x_timbre, norm_f0=norm_f0, timbre_norm=timbre_norm)
+        parts = OrderedDict()
+        parts["f0_predictor"] = CNNLSTM(in_dim, 1, 2, seed=1, engine=eng)
+        parts["phone_predictor"] = CNNLSTM(in_dim, 1024, 1, seed=2, engine=eng)
+        parts["timbre_predictor"] = (_HeadLinear(in_dim, n_speakers, seed=3, engine=eng) if timbre_norm
+                                     else CNNLSTM(in_dim, n_speakers, 1, global_pred=True, seed=3, engine=eng))
+        parts["rev_f0_predictor.1"] = CNNLSTM(in_dim, 1, 2, seed=4, engine=eng)
+        parts["rev_content_predictor.1"] = CNNLSTM(in_dim, 1024, 1, seed=5, engine=eng)
+        parts["rev_timbre_predictor.1"] = CNNLSTM(in_dim, n_speakers, 1, global_pred=True, seed=6, engine=eng)
+        if timbre_norm:
+            parts["global_f0_predictor"] = _HeadLinear(in_dim, 1, seed=7, engine=eng)           # built, unused by forward (as in the reference)
+        if use_gr_content_global_f0:
+            parts["rev_global_f0_predictor.1"] = CNNLSTM(in_dim, 1, 1, global_pred=True, seed=8, engine=eng)
+        self._parts = parts
+        self._mods = nn.ModuleList(list(parts.values()))
+        if timbre_norm:
+            self.forward = self.forward_v2
+
+    # ---- reference state_dict surface ----
+    def state_dict(self, *a, prefix="", **kw):
+        out = OrderedDict()
+        for name, m in self._parts.items():
+            if isinstance(m, _HeadLinear):
+                out[prefix + name + ".weight"] = m.weight.detach()
+                out[prefix + name + ".bias"] = m.bias.detach()
+            else:
+                out.update(m.state_dict(prefix=prefix + name + "."))
+        return out
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        for name, m in self._parts.items():
+            sub = {k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")}
+            if isinstance(m, _HeadLinear):
+                if strict and ("weight" not in sub or "bias" not in sub):
+                    raise RuntimeError("missing keys: %s.weight / bias" % name)
+                with torch.no_grad():
+                    if "weight" in sub:
+                        m.weight.copy_(sub["weight"])
+                    if "bias" in sub:
+                        m.bias.copy_(sub["bias"])
+            else:
+                m.load_state_dict(sub, strict=strict)
+
+    def _sum(self, terms):
+        """Left-to-right sum of 1-3 latents, as the reference accumulates them into zeros_like()."""
+        if len(terms) == 1:
+            return terms[0]
+        e = self._engine
+        a = [_f32c(t) for t in terms]
+        out = torch.empty_like(a[0])
+        _lib.check(e.handle, e.L.fac_add3(e.handle, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]) if len(a) > 2 else None, a[0].numel(), _ptr(out),
+                                          _stream(out.device)), "fac_add3")
+        return out
+
+    def _check(self, t):
+        if self.training:
+            raise NotImplementedError("eval mode only")
+        if t.device.type != "cuda":
+            raise _lib.FacError("FApredictors runs on CUDA tensors only (no CPU fallback)")
+        self._engine._ensure(t.device)
+
+    def forward_v2(self, quantized, timbre):
+        """modules/quantize.py:564-619: quantized = [prosody, content, residual] latents [B, in_dim, T], timbre [B, in_dim]."""
+        f = self.flags
+        p, c, r = quantized[0], quantized[1], quantized[2]
+        self._check(p)
+        P = self._parts
+        content_pred = P["phone_predictor"](c)[0]
+        spk_pred = P["timbre_predictor"](timbre)
+        f0_pred, uv_pred = P["f0_predictor"](p)
+        pro_terms = ([c] if f["use_gr_content_f0"] else []) + ([r] if f["use_gr_residual_f0"] else [])
+        con_terms = ([p] if f["use_gr_prosody_phone"] else []) + ([r] if f["use_gr_residual_phone"] else [])
+        zeros = None
+        if not pro_terms or not con_terms:
+            zeros = torch.zeros_like(p)
+        rev_f0_pred, rev_uv_pred = P["rev_f0_predictor.1"](self._sum(pro_terms) if pro_terms else zeros)
+        rev_content_pred = P["rev_content_predictor.1"](self._sum(con_terms) if con_terms else zeros)[0]
+        x_spk_pred = P["rev_timbre_predictor.1"](self._sum([p, c, r]))[0] if f["use_gr_x_timbre"] else None
+        preds = {"f0": f0_pred, "uv": uv_pred, "content": content_pred, "timbre": spk_pred}
+        rev_preds = {"rev_f0": rev_f0_pred, "rev_uv": rev_uv_pred, "rev_content": rev_content_pred, "x_timbre": x_spk_pred}
+        return preds, rev_preds
+
+    def forward(self, quantized):
+        """modules/quantize.py:507-563 (timbre_norm = False): quantized = [prosody, content, timbre, residual] latents."""
+        f = self.flags
+        p, c, t, r = quantized[0], quantized[1], quantized[2], quantized[3]
+        self._check(p)
+        P = self._parts
+        content_pred = P["phone_predictor"](c)[0]
+        if f["norm_f0"]:
+            spk_pred = P["timbre_predictor"](t)[0]
+            f0_pred, uv_pred = P["f0_predictor"](p)
+        else:
+            spk_pred = P["timbre_predictor"](self._sum([t, p]))[0]
+            f0_pred, uv_pred = P["f0_predictor"](self._sum([p, t]))
+        pro_terms = ([c] if f["use_gr_content_f0"] else []) + ([t] if f["use_gr_timbre_prosody"] else []) + ([r] if f["use_gr_residual_f0"] else [])
+        con_terms = ([p] if f["use_gr_prosody_phone"] else []) + ([t] if f["use_gr_timbre_content"] else []) + ([r] if f["use_gr_residual_phone"] else [])
+        zeros = torch.zeros_like(p) if (not pro_terms or not con_terms) else None
+        rev_f0_pred, rev_uv_pred = P["rev_f0_predictor.1"](self._sum(pro_terms) if pro_terms else zeros)
+        rev_content_pred = P["rev_content_predictor.1"](self._sum(con_terms) if con_terms else zeros)[0]
+        x_terms = [p, c, r] if f["norm_f0"] else [c, r]
+        x_spk_pred = P["rev_timbre_predictor.1"](self._sum(x_terms))[0] if f["use_gr_x_timbre"] else None
+        preds = {"f0": f0_pred, "uv": uv_pred, "content": content_pred, "timbre": spk_pred}
+        rev_preds = {"rev_f0": rev_f0_pred, "rev_uv": rev_uv_pred, "rev_content": rev_content_pred, "x_timbre": x_spk_pred}
+        return preds, rev_preds
+
+
+def build_model(args=None, stage="codec", with_predictors=False):
     """Mirror of modules/commons.py:283-348 build_model(args, stage='codec') for the hot-path
-    modules: returns Munch(encoder, quantizer, decoder) (discriminator / fa_predictors are training-only
-    and out of scope).  ``args`` may be the reference's recursive_munch(config['model_params']) or None.
+    modules: returns Munch(encoder, quantizer, decoder) (the discriminator is training-only and out of scope).
+    ``with_predictors=True`` adds ``fa_predictors`` (forward only) with the flags of modules/commons.py:311-322; it is
+    opt-in because its two 20 000-way speaker heads are 160 MB of weights no inference call touches.
+    ``args`` may be the reference's recursive_munch(config['model_params']) or None.
     stage='redecoder' returns the voice-conversion model Munch(encoder=Redecoder, decoder=Decoder(non-causal, no LSTM))."""
     if stage == "redecoder":
         # modules/commons.py:385-412: Munch(encoder=Redecoder(args), decoder=Decoder(causal=args.decoder_causal, lstm=args.decoder_lstm))
@@ -493,7 +661,15 @@ def build_model(args=None, stage="codec"):
     decoder = Decoder(input_channel=1024, channels=g(dac, "decoder_dim", 1536),
                       rates=tuple(g(dac, "decoder_rates", (6, 5, 5, 2))), causal=g(args, "causal", True),
                       lstm=g(args, "lstm", 2), engine=eng)
-    return Munch(encoder=encoder, quantizer=quantizer, decoder=decoder)
+    out = Munch(encoder=encoder, quantizer=quantizer, decoder=decoder)
+    if with_predictors:
+        out["fa_predictors"] = FApredictors(in_dim=1024, use_gr_content_f0=g(args, "use_gr_content_f0", False),
+                                            use_gr_prosody_phone=g(args, "use_gr_prosody_phone", False), use_gr_residual_f0=True,
+                                            use_gr_residual_phone=True, use_gr_timbre_content=True,
+                                            use_gr_timbre_prosody=g(args, "use_gr_timbre_prosody", False), use_gr_x_timbre=True,
+                                            norm_f0=g(args, "norm_f0", True), timbre_norm=g(args, "timbre_norm", True),
+                                            use_gr_content_global_f0=g(args, "use_gr_content_global_f0", True), engine=eng)
+    return out
 
 
 class ResidualVQ(nn.Module):
@@ -620,13 +796,13 @@ class CNNLSTM(nn.Module):
     Kaiser-sinc filter buffers of every Activation1d (accepted on load, regenerated on save).  forward(x [B, indim, T]) ->
     list of ``head`` tensors [B, T, outdim] ([B, outdim] when global_pred)."""
 
-    def __init__(self, indim, outdim, head, global_pred=False, seed=0):
+    def __init__(self, indim, outdim, head, global_pred=False, seed=0, engine=None):
         super().__init__()
         self.indim, self.outdim, self.nheads, self.global_pred = int(indim), int(outdim), int(head), bool(global_pred)
         sd = synth.synth_cnnlstm(500 + seed, self.indim, self.outdim, self.nheads)
         self._keys = list(sd.keys())
         self._p = nn.ParameterDict({k.replace(".", "/"): nn.Parameter(v, requires_grad=False) for k, v in sd.items()})
-        self._engine = Engine()
+        self._engine = engine if engine is not None else Engine()
         self._head_id = None
         self._tag = None
 

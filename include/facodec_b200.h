@@ -153,11 +153,17 @@ int fac_reconstruction_loss(fac_handle* h, const float* x, const float* gx, int 
  * `nheads` nn.Linear layers; mean over time first when global_pred).  fac_head_begin returns a head id; feed the reference
  * state_dict tensors (keys "model.0.block.0.act.alpha", "model.0.block.1.weight_g", ..., "heads.0.weight"; the registered
  * filter buffers are ignored) with fac_head_tensor, then fac_head_finalize.  fac_head_forward: x [B,indim,T] (device) ->
- * outs[i] [B,T,outdim] (or [B,outdim] when global_pred), i < nheads, caller-allocated device buffers. */
+ * outs[i] [B,T,outdim] (or [B,outdim] when global_pred), i < nheads, caller-allocated device buffers.
+ * global_pred = 2 makes the head a plain nn.Linear(indim, outdim) (FApredictors.timbre_predictor under timbre_norm,
+ * modules/quantize.py:470-473): stage "linear.weight" [outdim][indim] and "linear.bias", nheads = 1; fac_head_forward then
+ * takes x as [B*T rows][indim] and writes outs[0] [B*T][outdim].
+ * fac_add3: out = a + b (+ c when c is not NULL), n floats on the device: the latent sums FApredictors.forward_v2 feeds
+ * its gradient-reversal heads (modules/quantize.py:571-586). */
 int fac_head_begin(fac_handle* h);
 int fac_head_tensor(fac_handle* h, int head_id, const char* key, const float* data_host, const int64_t* shape, int ndim);
 int fac_head_finalize(fac_handle* h, int head_id, int indim, int outdim, int nheads, int global_pred);
 int fac_head_forward(fac_handle* h, int head_id, const float* x, int B, int T, float* const* outs, void* stream);
+int fac_add3(fac_handle* h, const float* a, const float* b, const float* c, long long n, float* out, void* stream);
 
 /* Engine options.  "tensor_cores": 0 = fp32 FMA kernels everywhere; 1 = tcgen05 3xTF32
  * kernel for every eligible layer downstream of the VQ (decoder, timbre branch), fp32 FMA upstream

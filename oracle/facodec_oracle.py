@@ -514,6 +514,58 @@ def cnnlstm_forward(sd, x, n_heads, global_pred=False):
     return [F.linear(h, sd[f"heads.{i}.weight"], sd[f"heads.{i}.bias"]) for i in range(n_heads)]
 
 
+def fa_predictors_forward(sd, quantized, timbre=None, use_gr_content_f0=False, use_gr_prosody_phone=False,
+                          use_gr_residual_f0=False, use_gr_residual_phone=False, use_gr_timbre_content=True,
+                          use_gr_timbre_prosody=True, use_gr_x_timbre=False, norm_f0=True, timbre_norm=False):
+    """FApredictors.forward (modules/quantize.py:507-563) / forward_v2 (:564-619, when timbre_norm) over the module's
+    state_dict: the GradientReversal layers are identities in the forward pass; the reversal heads sit at index 1 of their
+    nn.Sequential (keys ``rev_*_predictor.1.*``)."""
+    sub = lambda name: {k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")}
+    head = lambda name, x, n, glob=False: cnnlstm_forward(sub(name), x, n, global_pred=glob)
+    if timbre_norm:
+        p, c, r = quantized[0], quantized[1], quantized[2]
+        content_pred = head("phone_predictor", c, 1)[0]
+        spk_pred = F.linear(timbre, sd["timbre_predictor.weight"], sd["timbre_predictor.bias"])
+        f0_pred, uv_pred = head("f0_predictor", p, 2)
+        prosody_rev = torch.zeros_like(p)
+        if use_gr_content_f0:
+            prosody_rev = prosody_rev + c
+        if use_gr_residual_f0:
+            prosody_rev = prosody_rev + r
+        rev_f0_pred, rev_uv_pred = head("rev_f0_predictor.1", prosody_rev, 2)
+        content_rev = torch.zeros_like(c)
+        if use_gr_prosody_phone:
+            content_rev = content_rev + p
+        if use_gr_residual_phone:
+            content_rev = content_rev + r
+        rev_content_pred = head("rev_content_predictor.1", content_rev, 1)[0]
+        timbre_rev = p + c + r
+    else:
+        p, c, t, r = quantized[0], quantized[1], quantized[2], quantized[3]
+        content_pred = head("phone_predictor", c, 1)[0]
+        if norm_f0:
+            spk_pred = head("timbre_predictor", t, 1, True)[0]
+            f0_pred, uv_pred = head("f0_predictor", p, 2)
+        else:
+            spk_pred = head("timbre_predictor", t + p, 1, True)[0]
+            f0_pred, uv_pred = head("f0_predictor", p + t, 2)
+        prosody_rev = torch.zeros_like(p)
+        for flag, lat in ((use_gr_content_f0, c), (use_gr_timbre_prosody, t), (use_gr_residual_f0, r)):
+            if flag:
+                prosody_rev = prosody_rev + lat
+        rev_f0_pred, rev_uv_pred = head("rev_f0_predictor.1", prosody_rev, 2)
+        content_rev = torch.zeros_like(c)
+        for flag, lat in ((use_gr_prosody_phone, p), (use_gr_timbre_content, t), (use_gr_residual_phone, r)):
+            if flag:
+                content_rev = content_rev + lat
+        rev_content_pred = head("rev_content_predictor.1", content_rev, 1)[0]
+        timbre_rev = p + c + r if norm_f0 else c + r
+    x_spk_pred = head("rev_timbre_predictor.1", timbre_rev, 1, True)[0] if use_gr_x_timbre else None
+    preds = {"f0": f0_pred, "uv": uv_pred, "content": content_pred, "timbre": spk_pred}
+    rev_preds = {"rev_f0": rev_f0_pred, "rev_uv": rev_uv_pred, "rev_content": rev_content_pred, "x_timbre": x_spk_pred}
+    return preds, rev_preds
+
+
 # ----------------------------------------------------------------------------
 # meldataset.py:29-47 dataset-side mel (PseudoDataset training targets)
 # ----------------------------------------------------------------------------

@@ -389,6 +389,40 @@ def test_cnnlstm_predictor_heads_vs_oracle(indim, outdim, heads, glob, T, built_
         assert err <= 2e-3 * max(1.0, float(b.abs().max())), f"max err {err}"
 
 
+@pytest.mark.parametrize("timbre_norm", [True, False])
+def test_fa_predictors_vs_oracle(timbre_norm, built_lib):
+    """modules/quantize.py:456-619 FApredictors with build_model's flags (modules/commons.py:311-322), both forward variants,
+    in_dim 64 (the head widths 1 / 1024 / 20000 are the reference's): every prediction against the oracle (pinned to the
+    imported class in test_oracle.py).  Tolerance: decoder-class precision (bf16 hi/lo operands), 2e-3 of the output scale."""
+    import facodec_b200 as fb
+    from oracle import facodec_oracle as O
+    flags = dict(use_gr_content_f0=False, use_gr_prosody_phone=False, use_gr_residual_f0=True, use_gr_residual_phone=True,
+                 use_gr_timbre_content=True, use_gr_timbre_prosody=False, use_gr_x_timbre=True, norm_f0=True)
+    m = fb.FApredictors(in_dim=64, timbre_norm=timbre_norm, use_gr_content_global_f0=True, **flags).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    assert "rev_f0_predictor.1.model.0.block.1.weight_g" in sd and "rev_timbre_predictor.1.heads.0.weight" in sd
+    assert ("timbre_predictor.weight" in sd) == timbre_norm and ("global_f0_predictor.bias" in sd) == timbre_norm
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(8)
+    lat = [torch.randn(2, 64, 41, generator=g) for _ in range(3 if timbre_norm else 4)]
+    timbre = torch.randn(2, 64, generator=g)
+    with torch.no_grad():
+        ref = O.fa_predictors_forward(sd, lat, timbre if timbre_norm else None, timbre_norm=timbre_norm, **flags)
+    if timbre_norm:
+        got = m([t.cuda() for t in lat], timbre.cuda())
+    else:
+        got = m([t.cuda() for t in lat])
+    torch.cuda.synchronize()
+    for a, b in zip(got, ref):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert tuple(a[k].shape) == tuple(b[k].shape), k
+            err = float((a[k].cpu() - b[k]).abs().max())
+            assert err <= 2e-3 * max(1.0, float(b[k].abs().max())), f"{k}: max err {err}"
+    with pytest.raises(fb.FacError):
+        m([t for t in lat], timbre) if timbre_norm else m([t for t in lat])          # CPU tensors: no fallback
+
+
 def test_dataset_mel_vs_oracle(built_lib):
     """meldataset.py:37-47 (16 kHz-default filterbank, centre=True frames) through fac_dataset_mel against the oracle
     restatement (pinned to the imported meldataset module in test_oracle.py).  Log-mel values are O(1): 2e-4 absolute."""

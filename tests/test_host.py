@@ -456,3 +456,26 @@ def test_dac_code_file_round_trip(tmp_path):
         codefile.DACFile.load(tmp_path / "bad.dac")
     with pytest.raises(ValueError):
         codefile.unpack_codes(back.codes, n_c=2)
+
+
+def test_fa_predictors_state_dict_surface():
+    """facodec_b200.FApredictors (modules/quantize.py:456-619) without a GPU: the reference's key set (heads of the reversal
+    predictors at index 1 of their nn.Sequential, the Linear timbre predictor under timbre_norm), load/save round trip,
+    CPU tensors refused."""
+    import pytest
+    import torch
+    import facodec_b200 as fb
+    m = fb.FApredictors(in_dim=32, timbre_norm=True, use_gr_content_global_f0=True, use_gr_residual_f0=True, use_gr_residual_phone=True,
+                        use_gr_x_timbre=True, n_speakers=50).eval()
+    sd = m.state_dict()
+    tops = {k.split(".model.")[0].split(".heads.")[0] for k in sd if ".model." in k or ".heads." in k}
+    assert tops == {"f0_predictor", "phone_predictor", "rev_f0_predictor.1", "rev_content_predictor.1", "rev_timbre_predictor.1",
+                    "rev_global_f0_predictor.1"}
+    assert sd["timbre_predictor.weight"].shape == (50, 32) and sd["global_f0_predictor.weight"].shape == (1, 32)
+    assert sd["f0_predictor.heads.1.weight"].shape == (1, 32) and sd["phone_predictor.heads.0.weight"].shape == (1024, 32)
+    sd2 = {k: v + 1 for k, v in sd.items()}
+    m.load_state_dict(sd2)
+    assert torch.equal(m.state_dict()["timbre_predictor.bias"], sd2["timbre_predictor.bias"])
+    assert torch.equal(m.state_dict()["rev_f0_predictor.1.heads.0.weight"], sd2["rev_f0_predictor.1.heads.0.weight"])
+    with pytest.raises(fb.FacError):
+        m([torch.zeros(1, 32, 5)] * 3, torch.zeros(1, 32))

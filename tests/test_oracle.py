@@ -290,3 +290,42 @@ def test_reconstruction_loss_golden():
         L, terms = O.reconstruction_loss(x, G_x, return_terms=True)
     assert abs(float(L) - float(gold["loss"])) <= 2e-6 * abs(float(gold["loss"]))
     assert np.allclose(terms.numpy(), gold["terms"], rtol=2e-6, atol=0)
+
+
+FAP_FLAGS = dict(use_gr_content_f0=False, use_gr_prosody_phone=False, use_gr_residual_f0=True, use_gr_residual_phone=True,
+                 use_gr_timbre_content=True, use_gr_timbre_prosody=False, use_gr_x_timbre=True, norm_f0=True)   # modules/commons.py:311-322 + config.yml
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+@pytest.mark.parametrize("timbre_norm", [True, False])
+def test_fa_predictors_match_imported_reference(timbre_norm):
+    """FApredictors (modules/quantize.py:456-619) imported unmodified with build_model's flags, both forward variants:
+    the restatement over its state_dict is bit-identical, output by output."""
+    import warnings
+    warnings.simplefilter("ignore")
+    ref_import.import_reference()
+    from modules.quantize import FApredictors
+    torch.manual_seed(4)
+    m = FApredictors(in_dim=32, timbre_norm=timbre_norm, use_gr_content_global_f0=True, **FAP_FLAGS).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    lat = [torch.randn(2, 32, 19, generator=g) for _ in range(3 if timbre_norm else 4)]
+    with torch.no_grad():
+        if timbre_norm:
+            timbre = torch.randn(2, 32, generator=g)
+            ref = m(lat, timbre)
+            got = O.fa_predictors_forward(sd, lat, timbre, timbre_norm=True, **FAP_FLAGS)
+        else:
+            ref = m(lat)
+            got = O.fa_predictors_forward(sd, lat, None, timbre_norm=False, **FAP_FLAGS)
+    for a, b in zip(ref, got):
+        assert a.keys() == b.keys()
+        for k in a:
+            if a[k] is None or b[k] is None:
+                assert a[k] is None and b[k] is None, k
+            elif a[k].shape[-1] == 1:
+                # 1-wide nn.Linear heads (f0 / uv): torch's CPU F.linear takes another kernel for weights that do not require
+                # grad (the oracle works on detached state_dict tensors, the module on Parameters): 1-2 ulp apart
+                assert float((a[k] - b[k]).abs().max()) <= 5e-7 * max(1.0, float(a[k].abs().max())), k
+            else:
+                assert torch.equal(a[k], b[k]), k
