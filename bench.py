@@ -250,14 +250,19 @@ def trainfwd_bench(args, rank, local_rank, world):
     sds = synth.synth_state_dicts(0) if rank == 0 else None
     if world > 1:
         sds = D.broadcast_state_dicts(sds, 0, dev)
-    model = fb.build_model()
+    model = fb.build_model(with_predictors=True)
     for k in ("encoder", "quantizer", "decoder"):
         model[k].load_state_dict(sds[k]); model[k].eval()
+    model.fa_predictors.eval()                      # synthetic default weights (PyTorch-init statistics), identical on every rank
     codec = fb.Codec(model)
     xs = [synth.synth_waves(B, UTT_SAMPLES, seed=1000 + 17 * rank + i).to(dev) for i in range(4)]
 
     def step(x):
-        y, _, _ = codec.forward(x, n_c=2)
+        # train.py:265-272: encoder -> quantizer -> fa_predictors(quantized, timbre) -> decoder, then the loss forward
+        z = model.encoder(x)
+        outs, quantized, commit, cb, timbre = model.quantizer(z, x, n_c=2)
+        model.fa_predictors(quantized, timbre)
+        y = model.decoder(outs)
         return y, losses.reconstruction_loss(x, y)
 
     for i in range(max(3, args.warmup)):
@@ -293,13 +298,13 @@ def trainfwd_bench(args, rank, local_rank, world):
                           "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32 I/O; 3-MMA split products (see the codec line); loss sums in fp64", "data": "synthetic",
-                          "config": {"workload": "BASELINE configs[4], forward half only: codec forward (train.py:265-272, eval arithmetic) + "
-                                                 "losses.reconstruction_loss forward (losses.py:65-89), 8 x 4 s utterances per GPU; no backward, "
-                                                 "no discriminator, no audiotools losses",
+                          "config": {"workload": "BASELINE configs[4], forward half only: encoder -> quantizer -> fa_predictors -> decoder "
+                                                 "(train.py:265-272, eval arithmetic) + losses.reconstruction_loss forward (losses.py:65-89), "
+                                                 "8 x 4 s utterances per GPU; no backward, no discriminator, no audiotools losses",
                                      "l2": "inputs rotate over 4 distinct batches; the loss alone streams ~1.5 GB of scratch per step"},
                           "loss_ms_per_step": ms_loss,
                           "parity": {"loss_gpu": float(L), "loss_oracle_cpu": Lo, "rel_err": abs(float(L) - Lo) / abs(Lo)},
-                          "gpu_launches": (codec.launch_count() + 60) * args.steps}))
+                          "gpu_launches": 400 * args.steps}))
     if world > 1:
         dist.destroy_process_group()
     return 0
