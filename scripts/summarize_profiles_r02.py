@@ -28,8 +28,11 @@ tot = sum(v[1] for v in agg.values())
 out = ["# ncu summary, round 2 (B200, `--clock-control none`)\n",
        f"Sources: `profiles/r02/{LIST}` (the FINAL build of the round; `launches_r02.csv` is the mid-round list) (`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`, two "
        "full B=32 x 4 s forwards, the warm one summarised), `prof_*_r02_raw.csv` / `_details.txt` (`ncu --set full --import-source on`, "
-       "one launch each, `scripts/ncu_capture_r02.sh`), `layers_eventtimed_r02.txt` (CUDA events around every call site, no profiler), "
-       "`tt_role_probes_r02.log`, `lstm2_phase_clocks_r02.log`, `mma_probe_r02.log`, `bench_*_r02a.json`.  Numbers under ncu are cold-cache and "
+       "one launch each: `scripts/ncu_capture_r02f.sh` for the `_r02f` captures of the final build, `scripts/ncu_capture_r02.sh` for the mid-round "
+       "`_r02` ones), `layers_eventtimed_r02f.txt` (CUDA events around every call site of the final build, no profiler; `_r02.txt` mid-round), "
+       "`tc_chunk_trace_before_r02.log` / `tc_chunk_trace_r02f.log` (per-chunk clock64 timeline of one conv_tc CTA before / after the issue-loop "
+       "rework), `tma_probe_r02.log`, `tt_role_probes_r02.log`, `lstm2_phase_clocks_r02.log`, `mma_probe_r02.log`, `bench_1gpu_r02e/f.json`, "
+       "`bench_2gpu_r02e.json`, `bench_vq_r02e.json`, `bench_trainfwd_r02.json`, `gpu_tests_r02g.log`.  Numbers under ncu are cold-cache and "
        "serialised (and the quantizer front runs on a second stream in production): compare SHARES; bench numbers come from bench.py only.\n",
        f"\n## Launch list (one forward, {len(launch)} launches, {tot:.1f} ms under ncu)\n\n| kernel | launches | ms | share | DRAM read+write GB |\n|---|---|---|---|---|"]
 for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
