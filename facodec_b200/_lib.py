@@ -56,6 +56,9 @@ def load():
         "fac_stream_encode": ([vp, i32, fp, i32, fp, vp], i32),
         "fac_stream_decode": ([vp, i32, fp, i32, fp, vp], i32),
         "fac_stream_end": ([vp, i32], i32),
+        "fac_spectral_loss": ([vp, fp, fp, i32, i32, i32, i32, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), fp, fp,
+                               _c.c_float, _c.c_float, _c.c_float, _c.c_float, fp, vp], i32),
+        "fac_l1_loss": ([vp, fp, fp, _c.c_longlong, fp, vp], i32),
         "fac_add3": ([vp, fp, fp, fp, _c.c_longlong, fp, vp], i32),
         "fac_reconstruction_loss": ([vp, fp, fp, i32, i32, fp, fp, vp], i32),
         "fac_rvq_forward": ([vp, i32, fp, i32, i32, i32, fp, i64p, fp, vp], i32),
@@ -93,7 +96,7 @@ def load():
 
 EXPORTED = ["fac_abi_version", "fac_create", "fac_destroy", "fac_last_error", "fac_load_tensor", "fac_finalize",
             "fac_encode", "fac_encode_frames", "fac_quantize", "fac_decode", "fac_codec_forward",
-            "fac_codec_forward_host", "fac_redecode", "fac_redecoder_decode", "fac_voice_convert", "fac_dataset_mel", "fac_reconstruction_loss", "fac_head_begin", "fac_head_tensor", "fac_head_finalize", "fac_head_forward", "fac_add3", "fac_stream_begin", "fac_stream_encode", "fac_stream_decode", "fac_stream_end", "fac_rvq_create", "fac_rvq_destroy", "fac_rvq_forward", "fac_alias_free_act",
+            "fac_codec_forward_host", "fac_redecode", "fac_redecoder_decode", "fac_voice_convert", "fac_dataset_mel", "fac_reconstruction_loss", "fac_spectral_loss", "fac_l1_loss", "fac_head_begin", "fac_head_tensor", "fac_head_finalize", "fac_head_forward", "fac_add3", "fac_stream_begin", "fac_stream_encode", "fac_stream_decode", "fac_stream_end", "fac_rvq_create", "fac_rvq_destroy", "fac_rvq_forward", "fac_alias_free_act",
             "fac_debug_conv", "fac_debug_conv_tc", "fac_debug_resunit", "fac_debug_tc_phase_clocks", "fac_debug_tc_producer_clocks", "fac_debug_tc_trace", "fac_debug_lstm_pack", "fac_debug_convtr_pack", "fac_debug_pad_map", "fac_debug_tc_plan", "fac_debug_tc_pack", "fac_debug_lstm_phase_clocks", "fac_set_option", "fac_debug_slstm", "fac_debug_tap", "fac_profile_enable", "fac_profile_reset", "fac_profile_get", "fac_profile_dump",
             "fac_workspace_bytes", "fac_last_launch_count"]
 

@@ -116,6 +116,9 @@ struct fac_handle {
     // and the 64-band HTK filterbank [n_fft/2 + 1][64]; built on first use
     struct LossScale { ConvW dft; size_t fb = 0; int s = 0, nfft = 0, nb = 0, ld = 0; };
     float* loss_arena = nullptr; LossScale loss_scale[6];
+    // dac/nn/loss.py MultiScaleSTFTLoss / MelSpectrogramLoss: one cached configuration (rebuilt when the arguments change)
+    struct SpecScale { ConvW dft; size_t fb = 0; int w = 0, nb = 0, ld = 0, n_out = 0; bool mel = false; };
+    float* spec_arena = nullptr; std::vector<SpecScale> spec_scales; std::vector<double> spec_key;
     // optional per-kernel-family timing (fac_profile_*): CUDA events around every launch
     bool profiling = false;
     struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
@@ -1269,6 +1272,7 @@ int fac_destroy(fac_handle* h) {
     if (h->aa_filter) cudaFree(h->aa_filter);
     if (h->mel16_arena) cudaFree(h->mel16_arena);
     if (h->loss_arena) cudaFree(h->loss_arena);
+    if (h->spec_arena) cudaFree(h->spec_arena);
     for (float* p : h->rvq_arenas) if (p) cudaFree(p);
     for (auto* hs : h->heads) { if (hs->arena) cudaFree(hs->arena); delete hs; }
     for (auto* ss : h->streams) { for (void* p : ss->all) if (p) cudaFree(p); delete ss; }
@@ -1764,6 +1768,142 @@ int fac_reconstruction_loss(fac_handle* h, const float* x, const float* gx, int 
     });
     h->warena = saved;
     return rc;
+}
+
+// ---- dac/nn/loss.py:142-327 MultiScaleSTFTLoss / MelSpectrogramLoss, :11-47 L1Loss (forward values) ----
+// The reference computes them on audiotools AudioSignal objects (AudioSignal.stft / .magnitude / .mel_spectrogram; the
+// package is not vendored: SURVEY.md 8c, parity unpinned).  Restated semantics: torch.stft(n_fft = window_length, hop =
+// window_length / 4, periodic Hann window (scipy.signal.get_window("hann")), centre = True, reflect padding), magnitude =
+// |stft|; mel_spectrogram = magnitude @ librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax)^T (Slaney scale, Slaney area
+// normalisation).  loss = sum over scales of log_weight * L1(log10(clamp(v, eps)^pow)) + mag_weight * L1(v).
+namespace {
+void slaney_mel_fb(double sr, int n_fft, int n_mels, double fmin, double fmax, std::vector<float>& fb /* [nb][n_mels] */) {
+    const int nb = n_fft / 2 + 1;
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    auto hz2mel = [&](double f) { return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp; };
+    auto mel2hz = [&](double m) { return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m; };
+    std::vector<double> mf(n_mels + 2);
+    const double m0 = hz2mel(fmin), m1 = hz2mel(fmax);
+    for (int i = 0; i < n_mels + 2; ++i) mf[i] = mel2hz(m0 + (m1 - m0) * i / (n_mels + 1));
+    fb.assign((size_t)nb * n_mels, 0.f);
+    for (int k = 0; k < nb; ++k) {
+        const double f = (sr / 2.0) * k / (nb - 1);
+        for (int m = 0; m < n_mels; ++m) {
+            const double lower = (f - mf[m]) / (mf[m + 1] - mf[m]), upper = (mf[m + 2] - f) / (mf[m + 2] - mf[m + 1]);
+            const double w = std::max(0.0, std::min(lower, upper)) * (2.0 / (mf[m + 2] - mf[m]));
+            fb[(size_t)k * n_mels + m] = (float)w;
+        }
+    }
+}
+}  // namespace
+
+int fac_spectral_loss(fac_handle* h, const float* x, const float* y, int B, int T, int sample_rate, int n_scales, const int* window_lengths,
+                      const int* n_mels, const float* mel_fmin, const float* mel_fmax, float clamp_eps, float mag_weight, float log_weight,
+                      float pw, float* loss, void* stream) {
+    if (!h || !x || !y || !loss || !window_lengths || B <= 0 || T <= 0 || n_scales < 1 || n_scales > 16 || sample_rate <= 0) return FAC_ERR_INVALID;
+    if (B > 32767) { h->err = "fac_spectral_loss: B > 32767"; return FAC_ERR_UNSUPPORTED; }
+    std::vector<double> key{(double)sample_rate, (double)n_scales};
+    for (int i = 0; i < n_scales; ++i) {
+        const int w = window_lengths[i];
+        if (w < 16 || w > 4096 || (w & (w - 1)) != 0) { h->err = "fac_spectral_loss: window lengths must be powers of two in [16, 4096]"; return FAC_ERR_UNSUPPORTED; }
+        if (T <= w / 2) { h->err = "fac_spectral_loss: signals must be longer than half the largest window (reflect padding), as torch.stft"; return FAC_ERR_INVALID; }
+        const int nm = n_mels ? n_mels[i] : 0;
+        if (nm < 0 || nm > 1024) return FAC_ERR_INVALID;
+        const double f0 = (n_mels && mel_fmin) ? mel_fmin[i] : 0.0;
+        const double f1 = (n_mels && mel_fmax && mel_fmax[i] > 0.f) ? mel_fmax[i] : sample_rate / 2.0;
+        key.push_back(w); key.push_back(nm); key.push_back(f0); key.push_back(f1);
+    }
+    cudaSetDevice(h->device);
+    if (!h->spec_arena || h->spec_key != key) {
+        fac_handle tmp;
+        tmp.device = h->device;
+        std::vector<fac_handle::SpecScale> scales(n_scales);
+        try {
+            for (int i = 0; i < n_scales; ++i) {
+                fac_handle::SpecScale& L = scales[i];
+                L.w = window_lengths[i]; L.nb = L.w / 2 + 1; L.ld = (2 * L.nb + 127) / 128 * 128;
+                const int nm = (int)key[2 + 4 * i + 1];
+                L.mel = nm > 0; L.n_out = L.mel ? nm : L.nb;
+                ConvW& d = L.dft;
+                d = ConvW();
+                d.Cin = L.w; d.Cout = L.ld; d.K = 1; d.ldw = L.ld;
+                d.w = pack_alloc(&tmp, (size_t)L.w * L.ld);
+                d.b = pack_alloc(&tmp, L.ld);
+                for (int n = 0; n < L.w; ++n) {
+                    const double wv = 0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)L.w);      // periodic Hann
+                    for (int k = 0; k < L.nb; ++k) {
+                        const long long ph = ((long long)k * n) % L.w;
+                        const double ang = 2.0 * M_PI * (double)ph / (double)L.w;
+                        tmp.pack[d.w + (size_t)n * L.ld + 2 * k] = (float)(wv * std::cos(ang));
+                        tmp.pack[d.w + (size_t)n * L.ld + 2 * k + 1] = (float)(-wv * std::sin(ang));
+                    }
+                }
+                attach_tc(&tmp, d, 1, true);
+                if (L.mel) {
+                    std::vector<float> fb;
+                    slaney_mel_fb((double)sample_rate, L.w, nm, key[2 + 4 * i + 2], key[2 + 4 * i + 3], fb);
+                    L.fb = pack_alloc(&tmp, fb.size());
+                    for (size_t j = 0; j < fb.size(); ++j) tmp.pack[L.fb + j] = fb[j];
+                }
+            }
+        } catch (const PackError& e) { h->err = e.msg; return FAC_ERR_STATE; }
+        if (h->spec_arena) { cudaDeviceSynchronize(); cudaFree(h->spec_arena); h->spec_arena = nullptr; }
+        cudaError_t e = cudaMalloc(&h->spec_arena, (tmp.pack.size() + 64) * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->spec_arena, tmp.pack.data(), tmp.pack.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); cudaGetLastError(); h->spec_arena = nullptr; return FAC_ERR_CUDA; }
+        h->spec_scales = scales;
+        h->spec_key = key;
+    }
+    float* saved = h->warena;
+    h->warena = h->spec_arena;
+    int rc = two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        double* sums = c.alloc<double>(2 * 16 + 2);
+        const size_t mark = c.off;
+        size_t peak = c.off;
+        c.vq_critical = true;                                        // fp32-faithful DFT (promoted tensor-core class)
+        for (int i = 0; i < n_scales; ++i) {
+            c.off = mark;
+            const fac_handle::SpecScale& L = c.h->spec_scales[i];
+            const int hop = L.w / 4, F = T / hop + 1;
+            const size_t rows = (size_t)2 * B * F;
+            float* frames = c.alloc<float>(rows * L.w);
+            float* spec = c.alloc<float>(rows * L.ld);
+            float* tr = c.alloc<float>((size_t)B * F * 2);
+            if (!c.dry) {
+                c.check(launch_stft_frames(x, frames, B, T, F, hop, L.w, L.w / 2, c.st), "spec.frames");
+                c.check(launch_stft_frames(y, frames + (size_t)B * F * L.w, B, T, F, hop, L.w, L.w / 2, c.st), "spec.frames");
+            }
+            run_conv(c, L.dft, frames, spec, 1, (int)rows, (int)rows, ConvOpts(), "spec.dft");
+            if (!c.dry) {
+                const double inv = 1.0 / ((double)B * F * L.n_out);
+                c.check(launch_spec_loss_terms(spec, L.ld, L.nb, L.mel ? c.W(L.fb) : nullptr, L.n_out, B, F, clamp_eps, pw, tr, c.st), "spec.terms");
+                c.check(launch_strided_sum(tr, (long long)B * F, 2, inv, sums + 2 * i, c.st), "spec.mag");
+                c.check(launch_strided_sum(tr + 1, (long long)B * F, 2, inv, sums + 2 * i + 1, c.st), "spec.log");
+            }
+            if (c.off > peak) peak = c.off;
+        }
+        c.vq_critical = false;
+        c.off = peak;
+        if (!c.dry) c.check(launch_spec_loss_combine(sums, n_scales, mag_weight, log_weight, loss, c.st), "spec.combine");
+    });
+    h->warena = saved;
+    return rc;
+}
+
+// dac/nn/loss.py:11-47 L1Loss on the waveforms: mean |x - y| over n floats
+int fac_l1_loss(fac_handle* h, const float* x, const float* y, long long n, float* loss, void* stream) {
+    if (!h || !x || !y || !loss || n <= 0) return FAC_ERR_INVALID;
+    cudaSetDevice(h->device);
+    return two_pass(h, (cudaStream_t)stream, [&](Ctx& c) {
+        double* sum = c.alloc<double>(2);
+        const int nblk = 1024;
+        float* part = c.alloc<float>(nblk);
+        if (!c.dry) {
+            c.check(launch_absdiff_partial(x, y, n, part, nblk, c.st), "l1.partial");
+            c.check(launch_strided_sum(part, nblk, 1, 1.0 / (double)n, sum, c.st), "l1.sum");
+            c.check(launch_spec_loss_combine(sum, 0, 0.f, 0.f, loss, c.st), "l1.out");
+        }
+    });
 }
 
 // ---- predictor heads (training-side in the reference, forward only here) ----

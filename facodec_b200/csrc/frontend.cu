@@ -206,4 +206,98 @@ cudaError_t launch_add3(const float* a, const float* b, const float* c, long lon
     return cudaGetLastError();
 }
 
+// ---- dac/nn/loss.py:142-327 MultiScaleSTFTLoss / MelSpectrogramLoss: the per-frame tail of one scale ----------------
+// spec as for mel_loss_terms_kernel (rows of x, then rows of y).  Per (frame, utterance): magnitudes |X|, |Y| (audiotools
+// AudioSignal.magnitude = abs(stft)); with a filterbank fb [nb][n_out] the mel spectra mag @ fb (AudioSignal.mel_spectrogram),
+// else n_out = nb and the values are the magnitudes themselves.  terms[(b*F+f)*2] = sum_o |vx - vy| (the mag_weight term),
+// terms[.. + 1] = sum_o |log10(clamp(vx, eps)^pw) - log10(clamp(vy, eps)^pw)| (the log_weight term); both are means over
+// (utterance, o, frame) in the reference (nn.L1Loss), formed by the caller's fixed-order fp64 sums.
+__global__ void __launch_bounds__(128) spec_loss_terms_kernel(const float* __restrict__ spec, int ldspec, int nb, const float* __restrict__ fb,
+                                                              int n_out, int B, int F, float eps, float pw, float* __restrict__ terms) {
+    extern __shared__ float mg[];                    // [2][nb] magnitudes
+    __shared__ float red[4][2];
+    const int b = blockIdx.y, f = blockIdx.x, tid = threadIdx.x;
+    const float* rx = spec + ((size_t)b * F + f) * ldspec;
+    const float* ry = spec + ((size_t)(B + b) * F + f) * ldspec;
+    for (int i = tid; i < nb; i += blockDim.x) {
+        const float2 cx = *reinterpret_cast<const float2*>(rx + 2 * i), cy = *reinterpret_cast<const float2*>(ry + 2 * i);
+        mg[i] = sqrtf(cx.x * cx.x + cx.y * cx.y);
+        mg[nb + i] = sqrtf(cy.x * cy.x + cy.y * cy.y);
+    }
+    __syncthreads();
+    float d1 = 0.f, d2 = 0.f;
+    for (int o = tid; o < n_out; o += blockDim.x) {
+        float vx, vy;
+        if (fb) {
+            float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+            int i = 0;
+            for (; i + 1 < nb; i += 2) {
+                const float w0 = __ldg(fb + (size_t)i * n_out + o), w1 = __ldg(fb + (size_t)(i + 1) * n_out + o);
+                a0 = fmaf(mg[i], w0, a0); a1 = fmaf(mg[i + 1], w1, a1);
+                c0 = fmaf(mg[nb + i], w0, c0); c1 = fmaf(mg[nb + i + 1], w1, c1);
+            }
+            if (i < nb) { const float w0 = __ldg(fb + (size_t)i * n_out + o); a0 = fmaf(mg[i], w0, a0); c0 = fmaf(mg[nb + i], w0, c0); }
+            vx = a0 + a1; vy = c0 + c1;
+        } else {
+            vx = mg[o]; vy = mg[nb + o];
+        }
+        d1 += fabsf(vx - vy);
+        float lx = fmaxf(vx, eps), ly = fmaxf(vy, eps);
+        if (pw == 2.0f) { lx *= lx; ly *= ly; }
+        else if (pw != 1.0f) { lx = powf(lx, pw); ly = powf(ly, pw); }
+        d2 += fabsf(log10f(lx) - log10f(ly));
+    }
+    d1 = warp_sum(d1); d2 = warp_sum(d2);
+    if ((tid & 31) == 0) { red[tid >> 5][0] = d1; red[tid >> 5][1] = d2; }
+    __syncthreads();
+    if (tid == 0) {
+        terms[((size_t)b * F + f) * 2] = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+        terms[((size_t)b * F + f) * 2 + 1] = (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]);
+    }
+}
+cudaError_t launch_spec_loss_terms(const float* spec, int ldspec, int nb, const float* fb, int n_out, int B, int F, float eps, float pw,
+                                   float* terms, cudaStream_t st) {
+    if (B <= 0 || F <= 0) return cudaSuccess;
+    if (B > 65535) return cudaErrorInvalidValue;
+    spec_loss_terms_kernel<<<dim3(F, B), 128, (size_t)2 * nb * sizeof(float), st>>>(spec, ldspec, nb, fb, n_out, B, F, eps, pw, terms);
+    return cudaGetLastError();
+}
+
+// sum |a - b| over [n]: per-block fp64 partials (fixed partition); strided_sum over the partials gives the L1 loss
+__global__ void __launch_bounds__(256) absdiff_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                                              float* __restrict__ part) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        acc += fabs((double)a[i] - (double)b[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = (float)sh[0];
+}
+cudaError_t launch_absdiff_partial(const float* a, const float* b, long long n, float* part, int nblocks, cudaStream_t st) {
+    absdiff_partial_kernel<<<nblocks, 256, 0, st>>>(a, b, n, part);
+    return cudaGetLastError();
+}
+
+// loss = sum over scales of (log_weight * v[2i+1] + mag_weight * v[2i]) accumulated in fp32 in the reference's order
+// (dac/nn/loss.py:217-226: the log term first); n = 0: loss = (float)v[0] (L1Loss)
+__global__ void spec_loss_combine_kernel(const double* __restrict__ v, int n, float mag_weight, float log_weight, float* __restrict__ loss) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (n == 0) { loss[0] = (float)v[0]; return; }
+    float L = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        L += log_weight * (float)v[2 * i + 1];
+        L += mag_weight * (float)v[2 * i];
+    }
+    loss[0] = L;
+}
+cudaError_t launch_spec_loss_combine(const double* v, int n, float mag_weight, float log_weight, float* loss, cudaStream_t st) {
+    spec_loss_combine_kernel<<<1, 32, 0, st>>>(v, n, mag_weight, log_weight, loss);
+    return cudaGetLastError();
+}
+
 }  // namespace fac

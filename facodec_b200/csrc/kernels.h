@@ -173,6 +173,11 @@ cudaError_t launch_mel_loss_terms(const float* spec, int ldspec, int nb, const f
                                   float* terms /*[B*F][2]*/, cudaStream_t st);
 cudaError_t launch_strided_sum(const float* in, long long n, int stride, double scale, double* out, cudaStream_t st);
 cudaError_t launch_sqdiff_partial(const float* a, const float* b, long long n, float* part, int nblocks, cudaStream_t st);
+// dac/nn/loss.py:142-327 spectral losses (frontend.cu)
+cudaError_t launch_spec_loss_terms(const float* spec, int ldspec, int nb, const float* fb /*[nb][n_out] or null*/, int n_out, int B, int F,
+                                   float eps, float pw, float* terms /*[B*F][2]*/, cudaStream_t st);
+cudaError_t launch_absdiff_partial(const float* a, const float* b, long long n, float* part, int nblocks, cudaStream_t st);
+cudaError_t launch_spec_loss_combine(const double* v, int n, float mag_weight, float log_weight, float* loss, cudaStream_t st);
 cudaError_t launch_add3(const float* a, const float* b, const float* c /* or null */, long long n, float* out, cudaStream_t st);
 cudaError_t launch_loss_combine(const double* v13, float* loss, float* terms, cudaStream_t st);
 cudaError_t launch_transpose(const float* in, float* out, int B, int R, int C, cudaStream_t st);  // [B][R][C]->[B][C][R]

@@ -148,6 +148,18 @@ int fac_dataset_mel(fac_handle* h, const float* wave, int B, int T, float* mel, 
  * x, gx [B,T] (device, T > 1024).  loss: 1 float (device).  terms: NULL or 13 floats (device): mse, then (l1, l2) per scale. */
 int fac_reconstruction_loss(fac_handle* h, const float* x, const float* gx, int B, int T, float* loss, float* terms, void* stream);
 
+/* dac/nn/loss.py:142-327 MultiScaleSTFTLoss (n_mels = NULL) / MelSpectrogramLoss and :11-47 L1Loss, forward values.  The
+ * reference evaluates them on audiotools AudioSignal objects; audiotools / librosa are not vendored (parity
+ * UNPINNED), so their published semantics are restated: torch.stft(n_fft = window_length, hop = window_length/4, periodic Hann,
+ * centre = True, reflect), magnitude = |stft|, mel = magnitude @ librosa.filters.mel(sample_rate, n_fft, n_mels, fmin, fmax)^T
+ * (Slaney scale + area normalisation); loss = sum over scales of log_weight * mean|log10(clamp(v,eps)^pow) differences| +
+ * mag_weight * mean|v differences|.  x, y [B,T] (device).  window_lengths: powers of two in [16, 4096]; mel_fmax[i] <= 0 means
+ * sample_rate / 2.  loss: 1 float (device).  The (sample_rate, scales) configuration is cached on the handle. */
+int fac_spectral_loss(fac_handle* h, const float* x, const float* y, int B, int T, int sample_rate, int n_scales,
+                      const int* window_lengths, const int* n_mels, const float* mel_fmin, const float* mel_fmax, float clamp_eps,
+                      float mag_weight, float log_weight, float pow, float* loss, void* stream);
+int fac_l1_loss(fac_handle* h, const float* x, const float* y, long long n, float* loss, void* stream);
+
 /* Predictor heads: modules/quantize.py:106-125 CNNLSTM(indim, outdim, head, global_pred) forward (3 ResidualUnits of
  * alias-free SnakeBeta + weight-normed Conv1d k7 (dilation 1, 2, 3, zero padding) / k1, a final alias-free SnakeBeta,
  * `nheads` nn.Linear layers; mean over time first when global_pred).  fac_head_begin returns a head id; feed the reference

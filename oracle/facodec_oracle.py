@@ -613,3 +613,60 @@ def reconstruction_loss(x, G_x, eps=1e-7, return_terms=False):
         L = L + (l1_loss + alpha * l2_loss)
         terms += [l1_loss, l2_loss]
     return (L, torch.stack(terms)) if return_terms else L
+
+
+# ----------------------------------------------------------------------------
+# dac/nn/loss.py:11-47, :142-327 L1Loss / MultiScaleSTFTLoss / MelSpectrogramLoss
+# PARITY UNPINNED: the reference evaluates them on audiotools.AudioSignal (AudioSignal.stft / .magnitude / .mel_spectrogram),
+# and neither audiotools nor librosa is installed or vendored.  Their published semantics are restated here;
+# the Slaney filterbank is cross-checked against torchaudio's own Slaney implementation (tests/test_oracle.py).
+# ----------------------------------------------------------------------------
+def librosa_mel_filters(sr, n_fft, n_mels, fmin=0.0, fmax=None):
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) with its defaults (htk=False: Slaney mel scale; norm='slaney':
+    each triangle divided by half its width in Hz), evaluated in float64 and rounded to float32.  Returns [n_mels, 1 + n_fft // 2]."""
+    import numpy as np
+    fmax = sr / 2.0 if fmax is None else float(fmax)
+    f_sp, min_log_hz = 200.0 / 3.0, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+    hz2mel = lambda f: np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-30) / min_log_hz) / logstep, f / f_sp)
+    mel2hz = lambda m: np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+    fftfreqs = np.linspace(0.0, sr / 2.0, 1 + n_fft // 2)
+    mel_f = mel2hz(np.linspace(hz2mel(np.float64(fmin)), hz2mel(np.float64(fmax)), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    w = np.zeros((n_mels, 1 + n_fft // 2))
+    for i in range(n_mels):
+        w[i] = np.maximum(0.0, np.minimum(-ramps[i] / fdiff[i], ramps[i + 2] / fdiff[i + 1]))
+    w *= (2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels]))[:, None]
+    return torch.from_numpy(w.astype(np.float32))
+
+
+def _audiotools_magnitude(x, w):
+    """AudioSignal(x).stft(window_length=w, hop_length=w // 4) -> .magnitude, [B, C, w // 2 + 1, frames]."""
+    shape = x.shape
+    win = torch.hann_window(w, periodic=True, device=x.device)          # scipy.signal.get_window("hann", w) (fftbins=True)
+    st = torch.stft(x.reshape(-1, shape[-1]), n_fft=w, hop_length=w // 4, window=win, return_complex=True, center=True)
+    return st.abs().reshape(shape[:-1] + st.shape[-2:])
+
+
+def multiscale_stft_loss(x, y, window_lengths=(2048, 512), clamp_eps=1e-5, mag_weight=1.0, log_weight=1.0, pow=2.0):
+    """dac/nn/loss.py:201-231 with loss_fn = nn.L1Loss()."""
+    loss = 0.0
+    for w in window_lengths:
+        mx, my = _audiotools_magnitude(x, w), _audiotools_magnitude(y, w)
+        loss = loss + log_weight * F.l1_loss(mx.clamp(clamp_eps).pow(pow).log10(), my.clamp(clamp_eps).pow(pow).log10())
+        loss = loss + mag_weight * F.l1_loss(mx, my)
+    return loss
+
+
+def mel_spectrogram_loss(x, y, sample_rate=24000, n_mels=(150, 80), window_lengths=(2048, 512), clamp_eps=1e-5, mag_weight=1.0,
+                         log_weight=1.0, pow=2.0, mel_fmin=(0.0, 0.0), mel_fmax=(None, None)):
+    """dac/nn/loss.py:297-327 with loss_fn = nn.L1Loss(); mel_spectrogram = (magnitude.transpose(2, -1) @ mel_basis.T).transpose(-1, 2)."""
+    loss = 0.0
+    for nm, f0, f1, w in zip(n_mels, mel_fmin, mel_fmax, window_lengths):
+        basis = librosa_mel_filters(sample_rate, w, nm, f0, f1).to(x.device)
+        mel = lambda m: (m.transpose(2, -1) @ basis.T).transpose(-1, 2)
+        mx, my = mel(_audiotools_magnitude(x, w)), mel(_audiotools_magnitude(y, w))
+        loss = loss + log_weight * F.l1_loss(mx.clamp(clamp_eps).pow(pow).log10(), my.clamp(clamp_eps).pow(pow).log10())
+        loss = loss + mag_weight * F.l1_loss(mx, my)
+    return loss

@@ -55,3 +55,32 @@ def test_reconstruction_loss_error_paths(built_lib):
         losses.reconstruction_loss(x.cuda()[..., :1024], G_x.cuda()[..., :1024])   # not longer than the reflect padding
     with pytest.raises(fb.FacError):
         losses.reconstruction_loss(x.cuda(), G_x.cuda()[..., :1500])
+
+
+@pytest.mark.parametrize("B,T", [(4, 96000), (2, 5001)])
+def test_dac_spectral_losses_vs_oracle(B, T, built_lib):
+    """dac/nn/loss.py criteria as train.py:153-164 builds them -- MultiScaleSTFTLoss(), MelSpectrogramLoss(7 scales, pow = 1,
+    mag_weight = 0), L1Loss() -- against the oracle's restatement (parity unpinned against audiotools itself: not vendored)."""
+    import warnings
+    warnings.simplefilter("ignore")
+    from facodec_b200 import losses, synth
+    from oracle import facodec_oracle as O
+    x, y = synth.synth_loss_pair(B, T, seed=9)
+    xd, yd = x.cuda(), y.cuda()
+    stft = losses.MultiScaleSTFTLoss()
+    mel = losses.MelSpectrogramLoss(n_mels=[5, 10, 20, 40, 80, 160, 320], window_lengths=[32, 64, 128, 256, 512, 1024, 2048],
+                                    mel_fmin=[0] * 7, mel_fmax=[None] * 7, pow=1.0, mag_weight=0.0, clamp_eps=1e-5)
+    mel2 = losses.MelSpectrogramLoss()                                   # defaults: [150, 80] over [2048, 512], pow 2, both terms
+    l1 = losses.L1Loss()
+    got = [stft(xd, yd), mel(xd, yd), mel2(xd, yd), l1(xd, yd), stft(xd, yd)]
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = [O.multiscale_stft_loss(x, y),
+               O.mel_spectrogram_loss(x, y, 24000, n_mels=[5, 10, 20, 40, 80, 160, 320], window_lengths=[32, 64, 128, 256, 512, 1024, 2048],
+                                      mel_fmin=[0] * 7, mel_fmax=[None] * 7, pow=1.0, mag_weight=0.0),
+               O.mel_spectrogram_loss(x, y, 24000),
+               (x - y).abs().mean(),
+               O.multiscale_stft_loss(x, y)]
+    for name, a, b in zip(("stft", "mel_train", "mel_default", "l1", "stft_again"), got, ref):
+        assert a.dim() == 0
+        assert abs(float(a) - float(b)) <= 5e-5 * abs(float(b)), (name, float(a), float(b))

@@ -329,3 +329,31 @@ def test_fa_predictors_match_imported_reference(timbre_norm):
                 assert float((a[k] - b[k]).abs().max()) <= 5e-7 * max(1.0, float(a[k].abs().max())), k
             else:
                 assert torch.equal(a[k], b[k]), k
+
+
+def test_slaney_mel_filterbank_against_torchaudio():
+    """The restated librosa.filters.mel (Slaney scale + area norm; librosa itself is not installed) against torchaudio's
+    independent Slaney implementation, for the geometries train.py:155-163 uses."""
+    import torchaudio
+    for w, nm in ((32, 5), (64, 10), (256, 40), (512, 80), (2048, 320), (2048, 150)):
+        mine = O.librosa_mel_filters(24000, w, nm, 0.0, None)
+        ref = torchaudio.functional.melscale_fbanks(w // 2 + 1, 0.0, 12000.0, nm, 24000, norm="slaney", mel_scale="slaney").T
+        assert mine.shape == ref.shape == (nm, w // 2 + 1)
+        assert float((mine - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max())), (w, nm)
+
+
+def test_dac_spectral_losses_restatement_properties():
+    """dac/nn/loss.py MultiScaleSTFTLoss / MelSpectrogramLoss restatements (parity unpinned: audiotools absent): zero for
+    identical signals, the magnitude path equals a direct torch.stft evaluation, train.py's mel configuration runs."""
+    from facodec_b200 import synth
+    x, y = synth.synth_loss_pair(2, 3000, seed=3)
+    assert float(O.multiscale_stft_loss(x, x)) == 0.0
+    assert float(O.mel_spectrogram_loss(x, x)) == 0.0
+    st = torch.stft(x[:, 0], 512, hop_length=128, window=torch.hann_window(512), return_complex=True)
+    sy = torch.stft(y[:, 0], 512, hop_length=128, window=torch.hann_window(512), return_complex=True)
+    direct = (st.abs() - sy.abs()).abs().mean()
+    got = O.multiscale_stft_loss(x, y, window_lengths=(512,), log_weight=0.0)
+    assert abs(float(got) - float(direct)) <= 1e-6 * float(direct)
+    L = O.mel_spectrogram_loss(x, y, 24000, n_mels=[5, 10, 20, 40, 80, 160, 320], window_lengths=[32, 64, 128, 256, 512, 1024, 2048],
+                               mel_fmin=[0] * 7, mel_fmax=[None] * 7, pow=1.0, mag_weight=0.0)
+    assert torch.isfinite(L) and float(L) > 0
