@@ -14,17 +14,22 @@
 // experimental fp16 hi + 2^11-scaled fp16 lo upstream (conv_tcp_kernel<true>).
 //
 // Two kernels share the operand pipeline:
-//   conv_tc_kernel<FUSED, BF16>  accumulates in TMEM only (decoder, short K loops); 10 warps, planned for two CTAs per
-//                                SM wherever the tile fits 256 TMEM columns / 112 KB; FUSED = a whole ResidualUnit.
+//   conv_tc_kernel<FUSED, BF16, G1F16, NW, NG>  accumulates in TMEM only (decoder, short K loops); 2 control warps + NW = 8
+//                                worker warps, planned for two CTAs per SM wherever the tile fits 256 TMEM columns / 112 KB,
+//                                or NW = 16 when a tile owns the SM; NG = 2 producer groups on alternate chunks where a
+//                                group covers a chunk in <= 5 pieces per thread; FUSED = a whole ResidualUnit; G1F16 = the
+//                                layer's own GEMM in ONE fp16 pass (k = 7 convs downstream of the VQ).
 //   conv_tcp_kernel<F16>         promotes TMEM accumulators into fp32 registers every <= 48 MMAs (everything upstream of
 //                                the VQ with a long K loop); 20 warps re-allocated with setmaxnreg, persistent.
 // Roles in conv_tc_kernel (the promoted kernel splits the last group into producers and accumulators):
 //   warp 0    : weight producer -- one elected lane streams pre-arranged [tap][16 ci] weight
 //               blobs (hi|lo, already in the UMMA K-major core-matrix layout) with 1-D bulk
-//               TMA copies (cp.async.bulk, UBLKCP) into a 4-deep mbarrier ring.
+//               TMA copies (cp.async.bulk, UBLKCP) into an mbarrier ring of 2-4 slots; a slot holds every tap of
+//               `cps` consecutive chunks (tc_conv_plan).
 //   warp 1    : TMEM allocator + MMA issuer -- converged warp, every tcgen05.mma / tcgen05.commit predicated by
-//               elect.sync inside its asm block; descriptors assembled from warp-uniform 16-byte-unit offsets.
-//   warps 2-9 : activation producers, then epilogue.  Per 16-channel chunk they load the UNION
+//               elect.sync inside its asm block; slot > chunk > tap loop nest with the taps unrolled and every invariant
+//               pinned in a register (issue_taps): ~27 instructions per tap instead of ~440 cycles of dependent scalar work.
+//   warps 2.. : activation producers, then epilogue.  Per 16-channel chunk they load the UNION
 //               of the rows all taps need (128*MT + (K-1)*dil rows) once from HBM with 16-byte
 //               loads (reflect/zero padding = index map, no padded copy), apply Snake, split into
 //               hi/lo and store them in a no-swizzle K-major layout whose row pitch is a uniform
