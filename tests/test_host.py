@@ -479,3 +479,45 @@ def test_fa_predictors_state_dict_surface():
     assert torch.equal(m.state_dict()["rev_f0_predictor.1.heads.0.weight"], sd2["rev_f0_predictor.1.heads.0.weight"])
     with pytest.raises(fb.FacError):
         m([torch.zeros(1, 32, 5)] * 3, torch.zeros(1, 32))
+
+
+def test_tile_plans_of_every_codec_layer_fit_the_sm(built_lib):
+    """Host logic (no GPU): the tensor-core tile plans of every conv geometry of config.yml's encoder (transposed kernel, incl.
+    PAIR mode) and decoder (conv_tc bf16 / fused units) at the benchmark lengths stay inside one SM: <= 225 KB of dynamic
+    shared memory (<= 112 KB when two CTAs share the SM), <= 512 TMEM columns, time tiles of 16..256 steps."""
+    import ctypes
+    from facodec_b200 import _lib
+    L = _lib.load()
+    out = (ctypes.c_int * 8)()
+    enc = []                                    # (Cin, Cout, K, dil, stride, Tout)
+    T, c = 96000, 64
+    for s in (2, 5, 5, 6):
+        for d in (1, 3, 9):
+            enc += [(c, c, 7, d, 1, T), (c, c, 1, 1, 1, T)]
+        enc.append((c, 2 * c, 2 * s, 1, s, T // s))
+        T //= s
+        c *= 2
+    enc += [(1024, 4096, 1, 1, 1, 320 * 32), (1024, 1024, 3, 1, 1, 320)]
+    for (ci, co, k, d, st, to) in enc:
+        assert L.fac_debug_tc_plan(ci, co, k, d, st, to, 6, 0, out) == 0, (ci, co, k)
+        chans, nt, smem, cols = out[0], out[1], out[5], out[4]
+        assert chans in (128, 256) and 16 <= nt <= 256 and nt % 16 == 0 and (chans == 128 or nt <= 128)
+        assert smem <= 225 * 1024 and cols <= 512
+    dec = []
+    T, c = 320, 1536
+    for s in (6, 5, 5, 2):
+        dec.append((c, (c // 2) * s, 2, 1, 1, T, 2))                 # transposed conv as a 2-tap conv with s * Cout channels
+        T *= s
+        c //= 2
+        for d in (1, 3, 9):
+            if c <= 256:
+                dec.append((c, c, 7, d, 1, T, 4))                    # fused ResidualUnit
+            else:
+                dec += [(c, c, 7, d, 1, T, 2), (c, c, 1, 1, 1, T, 2)]
+    dec += [(1024, 1536, 7, 1, 1, 320, 2), (1536, 6144, 1, 1, 1, 320 * 32, 2)]
+    for (ci, co, k, d, st, to, mode) in dec:
+        for occ2 in (0, 256):
+            assert L.fac_debug_tc_plan(ci, co, k, d, st, to, mode, occ2, out) == 0, (ci, co, k, mode)
+            n, mt, smem, cols = out[0], out[1], out[5], out[4]
+            assert co % n == 0 and mt in (1, 2, 4) and cols <= 512 and (mode == 4 or mt * n <= cols) and (mode != 4 or 2 * mt * n <= cols)
+            assert smem <= (112 * 1024 if (occ2 and cols <= 256) else 225 * 1024)
