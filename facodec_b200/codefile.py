@@ -30,35 +30,34 @@ class DACFile:
     padding: bool
     dac_version: str
 
+    # the order of the metadata entries is part of the byte format (np.save pickles the dict)
+    _META_ORDER = ("input_db", "original_length", "sample_rate", "chunk_length", "channels", "padding", "dac_version")
+
+    def _metadata(self):
+        db = self.input_db.detach().cpu().numpy() if torch.is_tensor(self.input_db) else np.asarray(self.input_db)
+        values = dict(input_db=db.astype(np.float32), original_length=self.original_length, sample_rate=self.sample_rate,
+                      chunk_length=self.chunk_length, channels=self.channels, padding=self.padding,
+                      dac_version=SUPPORTED_VERSIONS[-1])
+        return {k: values[k] for k in self._META_ORDER}
+
     def save(self, path):
-        codes = self.codes.detach().cpu().numpy()
-        if codes.size and (codes.min() < 0 or codes.max() > np.iinfo(np.uint16).max):
+        """Writes ``<path>.dac`` (the suffix is forced, as the reference does) and returns the path."""
+        grid = self.codes.detach().cpu().numpy()
+        if grid.size and (grid.min() < 0 or grid.max() > np.iinfo(np.uint16).max):
             raise ValueError("codes do not fit the format's uint16")
-        input_db = self.input_db.detach().cpu().numpy() if torch.is_tensor(self.input_db) else np.asarray(self.input_db)
-        artifacts = {
-            "codes": codes.astype(np.uint16),
-            "metadata": {
-                "input_db": input_db.astype(np.float32),
-                "original_length": self.original_length,
-                "sample_rate": self.sample_rate,
-                "chunk_length": self.chunk_length,
-                "channels": self.channels,
-                "padding": self.padding,
-                "dac_version": SUPPORTED_VERSIONS[-1],
-            },
-        }
-        path = Path(path).with_suffix(".dac")
-        with open(path, "wb") as f:
-            np.save(f, artifacts)
-        return path
+        target = Path(path).with_suffix(".dac")
+        with open(target, "wb") as fh:
+            np.save(fh, {"codes": grid.astype(np.uint16), "metadata": self._metadata()})
+        return target
 
     @classmethod
     def load(cls, path):
-        artifacts = np.load(path, allow_pickle=True)[()]
-        codes = torch.from_numpy(artifacts["codes"].astype(int))
-        if artifacts["metadata"].get("dac_version", None) not in SUPPORTED_VERSIONS:
+        """Reads a ``.dac`` file written here or by the reference; refuses unknown format versions."""
+        blob = np.load(path, allow_pickle=True)[()]
+        meta = dict(blob["metadata"])
+        if meta.get("dac_version", None) not in SUPPORTED_VERSIONS:
             raise RuntimeError(f"Given file {path} can't be loaded with this version of descript-audio-codec.")
-        return cls(codes=codes, **artifacts["metadata"])
+        return cls(codes=torch.from_numpy(blob["codes"].astype(int)), **meta)
 
 
 def pack_codes(codes: Sequence[torch.Tensor]) -> torch.Tensor:
